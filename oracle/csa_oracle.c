@@ -1,0 +1,522 @@
+/*
+ * csa_oracle.c -- CPU restatement of fjdf/CSA's `./CSA R` rotation path.
+ * TEST INFRASTRUCTURE ONLY (see csa_oracle.h).  Parity status: PINNED against the
+ * compiled reference (oracle/validate_against_ref.py) and tests/golden/.
+ *
+ * How the reference's suffix-tree vocabulary maps onto a suffix array:
+ *
+ *   tree                                            | here
+ *   ------------------------------------------------+---------------------------------------
+ *   compact trie of every rotation of every         | all (k,p) sorted by the cyclic string
+ *   sequence  gencycsuffixtrees.c:418-545            | s_k[p..] (prefix doubling) + LCP
+ *   internal node                                    | LCP interval [lb,rb], depth = its lcp
+ *   node->fromseqs == allseqsmask  (:34)             | every sequence occurs in SA[lb..rb]
+ *   collectNodes (csamsa.c:64): deepest all-seq      | all-seq interval with no all-seq child
+ *   removeSuffixNodes (csamsa.c:80)                  | drop X when some x.X is common to all
+ *   removeNonUniqueNodes (csamsa.c:283)              | keep intervals of exactly m suffixes
+ *   order of blockslist: insertSortedItem            | depth desc, then LATER-visited first;
+ *   (nodeslinkedlists.c:36) over a DFS whose child   | DFS order == order of first occurrence
+ *   order is creation order (addBranch :193)         | in sequence 0 (see dfs_rank_seq0)
+ *   collectNodeChains (csamsa.c:135)                 | chain_blocks() below, literal
+ *   sortList (nodeslinkedlists.c:59)                 | stable sort by size, descending
+ */
+#include "csa_oracle.h"
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned long long u64;
+
+/* gencycsuffixtrees.c:283/297: every letter that is not A/C/G/T is the same 5th letter */
+static inline unsigned char code_of(char c) {
+    switch (c) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': return 3;
+    default: return 4;
+    }
+}
+
+typedef struct gtext {
+    int m;
+    int N;               /* total number of rotations = sum of lengths */
+    int nmax, nmin;
+    int *off;            /* m+1 */
+    const int *n;        /* lengths */
+    unsigned char *code; /* N */
+    int *seqof;          /* N */
+} gtext;
+
+static inline int cyc(const gtext *t, int g, int h) {
+    int k = t->seqof[g];
+    int p = g - t->off[k];
+    long long q = ((long long)p + h) % t->n[k];
+    return t->off[k] + (int)q;
+}
+
+static int gtext_init(gtext *t, int m, const char *const *texts, const int *sizes) {
+    long long tot = 0;
+    t->m = m;
+    t->n = sizes;
+    t->off = (int *)malloc(sizeof(int) * (m + 1));
+    t->nmax = 0;
+    t->nmin = INT_MAX;
+    for (int k = 0; k < m; k++) {
+        t->off[k] = (int)tot;
+        tot += sizes[k];
+        if (sizes[k] > t->nmax) t->nmax = sizes[k];
+        if (sizes[k] < t->nmin) t->nmin = sizes[k];
+    }
+    if (tot >= INT_MAX) return -1;
+    t->off[m] = (int)tot;
+    t->N = (int)tot;
+    t->code = (unsigned char *)malloc(t->N ? t->N : 1);
+    t->seqof = (int *)malloc(sizeof(int) * (t->N ? t->N : 1));
+    for (int k = 0; k < m; k++)
+        for (int p = 0; p < sizes[k]; p++) {
+            t->code[t->off[k] + p] = code_of(texts[k][p]);
+            t->seqof[t->off[k] + p] = k;
+        }
+    return 0;
+}
+
+static void gtext_free(gtext *t) {
+    free(t->off);
+    free(t->code);
+    free(t->seqof);
+}
+
+/* stable counting sort of idx[0..N) by key[idx[i]] in [0,K) */
+static void counting_sort(const int *in, int *out, int N, const int *key, int K, int *cnt) {
+    memset(cnt, 0, sizeof(int) * (size_t)(K + 1));
+    for (int i = 0; i < N; i++) cnt[key[in[i]] + 1]++;
+    for (int i = 0; i < K; i++) cnt[i + 1] += cnt[i];
+    for (int i = 0; i < N; i++) out[cnt[key[in[i]]]++] = in[i];
+}
+
+/* Generalized cyclic suffix array: every rotation (k,p) sorted by the periodic string
+ * s_k[p], s_k[p+1], ...  Replaces Ukkonen's construction at gencycsuffixtrees.c:418. */
+static void build_gsa(const gtext *t, int *sa, int *isa) {
+    int N = t->N;
+    int *rank = (int *)calloc(N + 1, sizeof(int));
+    int *key2 = (int *)malloc(sizeof(int) * N);
+    int *tmp = (int *)calloc(N + 1, sizeof(int));
+    int *cnt = (int *)malloc(sizeof(int) * ((size_t)N + 8));
+    for (int g = 0; g < N; g++) {
+        rank[g] = t->code[g];
+        tmp[g] = g;
+    }
+    counting_sort(tmp, sa, N, rank, 5, cnt);
+    /* densify initial ranks */
+    {
+        int r = -1, prev = -1;
+        for (int i = 0; i < N; i++) {
+            int c = t->code[sa[i]];
+            if (c != prev) { r++; prev = c; }
+            key2[sa[i]] = r;
+        }
+        memcpy(rank, key2, sizeof(int) * N);
+    }
+    int nranks = 0;
+    for (int g = 0; g < N; g++) if (rank[g] + 1 > nranks) nranks = rank[g] + 1;
+    for (long long h = 1; nranks < N && h < 2LL * t->nmax; h *= 2) {
+        for (int g = 0; g < N; g++) key2[g] = rank[cyc(t, g, (int)(h % INT_MAX))];
+        counting_sort(sa, tmp, N, key2, nranks, cnt);
+        counting_sort(tmp, sa, N, rank, nranks, cnt);
+        int r = 0;
+        tmp[sa[0]] = 0;
+        for (int i = 1; i < N; i++) {
+            if (rank[sa[i]] != rank[sa[i - 1]] || key2[sa[i]] != key2[sa[i - 1]]) r++;
+            tmp[sa[i]] = r;
+        }
+        memcpy(rank, tmp, sizeof(int) * N);
+        nranks = r + 1;
+    }
+    for (int i = 0; i < N; i++) isa[sa[i]] = i;
+    free(rank); free(key2); free(tmp); free(cnt);
+}
+
+/* lcp[i] = length of the common prefix of rotations sa[i-1], sa[i], never more than either
+ * rotation's length (a tree path ends at depth textsize, gencycsuffixtrees.c:500). */
+static void build_lcp(const gtext *t, const int *sa, const int *isa, int *lcp) {
+    for (int k = 0; k < t->m; k++) {
+        int h = 0;
+        for (int p = 0; p < t->n[k]; p++) {
+            int g = t->off[k] + p;
+            int r = isa[g];
+            if (r == 0) { lcp[0] = 0; h = 0; continue; }
+            int b = sa[r - 1];
+            int cap = t->n[k] < t->n[t->seqof[b]] ? t->n[k] : t->n[t->seqof[b]];
+            if (h > cap) h = cap;
+            while (h < cap && t->code[cyc(t, g, h)] == t->code[cyc(t, b, h)]) h++;
+            lcp[r] = h;
+            if (h > 0) h--;
+        }
+    }
+}
+
+/* ---- interval scan: collectNodes / removeSuffixNodes / removeNonUniqueNodes ---------- */
+
+typedef struct blk {
+    int depth, lb;
+    int dfs;     /* DFS visit index of the block (first-occurrence order in sequence 0) */
+    int *pos;    /* m positions */
+} blk;
+
+typedef struct scan_out {
+    int count_collected, count_suffixfree, count_unique;
+    int degenerate;
+    blk *blocks;
+    int nblocks, cap;
+} scan_out;
+
+#define NMASK 6 /* [0] sequences present, [1..5] sequences with an occurrence preceded by letter x */
+
+static void scan_intervals(const gtext *t, const int *sa, const int *lcp, scan_out *o) {
+    int N = t->N, m = t->m, W = (m + 63) / 64;
+    size_t ew = (size_t)NMASK * W;
+    int cap = 1024, top = 0;
+    int *s_lcp = (int *)malloc(sizeof(int) * cap), *s_lb = (int *)malloc(sizeof(int) * cap);
+    char *s_allchild = (char *)malloc(cap);
+    u64 *s_mask = (u64 *)malloc(sizeof(u64) * ew * cap);
+    u64 *carry = (u64 *)malloc(sizeof(u64) * ew);
+    u64 *full = (u64 *)calloc(W, sizeof(u64));
+    for (int k = 0; k < m; k++) full[k >> 6] |= 1ULL << (k & 63);
+    memset(o, 0, sizeof(*o));
+    /* root */
+    s_lcp[0] = 0; s_lb[0] = 0; s_allchild[0] = 0;
+    memset(s_mask, 0, sizeof(u64) * ew);
+    top = 1;
+    for (int i = 1; i <= N; i++) {
+        int cur = (i < N) ? lcp[i] : -1;
+        int lb = i - 1;
+        /* leaf i-1 (one rotation): gencycsuffixtrees.c:160 newNode fromseqs=masks[currentseq] */
+        int g = sa[i - 1], k = t->seqof[g];
+        int x = t->code[cyc(t, g, t->n[k] - 1)];
+        int carry_allseq = 0;
+        memset(carry, 0, sizeof(u64) * ew);
+        carry[k >> 6] |= 1ULL << (k & 63);
+        carry[(size_t)(1 + x) * W + (k >> 6)] |= 1ULL << (k & 63);
+        while (top > 0 && cur < s_lcp[top - 1]) {
+            u64 *tm = s_mask + ew * (top - 1);
+            for (size_t w = 0; w < ew; w++) tm[w] |= carry[w];
+            if (carry_allseq) s_allchild[top - 1] = 1;
+            /* node complete: [s_lb, i-1], depth s_lcp */
+            int allseq = 1;
+            for (int w = 0; w < W; w++) if (tm[w] != full[w]) allseq = 0;
+            if (allseq && !s_allchild[top - 1]) { /* csamsa.c:64 collectNodes */
+                int depth = s_lcp[top - 1], nlb = s_lb[top - 1], size = i - nlb;
+                o->count_collected++;
+                if (depth >= t->nmin) o->degenerate = 1;
+                /* csamsa.c:80 removeSuffixNodes: X goes when x.X is common for some x */
+                int sfx = 0;
+                for (int c = 0; c < 5 && !sfx; c++) {
+                    int all = 1;
+                    for (int w = 0; w < W; w++) if (tm[(size_t)(1 + c) * W + w] != full[w]) all = 0;
+                    if (all) sfx = 1;
+                }
+                if (depth == 0) sfx = 0; /* csamsa.c:85: list holding only the root is left alone */
+                if (!sfx) {
+                    o->count_suffixfree++;
+                    if (size == m) { /* csamsa.c:283 removeNonUniqueNodes */
+                        if (o->nblocks == o->cap) {
+                            o->cap = o->cap ? o->cap * 2 : 256;
+                            o->blocks = (blk *)realloc(o->blocks, sizeof(blk) * o->cap);
+                        }
+                        blk *b = &o->blocks[o->nblocks++];
+                        b->depth = depth; b->lb = nlb; b->dfs = 0;
+                        b->pos = (int *)malloc(sizeof(int) * m);
+                        for (int j = nlb; j < nlb + m; j++) {
+                            int gg = sa[j], kk = t->seqof[gg];
+                            b->pos[kk] = gg - t->off[kk];
+                        }
+                        o->count_unique++;
+                    }
+                }
+            }
+            memcpy(carry, tm, sizeof(u64) * ew);
+            carry_allseq = allseq;
+            lb = s_lb[top - 1];
+            top--;
+        }
+        if (top == 0) break; /* root popped (i==N) */
+        if (cur > s_lcp[top - 1]) {
+            if (top == cap) {
+                cap *= 2;
+                s_lcp = (int *)realloc(s_lcp, sizeof(int) * cap);
+                s_lb = (int *)realloc(s_lb, sizeof(int) * cap);
+                s_allchild = (char *)realloc(s_allchild, cap);
+                s_mask = (u64 *)realloc(s_mask, sizeof(u64) * ew * cap);
+            }
+            s_lcp[top] = cur; s_lb[top] = lb; s_allchild[top] = (char)carry_allseq;
+            memcpy(s_mask + ew * top, carry, sizeof(u64) * ew);
+            top++;
+        } else {
+            u64 *tm = s_mask + ew * (top - 1);
+            for (size_t w = 0; w < ew; w++) tm[w] |= carry[w];
+            if (carry_allseq) s_allchild[top - 1] = 1;
+        }
+    }
+    free(s_lcp); free(s_lb); free(s_allchild); free(s_mask); free(carry); free(full);
+}
+
+/* ---- DFS order of the reference's tree, restricted to what decides block order -------
+ * Children of a node are stored in creation order (gencycsuffixtrees.c:193 addBranch appends,
+ * :210 splitNode keeps the slot), and Ukkonen's phase ii creates the branch for string S.c when
+ * the first occurrence of S.c ends at ii.  Sequence 0 is inserted first and every ancestor of
+ * a block contains sequence 0, so two blocks are visited in the order of the first occurrence,
+ * in sequence 0, of the strings on which they diverge.  dfs_rank_seq0 numbers all rotations of
+ * sequence 0 in that visiting order. */
+static void dfs_rank_seq0(const gtext *t, const int *sa, const int *lcp, int *dfsrank /* n0 */) {
+    int n0 = t->n[0], N = t->N;
+    int *sa0 = (int *)malloc(sizeof(int) * n0), *lcp0 = (int *)malloc(sizeof(int) * n0);
+    int c = 0, run = INT_MAX;
+    for (int i = 0; i < N; i++) {
+        if (i > 0 && lcp[i] < run) run = lcp[i];
+        if (t->seqof[sa[i]] == 0) {
+            sa0[c] = sa[i] - t->off[0];
+            lcp0[c] = (c == 0) ? 0 : run;
+            c++;
+            run = INT_MAX;
+        }
+    }
+    /* explicit stack of [l,r] intervals */
+    int cap = 1024, top = 0;
+    int *st = (int *)malloc(sizeof(int) * 2 * cap);
+    int counter = 0;
+    st[0] = 0; st[1] = n0 - 1; top = 1;
+    int ccap = 64;
+    int *cl = (int *)malloc(sizeof(int) * ccap), *cr = (int *)malloc(sizeof(int) * ccap),
+        *cm = (int *)malloc(sizeof(int) * ccap);
+    while (top > 0) {
+        top--;
+        int l = st[2 * top], r = st[2 * top + 1];
+        if (l == r) { dfsrank[sa0[l]] = counter++; continue; }
+        int mn = INT_MAX;
+        for (int i = l + 1; i <= r; i++) if (lcp0[i] < mn) mn = lcp0[i];
+        int nc = 0, start = l;
+        for (int i = l + 1; i <= r + 1; i++) {
+            if (i == r + 1 || lcp0[i] == mn) {
+                if (nc == ccap) {
+                    ccap *= 2;
+                    cl = (int *)realloc(cl, sizeof(int) * ccap);
+                    cr = (int *)realloc(cr, sizeof(int) * ccap);
+                    cm = (int *)realloc(cm, sizeof(int) * ccap);
+                }
+                int mp = INT_MAX;
+                for (int j = start; j < i; j++) if (sa0[j] < mp) mp = sa0[j];
+                cl[nc] = start; cr[nc] = i - 1; cm[nc] = mp; nc++;
+                start = i;
+            }
+        }
+        /* insertion sort children by first occurrence, then push in reverse */
+        for (int a = 1; a < nc; a++) {
+            int tl = cl[a], tr = cr[a], tm = cm[a], b = a - 1;
+            while (b >= 0 && cm[b] > tm) { cl[b + 1] = cl[b]; cr[b + 1] = cr[b]; cm[b + 1] = cm[b]; b--; }
+            cl[b + 1] = tl; cr[b + 1] = tr; cm[b + 1] = tm;
+        }
+        while (top + nc > cap) { cap *= 2; st = (int *)realloc(st, sizeof(int) * 2 * cap); }
+        for (int a = nc - 1; a >= 0; a--) { st[2 * top] = cl[a]; st[2 * top + 1] = cr[a]; top++; }
+    }
+    free(sa0); free(lcp0); free(st); free(cl); free(cr); free(cm);
+}
+
+static int cmp_blocklist(const void *a, const void *b) {
+    const blk *x = (const blk *)a, *y = (const blk *)b;
+    if (x->depth != y->depth) return (x->depth > y->depth) ? -1 : 1; /* nodeslinkedlists.c:36 */
+    if (x->dfs != y->dfs) return (x->dfs > y->dfs) ? -1 : 1;         /* later visited goes first */
+    return 0;
+}
+
+/* ---- collectNodeChains (csamsa.c:135-279), literal ---------------------------------- */
+typedef struct ekey { int e, b; } ekey;
+static int cmp_ekey(const void *a, const void *b) {
+    const ekey *x = (const ekey *)a, *y = (const ekey *)b;
+    if (x->e != y->e) return x->e < y->e ? -1 : 1;
+    return x->b - y->b;
+}
+
+static int chain_blocks(const gtext *t, scan_out *o, int max_interval, csa_oracle_result *res) {
+    int B = o->nblocks, m = t->m;
+    blk *bl = o->blocks;
+    int *size = (int *)calloc(B, sizeof(int)), *total = (int *)calloc(B, sizeof(int));
+    int *interval = (int *)calloc(B, sizeof(int)), *next = (int *)malloc(sizeof(int) * B);
+    ekey *ek = (ekey *)malloc(sizeof(ekey) * B);
+    int mcs = B;
+    int hang = 0;
+    for (int b = 0; b < B; b++) next[b] = -1;
+    /* csamsa.c:147-183: walk every sequence through the tree; a block is noticed at the text
+     * index that follows it (e = position+depth, unrolled coordinates); the walk stops at
+     * textsize + start of the first block noticed (:168 n+=...). */
+    for (int k = 0; k < m; k++) {
+        int n = t->n[k];
+        for (int b = 0; b < B; b++) { ek[b].e = bl[b].pos[k] + bl[b].depth; ek[b].b = b; }
+        qsort(ek, B, sizeof(ekey), cmp_ekey);
+        if (B == 0 || ek[0].e >= n) continue;
+        int limit = n + bl[ek[0].b].pos[k];
+        int prev = -1;
+        for (int j = 0; j < B && ek[j].e < limit; j++) {
+            int b = ek[j].b;
+            if (prev != -1 && size[prev] == 0) {
+                if (next[prev] == -1) next[prev] = b;
+                else if (next[prev] != b) { next[prev] = -1; size[prev] = -1; }
+            }
+            prev = b;
+        }
+    }
+    /* csamsa.c:185-233 */
+    for (int b = 0; b < B && !hang; b++) {
+        if (total[b] == -1) continue;
+        size[b] = bl[b].depth;
+        int prev = b, cur = next[b];
+        long long guard = 0;
+        while (cur != -1) {
+            if (++guard > 4LL * B + 16) { hang = 1; break; }
+            int iv = INT_MAX;
+            for (int k = 0; k < m; k++) {
+                int count = 0;
+                if (bl[cur].pos[k] < bl[prev].pos[k]) count += t->n[k];
+                count += bl[cur].pos[k] - (bl[prev].pos[k] + bl[prev].depth);
+                if (count < iv) iv = count;
+            }
+            if (iv > max_interval) { next[prev] = -1; break; }
+            if (total[cur] > 0) {
+                size[b] += size[cur];
+                total[b] += total[cur];
+                interval[prev] = iv;
+                total[b] += iv;
+                size[cur] = bl[cur].depth;
+                total[cur] = -1;
+                mcs--;
+                break;
+            }
+            size[cur] = bl[cur].depth;
+            size[b] += size[cur];
+            interval[prev] = iv;
+            total[b] += iv;
+            total[cur] = -1;
+            mcs--;
+            prev = cur;
+            cur = next[cur];
+        }
+        total[b] += size[b];
+    }
+    /* nodeslinkedlists.c:59 sortList: repeatedly move the first strictly-largest to the front
+     * == stable sort by size, descending */
+    int *ord = (int *)malloc(sizeof(int) * (B ? B : 1)), *inv = (int *)malloc(sizeof(int) * (B ? B : 1));
+    for (int b = 0; b < B; b++) ord[b] = b;
+    for (int a = 1; a < B; a++) { /* insertion sort keeps ties in list order */
+        int v = ord[a], j = a - 1;
+        while (j >= 0 && size[ord[j]] < size[v]) { ord[j + 1] = ord[j]; j--; }
+        ord[j + 1] = v;
+    }
+    for (int i = 0; i < B; i++) inv[ord[i]] = i;
+    res->nblocks = B;
+    res->count_chains = mcs;
+    res->depth = (int *)malloc(sizeof(int) * (B ? B : 1));
+    res->size = (int *)malloc(sizeof(int) * (B ? B : 1));
+    res->totalsize = (int *)malloc(sizeof(int) * (B ? B : 1));
+    res->interval = (int *)malloc(sizeof(int) * (B ? B : 1));
+    res->next = (int *)malloc(sizeof(int) * (B ? B : 1));
+    res->positions = (int *)malloc(sizeof(int) * (size_t)(B ? B : 1) * m);
+    for (int i = 0; i < B; i++) {
+        int b = ord[i];
+        res->depth[i] = bl[b].depth;
+        res->size[i] = size[b];
+        res->totalsize[i] = total[b];
+        res->interval[i] = interval[b];
+        res->next[i] = next[b] == -1 ? -1 : inv[next[b]];
+        memcpy(res->positions + (size_t)i * m, bl[b].pos, sizeof(int) * m);
+    }
+    free(size); free(total); free(interval); free(next); free(ek); free(ord); free(inv);
+    return hang;
+}
+
+int csa_oracle_run(int m, const char *const *texts, const int *textsizes, int max_interval,
+                   csa_oracle_result *res) {
+    gtext t;
+    memset(res, 0, sizeof(*res));
+    res->m = m;
+    if (m < 2 || gtext_init(&t, m, texts, textsizes) != 0) { res->status = -1; return -1; }
+    int N = t.N;
+    int *sa = (int *)malloc(sizeof(int) * N), *isa = (int *)malloc(sizeof(int) * N);
+    int *lcp = (int *)malloc(sizeof(int) * N);
+    build_gsa(&t, sa, isa);
+    build_lcp(&t, sa, isa, lcp);
+    scan_out o;
+    scan_intervals(&t, sa, lcp, &o);
+    res->count_collected = o.count_collected;
+    res->count_suffixfree = o.count_suffixfree;
+    res->count_unique = o.count_unique;
+    if (o.degenerate) res->status = CSA_ORACLE_DEGENERATE;
+    else if (o.count_collected == 0) res->status = CSA_ORACLE_NO_COMMON;
+    else if (o.count_unique == 0) res->status = CSA_ORACLE_NO_UNIQUE;
+    if (res->status == 0) {
+        int *dfsrank = (int *)malloc(sizeof(int) * t.n[0]);
+        dfs_rank_seq0(&t, sa, lcp, dfsrank);
+        for (int b = 0; b < o.nblocks; b++) o.blocks[b].dfs = dfsrank[o.blocks[b].pos[0]];
+        free(dfsrank);
+        qsort(o.blocks, o.nblocks, sizeof(blk), cmp_blocklist);
+        if (chain_blocks(&t, &o, max_interval, res)) res->status = CSA_ORACLE_HANG;
+        else {
+            /* csamsa.c:311 getRotations: positions of the head of the sorted list */
+            res->rotations = (int *)malloc(sizeof(int) * m);
+            for (int k = 0; k < m; k++) res->rotations[k] = res->positions[k];
+        }
+    }
+    for (int b = 0; b < o.nblocks; b++) free(o.blocks[b].pos);
+    free(o.blocks);
+    free(sa); free(isa); free(lcp);
+    gtext_free(&t);
+    return res->status;
+}
+
+void csa_oracle_free(csa_oracle_result *r) {
+    free(r->depth); free(r->size); free(r->totalsize); free(r->interval); free(r->next);
+    free(r->positions); free(r->rotations);
+    memset(r, 0, sizeof(*r));
+}
+
+/* nodeslinkedlists.c:144 blockLabel.  The reference spells each block from the tree labels;
+ * every node on a block's path was created while sequence 0 was inserted, so the letters are
+ * those of sequence 0 at the block's (unique) position there. */
+char *csa_oracle_block_label(const csa_oracle_result *r, int b, const char *const *texts,
+                             const int *textsizes) {
+    size_t cap = 256, len = 0; /* len plays labelpos */
+    char *label = (char *)calloc(cap, 1);
+    int guard = 0;
+    for (int cur = b; cur != -1 && guard <= r->nblocks; cur = r->next[cur], guard++) {
+        int d = r->depth[cur], p0 = r->positions[(size_t)cur * r->m + 0];
+        while (len + d + 32 > cap) {
+            label = (char *)realloc(label, cap * 2);
+            memset(label + cap, 0, cap);
+            cap *= 2;
+        }
+        for (int i = 0; i < d; i++) label[len + i] = texts[0][(p0 + i) % textsizes[0]];
+        len += d;
+        int n = r->interval[cur];
+        if (n < 0) {
+            len = ((long long)len + n < 0) ? 0 : len + n;
+        } else if (n > 7) {
+            len += (size_t)sprintf(label + len, "-(%d)-", n);
+        } else {
+            for (int i = 0; i < n; i++) label[len++] = '-';
+        }
+    }
+    label[len] = '\0';
+    return label;
+}
+
+int csa_oracle_gsa(int m, const char *const *texts, const int *textsizes, int *sa_out,
+                   int *lcp_out) {
+    gtext t;
+    if (gtext_init(&t, m, texts, textsizes) != 0) return -1;
+    int *isa = (int *)malloc(sizeof(int) * t.N);
+    build_gsa(&t, sa_out, isa);
+    build_lcp(&t, sa_out, isa, lcp_out);
+    free(isa);
+    gtext_free(&t);
+    return 0;
+}
