@@ -1,0 +1,201 @@
+"""ctypes binding of libcsa_gpu.so (include/csa_gpu.h) -- the Python face of the C ABI.
+
+The product path is the CUDA library built by csa_b200/csrc/Makefile.  There is NO CPU
+fallback: if the library is missing, or no CUDA device is present, the calls raise.
+
+Reference interface mirrored (fjdf/CSA, source/csamsa.c): the globals `numberofseqs`, `texts`,
+`textsizes` go in; `rotations` (csamsa.h:12) and the sorted `blockslist` (csamsa.c:30) come out.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "csrc", "libcsa_gpu.so")
+
+SET_OK, SET_NO_COMMON, SET_NO_UNIQUE, SET_DEGENERATE, SET_NONTERMINATING = 0, 1, 2, 3, 4
+FLAG_STATS = 1
+INT_MAX = 2**31 - 1
+
+
+class CsaGpuError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"csa_gpu error {code}: {text}")
+        self.code = code
+
+
+class SetInfo(C.Structure):
+    _fields_ = [("status", C.c_int), ("nseqs", C.c_int), ("count_collected", C.c_int),
+                ("count_suffixfree", C.c_int), ("count_unique", C.c_int), ("count_chains", C.c_int),
+                ("nblocks", C.c_int), ("chain_is_cyclic", C.c_int), ("block_offset", C.c_longlong)]
+
+
+@dataclass
+class SetResult:
+    """what analyzeTree() (csamsa.c:324) leaves behind for one set"""
+    status: int
+    rotations: Optional[np.ndarray]       # csamsa.h:12, None unless status == SET_OK
+    count_collected: int
+    count_suffixfree: int
+    count_unique: int
+    count_chains: int
+    chain_is_cyclic: bool
+    # the sorted blockslist (nodeslinkedlists.h:4-13)
+    depth: np.ndarray = field(default=None)
+    size: np.ndarray = field(default=None)
+    totalsize: np.ndarray = field(default=None)
+    interval: np.ndarray = field(default=None)
+    next: np.ndarray = field(default=None)
+    positions: np.ndarray = field(default=None)   # nblocks x nseqs
+
+
+def _load(path):
+    if not os.path.exists(path):
+        raise CsaGpuError(-1, f"{path} not built (run `make -C csa_b200/csrc` or __graft_entry__.build()); "
+                              "there is no CPU fallback")
+    lib = C.CDLL(path)
+    vp, ip, i = C.c_void_p, C.POINTER(C.c_int), C.c_int
+    lib.csa_gpu_create.argtypes = [i, C.POINTER(vp)]
+    lib.csa_gpu_destroy.argtypes = [vp]
+    lib.csa_gpu_destroy.restype = None
+    lib.csa_gpu_last_error.restype = C.c_char_p
+    lib.csa_gpu_batch_upload_flat.argtypes = [vp, i, ip, C.c_char_p, C.POINTER(C.c_longlong)]
+    lib.csa_gpu_batch_run.argtypes = [vp, i, C.c_uint]
+    lib.csa_gpu_batch_download.argtypes = [vp, ip, C.POINTER(SetInfo)]
+    lib.csa_gpu_batch_num_blocks.argtypes = [vp]
+    lib.csa_gpu_batch_num_blocks.restype = C.c_longlong
+    lib.csa_gpu_batch_num_positions.argtypes = [vp]
+    lib.csa_gpu_batch_num_positions.restype = C.c_longlong
+    lib.csa_gpu_batch_blocks.argtypes = [vp, ip, ip, ip, ip, ip, ip]
+    lib.csa_gpu_batch_num_suffixes.argtypes = [vp]
+    lib.csa_gpu_batch_num_suffixes.restype = C.c_longlong
+    lib.csa_gpu_batch_suffix_array.argtypes = [vp, C.POINTER(C.c_uint), ip]
+    lib.csa_gpu_batch_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
+    return lib
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Batch:
+    """A batch of independent sequence sets laid out flat, ready for csa_gpu_batch_upload_flat."""
+
+    def __init__(self, sets: Sequence[Sequence[bytes]]):
+        self.nsets = len(sets)
+        self.set_start = np.zeros(self.nsets + 1, dtype=np.int32)
+        lens = []
+        for s, seqs in enumerate(sets):
+            self.set_start[s + 1] = self.set_start[s] + len(seqs)
+            lens.extend(len(x) for x in seqs)
+        self.nseqs = int(self.set_start[-1])
+        self.text_start = np.zeros(self.nseqs + 1, dtype=np.int64)
+        np.cumsum(np.asarray(lens, dtype=np.int64), out=self.text_start[1:])
+        self.text = b"".join(b"".join(seqs) for seqs in sets)
+        self.nbases = len(self.text)
+
+    @classmethod
+    def from_arrays(cls, text: bytes, text_start: np.ndarray, set_start: np.ndarray):
+        self = cls.__new__(cls)
+        self.text = text
+        self.text_start = np.ascontiguousarray(text_start, dtype=np.int64)
+        self.set_start = np.ascontiguousarray(set_start, dtype=np.int32)
+        self.nsets = len(self.set_start) - 1
+        self.nseqs = int(self.set_start[-1])
+        self.nbases = int(self.text_start[-1])
+        return self
+
+
+class RotationFinder:
+    """One context = one GPU + its buffers.  find_rotations() replaces
+    buildGeneralizedTree()+analyzeTree() (csamsa.c:599,610)."""
+
+    def __init__(self, device: int = 0, lib_path: str = DEFAULT_LIB):
+        self.lib = _load(lib_path)
+        self.ctx = C.c_void_p()
+        self._check(self.lib.csa_gpu_create(device, C.byref(self.ctx)))
+
+    def close(self):
+        if getattr(self, "ctx", None) and self.ctx.value:
+            self.lib.csa_gpu_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CsaGpuError(rc, self.lib.csa_gpu_last_error().decode(errors="replace"))
+
+    # ---- the three steps, separately (bench.py times run() alone and all three together) ----
+    def upload(self, batch: Batch):
+        self._batch = batch
+        self._check(self.lib.csa_gpu_batch_upload_flat(
+            self.ctx, batch.nsets, _ip(batch.set_start), batch.text,
+            batch.text_start.ctypes.data_as(C.POINTER(C.c_longlong))))
+
+    def run(self, max_interval: int = INT_MAX, flags: int = 0):
+        self._check(self.lib.csa_gpu_batch_run(self.ctx, max_interval, flags))
+
+    def download(self):
+        b = self._batch
+        rot = np.zeros(b.nseqs, dtype=np.int32)
+        info = (SetInfo * b.nsets)()
+        self._check(self.lib.csa_gpu_batch_download(self.ctx, _ip(rot), info))
+        return rot, info
+
+    def blocks(self):
+        nb = self.lib.csa_gpu_batch_num_blocks(self.ctx)
+        ne = self.lib.csa_gpu_batch_num_positions(self.ctx)
+        arrs = [np.zeros(max(nb, 1), dtype=np.int32) for _ in range(5)]
+        pos = np.zeros(max(ne, 1), dtype=np.int32)
+        self._check(self.lib.csa_gpu_batch_blocks(self.ctx, *[_ip(a) for a in arrs], _ip(pos)))
+        return [a[:nb] for a in arrs], pos[:ne]
+
+    def suffix_array(self):
+        n = self.lib.csa_gpu_batch_num_suffixes(self.ctx)
+        sa = np.zeros(n, dtype=np.uint32)
+        lcp = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.csa_gpu_batch_suffix_array(self.ctx, sa.ctypes.data_as(C.POINTER(C.c_uint)), _ip(lcp)))
+        return sa, lcp
+
+    def timings(self):
+        ms = (C.c_float * 6)()
+        launches = C.c_longlong()
+        self._check(self.lib.csa_gpu_batch_timings(self.ctx, ms, C.byref(launches)))
+        return list(ms), launches.value
+
+    # ---- whole calls ----
+    def find_rotations_batch(self, sets: Sequence[Sequence[bytes]], max_interval: int = INT_MAX,
+                             flags: int = 0, with_blocks: bool = True) -> List[SetResult]:
+        batch = sets if isinstance(sets, Batch) else Batch(sets)
+        self.upload(batch)
+        self.run(max_interval, flags)
+        rot, info = self.download()
+        out = []
+        if with_blocks:
+            (depth, size, total, interval, nxt), pos = self.blocks()
+        p = 0
+        for s in range(batch.nsets):
+            q0, q1 = int(batch.set_start[s]), int(batch.set_start[s + 1])
+            inf = info[s]
+            r = SetResult(inf.status, rot[q0:q1].copy() if inf.status == SET_OK else None,
+                          inf.count_collected, inf.count_suffixfree, inf.count_unique, inf.count_chains,
+                          bool(inf.chain_is_cyclic))
+            if with_blocks:
+                b0, nb, m = inf.block_offset, inf.nblocks, q1 - q0
+                r.depth, r.size, r.totalsize = depth[b0:b0 + nb], size[b0:b0 + nb], total[b0:b0 + nb]
+                r.interval, r.next = interval[b0:b0 + nb], nxt[b0:b0 + nb]
+                r.positions = pos[p:p + nb * m].reshape(nb, m)
+                p += nb * m
+            out.append(r)
+        return out
+
+    def find_rotations(self, seqs: Sequence[bytes], max_interval: int = INT_MAX, flags: int = 0) -> SetResult:
+        return self.find_rotations_batch([seqs], max_interval, flags)[0]

@@ -1,0 +1,541 @@
+// csa_gpu.cu -- C ABI of the B200 rotation finder (include/csa_gpu.h) and the host-side
+// sequencing of the kernels in pipeline.cuh.  Built by nvcc for sm_100a into libcsa_gpu.so.
+// (With -DCSA_EMU and g++ the same file gives tests/emu/libcsa_emu.so, a CPU single-stepper of
+// the kernel bodies used by the CPU-only tests; it is never part of the product.)
+#include "pipeline.cuh"
+#include "../../include/csa_gpu.h"
+#include <vector>
+#include <new>
+
+thread_local char g_csa_err[512] = "";
+
+#define TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+static inline int bits_for(u64 x) { // bits needed to hold values 0..x
+    int b = 1;
+    while (b < 64 && (x >> b)) b++;
+    return b;
+}
+
+struct StageTimer {
+#ifndef CSA_EMU
+    cudaEvent_t ev[8];
+    bool ok = false;
+#endif
+    float ms[6] = {0, 0, 0, 0, 0, 0};
+};
+
+struct csa_gpu_ctx {
+    int device = 0;
+    Exec ex{};
+    PrimScratch ps;
+    StageTimer tm;
+    // ---- batch description (host) ----
+    bool uploaded = false, ran = false;
+    int nsets = 0;
+    u32 M = 0, N = 0, N0 = 0, nmax = 0, n0max = 0, mmax = 0;
+    u64 TW = 0; // words of the doubled text
+    std::vector<u32> h_seq_off, h_seq_set, h_set_seq0, h_set_base0, h_set_nmin, h_z0;
+    std::vector<u64> h_dbl_off;
+    // ---- results (host mirrors of the small arrays) ----
+    std::vector<u32> h_set_nblocks, h_set_blk0, h_set_pos0, h_set_flags, h_set_nchains, h_set_cyclic;
+    u32 B = 0, E = 0;
+    long long launches = 0;
+    // ---- device ----
+    DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, dbl_off, z0;
+    DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, counter;
+    DevMem sa0, saidx0, leaf_set, lcp0, psv, nsv, pse, parent, nsize, minpos, val, up, val2, up2;
+    DevMem set_nblocks, set_blk0, set_pos0, set_flags, set_nchains, set_cyclic, firstmax;
+    DevMem blk_lb, blk_depth, blk_set, order, o_depth, o_set, o_pos, elem_blk, seghead, succ_lo, succ_hi;
+    DevMem next, gap, size, total, interval, inv, f_depth, f_size, f_total, f_interval, f_next, f_pos, rotations;
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+template <class T> static inline T *P(DevMem &m) { return (T *)m.p; }
+
+static BatchView view_of(csa_gpu_ctx *c) {
+    BatchView v;
+    v.nsets = c->nsets; v.M = c->M; v.N = c->N;
+    v.seq_off = P<u32>(c->seq_off); v.seq_set = P<u32>(c->seq_set);
+    v.set_seq0 = P<u32>(c->set_seq0); v.set_base0 = P<u32>(c->set_base0);
+    v.set_nmin = P<u32>(c->set_nmin); v.dbl_off = P<u64>(c->dbl_off);
+    v.seqof = P<u32>(c->seqof); v.code = P<unsigned char>(c->code);
+    v.p2 = P<u64>(c->p2); v.pm = P<u32>(c->pm);
+    return v;
+}
+
+// ---- lifetime ---------------------------------------------------------------------------------
+extern "C" int csa_gpu_abi_version(void) { return CSA_GPU_ABI_VERSION; }
+extern "C" const char *csa_gpu_last_error(void) { return g_csa_err; }
+
+extern "C" int csa_gpu_create(int device, csa_gpu_ctx **out) {
+    if (!out) CSA_FAIL(CSA_GPU_EINVAL, "csa_gpu_create: null ctx pointer");
+    *out = nullptr;
+#ifndef CSA_EMU
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        CSA_FAIL(CSA_GPU_ENODEV, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) CSA_FAIL(CSA_GPU_ENODEV, "device %d not present (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+#endif
+    csa_gpu_ctx *c = new (std::nothrow) csa_gpu_ctx();
+    if (!c) CSA_FAIL(CSA_GPU_ENOMEM, "out of host memory");
+    c->device = device;
+#ifndef CSA_EMU
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->ex.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreate(&c->tm.ev[i]));
+    c->tm.ok = true;
+#endif
+    *out = c;
+    return CSA_GPU_OK;
+}
+
+extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
+    if (!c) return;
+#ifndef CSA_EMU
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->ex.stream);
+#endif
+    DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
+                     &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
+                     &c->t2, &c->t3, &c->t4, &c->counter, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
+                     &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
+                     &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->blk_lb,
+                     &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
+                     &c->succ_lo, &c->succ_hi, &c->next, &c->gap, &c->size, &c->total, &c->interval, &c->inv, &c->f_depth,
+                     &c->f_size, &c->f_total, &c->f_interval, &c->f_next, &c->f_pos, &c->rotations};
+    for (DevMem *m : all) dev_free(*m);
+    for (int i = 0; i < 4; i++) dev_free(c->ps.block_sums[i]);
+    dev_free(c->ps.counts);
+#ifndef CSA_EMU
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->tm.ok) for (int i = 0; i < 8; i++) cudaEventDestroy(c->tm.ev[i]);
+    cudaStreamDestroy(c->ex.stream);
+#else
+    free(c->pinned);
+#endif
+    delete c;
+}
+
+static int pinned_reserve(csa_gpu_ctx *c, size_t bytes) {
+    if (c->pinned_bytes >= bytes) return 0;
+#ifndef CSA_EMU
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr; c->pinned_bytes = 0;
+    CUDA_TRY(cudaMallocHost(&c->pinned, bytes));
+#else
+    free(c->pinned);
+    c->pinned = malloc(bytes);
+    if (!c->pinned) CSA_FAIL(CSA_GPU_ENOMEM, "out of host memory");
+#endif
+    c->pinned_bytes = bytes;
+    return 0;
+}
+
+// ---- upload ----------------------------------------------------------------------------------------
+// describe the batch; `fill` copies the letters of sequence k into the staging buffer
+template <class Fill>
+static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const long long *lens, Fill fill) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (nsets < 1 || !set_start) CSA_FAIL(CSA_GPU_EINVAL, "batch needs at least one set");
+    if (set_start[0] != 0) CSA_FAIL(CSA_GPU_EINVAL, "set_start[0] must be 0");
+    c->uploaded = false; c->ran = false;
+    long long M = set_start[nsets];
+    if (M < 2 || M >= (1ll << 31)) CSA_FAIL(CSA_GPU_EINVAL, "bad number of sequences %lld", M);
+    c->nsets = nsets; c->M = (u32)M;
+    c->h_seq_off.assign(M + 1, 0); c->h_seq_set.assign(M, 0);
+    c->h_set_seq0.assign(nsets + 1, 0); c->h_set_base0.assign(nsets + 1, 0);
+    c->h_set_nmin.assign(nsets, 0); c->h_z0.assign(nsets + 1, 0);
+    c->h_dbl_off.assign(M + 1, 0);
+    u64 tot = 0, dbl = 0;
+    u32 nmax = 0, n0max = 0, mmax = 0, z = 0;
+    for (int s = 0; s < nsets; s++) {
+        int q0 = set_start[s], q1 = set_start[s + 1];
+        if (q1 - q0 < 2) CSA_FAIL(CSA_GPU_EINVAL, "set %d has %d sequences; the path needs at least 2 (csamsa.c:533)", s, q1 - q0);
+        c->h_set_seq0[s] = (u32)q0;
+        c->h_set_base0[s] = (u32)tot;
+        c->h_z0[s] = z;
+        if ((u32)(q1 - q0) > mmax) mmax = (u32)(q1 - q0);
+        u32 nmin = 0xFFFFFFFFu;
+        for (int k = q0; k < q1; k++) {
+            long long n = lens[k];
+            if (n < 1) CSA_FAIL(CSA_GPU_EINVAL, "sequence %d is empty", k);
+            if (tot + (u64)n >= (1ull << 31) - 64) CSA_FAIL(CSA_GPU_EINVAL, "batch larger than 2^31 bases; split it");
+            c->h_seq_off[k] = (u32)tot;
+            c->h_seq_set[k] = (u32)s;
+            c->h_dbl_off[k] = dbl;
+            tot += (u64)n;
+            dbl += ((2 * (u64)n + 64 + 31) / 32) * 32;
+            if ((u32)n > nmax) nmax = (u32)n;
+            if ((u32)n < nmin) nmin = (u32)n;
+            if (k == q0) { z += (u32)n; if ((u32)n > n0max) n0max = (u32)n; }
+        }
+        c->h_set_nmin[s] = nmin;
+    }
+    c->h_seq_off[M] = (u32)tot; c->h_dbl_off[M] = dbl;
+    c->h_set_seq0[nsets] = (u32)M; c->h_set_base0[nsets] = (u32)tot; c->h_z0[nsets] = z;
+    c->N = (u32)tot; c->N0 = z; c->nmax = nmax; c->n0max = n0max; c->mmax = mmax; c->TW = dbl / 32 + 2;
+    u32 N = c->N;
+    // stage the letters
+    TRY(pinned_reserve(c, (size_t)N));
+    for (long long k = 0; k < M; k++) fill((int)k, (char *)c->pinned + c->h_seq_off[k]);
+#ifndef CSA_EMU
+    CUDA_TRY(cudaSetDevice(c->device));
+#endif
+    Exec &ex = c->ex;
+    TRY(dev_alloc(c->raw, N)); TRY(dev_alloc(c->code, N)); TRY(dev_alloc(c->seqof, sizeof(u32) * (size_t)N));
+    TRY(dev_alloc(c->p2, sizeof(u64) * c->TW)); TRY(dev_alloc(c->pm, sizeof(u32) * c->TW));
+    TRY(dev_alloc(c->seq_off, sizeof(u32) * (M + 1))); TRY(dev_alloc(c->seq_set, sizeof(u32) * M));
+    TRY(dev_alloc(c->set_seq0, sizeof(u32) * (nsets + 1))); TRY(dev_alloc(c->set_base0, sizeof(u32) * (nsets + 1)));
+    TRY(dev_alloc(c->set_nmin, sizeof(u32) * nsets)); TRY(dev_alloc(c->dbl_off, sizeof(u64) * (M + 1)));
+    TRY(dev_alloc(c->z0, sizeof(u32) * (nsets + 1)));
+    TRY(h2d(ex, c->raw.p, c->pinned, N));
+    TRY(h2d(ex, c->seq_off.p, c->h_seq_off.data(), sizeof(u32) * (M + 1)));
+    TRY(h2d(ex, c->seq_set.p, c->h_seq_set.data(), sizeof(u32) * M));
+    TRY(h2d(ex, c->set_seq0.p, c->h_set_seq0.data(), sizeof(u32) * (nsets + 1)));
+    TRY(h2d(ex, c->set_base0.p, c->h_set_base0.data(), sizeof(u32) * (nsets + 1)));
+    TRY(h2d(ex, c->set_nmin.p, c->h_set_nmin.data(), sizeof(u32) * nsets));
+    TRY(h2d(ex, c->dbl_off.p, c->h_dbl_off.data(), sizeof(u64) * (M + 1)));
+    TRY(h2d(ex, c->z0.p, c->h_z0.data(), sizeof(u32) * (nsets + 1)));
+    TRY(exec_sync(ex)); // the host vectors and the staging buffer may change after we return
+    c->uploaded = true;
+    return CSA_GPU_OK;
+}
+
+extern "C" int csa_gpu_batch_upload(csa_gpu_ctx *c, int nsets, const int *set_start, const char *const *texts,
+                                    const int *textsizes) {
+    if (!texts || !textsizes || !set_start || nsets < 1) CSA_FAIL(CSA_GPU_EINVAL, "null argument");
+    long long M = set_start[nsets];
+    if (M < 0) CSA_FAIL(CSA_GPU_EINVAL, "bad set_start");
+    std::vector<long long> lens((size_t)M);
+    for (long long k = 0; k < M; k++) lens[k] = textsizes[k];
+    return upload_common(c, nsets, set_start, lens.data(),
+                         [&](int k, char *dst) { memcpy(dst, texts[k], (size_t)textsizes[k]); });
+}
+
+extern "C" int csa_gpu_batch_upload_flat(csa_gpu_ctx *c, int nsets, const int *set_start, const char *text,
+                                         const long long *text_start) {
+    if (!text || !text_start || !set_start || nsets < 1) CSA_FAIL(CSA_GPU_EINVAL, "null argument");
+    long long M = set_start[nsets];
+    if (M < 0) CSA_FAIL(CSA_GPU_EINVAL, "bad set_start");
+    std::vector<long long> lens((size_t)M);
+    for (long long k = 0; k < M; k++) lens[k] = text_start[k + 1] - text_start[k];
+    return upload_common(c, nsets, set_start, lens.data(),
+                         [&](int k, char *dst) { memcpy(dst, text + text_start[k], (size_t)(text_start[k + 1] - text_start[k])); });
+}
+
+// ---- run --------------------------------------------------------------------------------------------
+static inline void mark(csa_gpu_ctx *c, int i) {
+#ifndef CSA_EMU
+    cudaEventRecord(c->tm.ev[i], c->ex.stream);
+#else
+    (void)c; (void)i;
+#endif
+}
+
+static int read_u32(csa_gpu_ctx *c, const void *dev, u32 *out) { return d2h(c->ex, out, dev, sizeof(u32)); }
+
+// sort helper on the context's double buffers: on return keysA/valsA hold the sorted data
+static int sort_pairs(csa_gpu_ctx *c, long long n, int begin_bit, int end_bit) {
+    u64 *k = P<u64>(c->keysA), *ka = P<u64>(c->keysB);
+    u32 *v = P<u32>(c->valsA), *va = P<u32>(c->valsB);
+    TRY(radix_sort_pairs(c->ex, c->ps, k, v, ka, va, n, begin_bit, end_bit));
+    if (k != P<u64>(c->keysA)) { std::swap(c->keysA, c->keysB); std::swap(c->valsA, c->valsB); }
+    return 0;
+}
+
+static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
+    Exec &ex = c->ex;
+    u32 N = c->N;
+    u32 *head = P<u32>(c->t0), *rank = P<u32>(c->t1), *counter = P<u32>(c->counter);
+    { InitKeyArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA)}; launch_initkey(ex, N, a); }
+    TRY(sort_pairs(c, N, 0, CSA_K0_BITS + bits_for((u64)c->nsets - 1)));
+    int nbits = bits_for((u64)N - 1);
+    u64 sorted_len = CSA_K0;
+    for (;;) {
+        TRY(dev_zero(ex, counter, sizeof(u32)));
+        { FlagArgs a{P<u64>(c->keysA), head, counter}; launch_flag(ex, N, a); }
+        TRY((scan_u32<ScanMax, true>(ex, c->ps, head, head, N)));
+        { SetRankArgs a{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, a); }
+        u32 ngroups = 0;
+        TRY(read_u32(c, counter, &ngroups));
+        // gencycsuffixtrees.c compares rotations letter by letter; two periodic strings that agree on
+        // n_a+n_b letters agree for ever, so 2*nmax sorted letters settle every comparison
+        if (ngroups == N || sorted_len >= 2ull * c->nmax) break;
+        { Key2Args a{v, P<u32>(c->valsA), rank, P<u64>(c->keysA), (u32)sorted_len, nbits}; launch_key2(ex, N, a); }
+        TRY(sort_pairs(c, N, 0, 2 * nbits));
+        sorted_len *= 2;
+    }
+    TRY(d2d(ex, c->sa.p, c->valsA.p, sizeof(u32) * (size_t)N));
+    return 0;
+}
+
+static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
+    Exec &ex = c->ex;
+    u32 N = c->N;
+    int nsets = c->nsets;
+    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t2), *nxt = P<u32>(c->t0), *R = P<u32>(c->t1);
+    TRY(dev_zero(ex, c->firstmax.p, sizeof(u32) * nsets));
+    { ColorKeyArgs a{v, sa, P<u64>(c->keysA), P<u32>(c->valsA)}; launch_colorkey(ex, N, a); }
+    TRY(sort_pairs(c, N, 0, bits_for((u64)c->mmax - 1)));
+    { NextArgs a{v, sa, P<u32>(c->valsA), nxt, P<u32>(c->firstmax)}; launch_next(ex, N, a); }
+    { CoverArgs a{v, sa, nxt, P<u32>(c->firstmax), R}; launch_cover(ex, N, a); }
+    TRY((scan_u32<ScanMax, true>(ex, c->ps, R, R, N)));
+    u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3), *bidx = P<u32>(c->t4);
+    { BlockFindArgs a{v, sa, lcp, R, isblock, depth}; launch_blockfind(ex, N, a); }
+    { DegenArgs a{v, sa, lcp, R, P<u32>(c->set_flags)}; launch_degen(ex, N, a); }
+    TRY((scan_u32<ScanSum, false>(ex, c->ps, isblock, bidx, N)));
+    u32 last_idx = 0, last_flag = 0;
+    TRY(read_u32(c, bidx + (N - 1), &last_idx));
+    TRY(read_u32(c, isblock + (N - 1), &last_flag));
+    c->B = last_idx + last_flag;
+    u32 B = c->B;
+    TRY(dev_alloc(c->blk_lb, sizeof(u32) * (size_t)B)); TRY(dev_alloc(c->blk_depth, sizeof(u32) * (size_t)B));
+    TRY(dev_alloc(c->blk_set, sizeof(u32) * (size_t)B));
+    TRY(dev_zero(ex, c->set_nblocks.p, sizeof(u32) * nsets));
+    { BlockEmitArgs a{v, sa, isblock, bidx, depth, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set), P<u32>(c->set_nblocks)};
+      launch_blockemit(ex, N, a); }
+    c->h_set_nblocks.assign(nsets, 0);
+    TRY(d2h(ex, c->h_set_nblocks.data(), c->set_nblocks.p, sizeof(u32) * nsets));
+    c->h_set_blk0.assign(nsets + 1, 0); c->h_set_pos0.assign(nsets + 1, 0);
+    u64 e = 0;
+    u32 b = 0;
+    for (int s = 0; s < nsets; s++) {
+        c->h_set_blk0[s] = b; c->h_set_pos0[s] = (u32)e;
+        b += c->h_set_nblocks[s];
+        e += (u64)c->h_set_nblocks[s] * (c->h_set_seq0[s + 1] - c->h_set_seq0[s]);
+    }
+    c->h_set_blk0[nsets] = b; c->h_set_pos0[nsets] = (u32)e;
+    c->E = (u32)e;
+    TRY(h2d(ex, c->set_blk0.p, c->h_set_blk0.data(), sizeof(u32) * (nsets + 1)));
+    TRY(h2d(ex, c->set_pos0.p, c->h_set_pos0.data(), sizeof(u32) * (nsets + 1)));
+    return 0;
+}
+
+static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
+    Exec &ex = c->ex;
+    u32 N = c->N, N0 = c->N0, B = c->B;
+    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t2), *flag0 = P<u32>(c->t0), *idx0 = P<u32>(c->t3);
+    size_t n1 = sizeof(u32) * (size_t)N0, n2 = 2 * n1;
+    DevMem *one[] = {&c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv, &c->pse};
+    for (DevMem *m : one) TRY(dev_alloc(*m, n1));
+    DevMem *two[] = {&c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2};
+    for (DevMem *m : two) TRY(dev_alloc(*m, n2));
+    { Seq0FlagArgs a{v, sa, flag0}; launch_seq0flag(ex, N, a); }
+    TRY((scan_u32<ScanSum, false>(ex, c->ps, flag0, idx0, N)));
+    { Seq0EmitArgs a{v, sa, flag0, idx0, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0emit(ex, N, a); }
+    { Lcp0Args a{lcp, P<u32>(c->saidx0), P<u32>(c->leaf_set), P<u32>(c->z0), P<u32>(c->lcp0)}; launch_lcp0(ex, N0, a); }
+    Seq0View q{N0, P<u32>(c->z0), P<u32>(c->leaf_set), P<u32>(c->lcp0)};
+    { AnsvArgs a{q, P<u32>(c->psv), P<u32>(c->nsv), P<u32>(c->pse)}; launch_ansv(ex, N0, a); }
+    { TreeArgs a{q, P<u32>(c->psv), P<u32>(c->nsv), P<u32>(c->pse), P<u32>(c->sa0), P<u32>(c->parent), P<u32>(c->nsize), P<u32>(c->minpos)};
+      launch_tree(ex, 2ll * N0, a); }
+    { MinposArgs a{N0, P<u32>(c->parent), P<u32>(c->minpos)}; launch_minpos(ex, N0, a); }
+    { ChildKeyArgs a{N0, P<u32>(c->parent), P<u32>(c->minpos), P<u64>(c->keysA), P<u32>(c->valsA)}; launch_childkey(ex, 2ll * N0, a); }
+    TRY(sort_pairs(c, 2ll * N0, 0, 32 + bits_for(2ull * N0)));
+    { BeforeArgs a{P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->nsize), P<u32>(c->val), P<u32>(c->up), P<u32>(c->parent)};
+      launch_before(ex, 2ll * N0, a); }
+    int rounds = bits_for(c->n0max) + 1;
+    u32 *val = P<u32>(c->val), *up = P<u32>(c->up), *val2 = P<u32>(c->val2), *up2 = P<u32>(c->up2);
+    for (int r = 0; r < rounds; r++) {
+        JumpArgs a{val, up, val2, up2};
+        launch_jump(ex, 2ll * N0, a);
+        std::swap(val, val2); std::swap(up, up2);
+    }
+    // order the blocks: DFS number descending, then stably (set, depth descending)
+    BlockKeyArgs k{v, sa, idx0, flag0, val, N0, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set),
+                   P<u64>(c->keysA), P<u32>(c->valsA), 0};
+    launch_blockkey(ex, B, k);
+    TRY(sort_pairs(c, B, 0, 32));
+    k.keys = P<u64>(c->keysA); k.vals = P<u32>(c->valsA); k.pass = 1;
+    launch_blockkey(ex, B, k);
+    TRY(sort_pairs(c, B, 0, 32 + bits_for((u64)c->nsets - 1)));
+    TRY(dev_alloc(c->order, sizeof(u32) * (size_t)B));
+    TRY(d2d(ex, c->order.p, c->valsA.p, sizeof(u32) * (size_t)B));
+    return 0;
+}
+
+static int stage_chain(csa_gpu_ctx *c, const BatchView &v, int max_interval) {
+    Exec &ex = c->ex;
+    u32 B = c->B, E = c->E;
+    int nsets = c->nsets;
+    size_t nb = sizeof(u32) * (size_t)B, ne = sizeof(u32) * (size_t)E;
+    DevMem *perblock[] = {&c->o_depth, &c->o_set, &c->succ_lo, &c->succ_hi, &c->next, &c->gap, &c->size, &c->total,
+                          &c->interval, &c->inv, &c->f_depth, &c->f_size, &c->f_total, &c->f_interval, &c->f_next};
+    for (DevMem *m : perblock) TRY(dev_alloc(*m, nb));
+    DevMem *perelem[] = {&c->o_pos, &c->elem_blk, &c->seghead, &c->f_pos};
+    for (DevMem *m : perelem) TRY(dev_alloc(*m, ne));
+    u32 *sa = P<u32>(c->sa);
+    u32 *set_blk0 = P<u32>(c->set_blk0), *set_pos0 = P<u32>(c->set_pos0);
+    { BlockGatherArgs a{v, sa, P<u32>(c->order), P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set), set_blk0, set_pos0,
+                        P<u32>(c->o_depth), P<u32>(c->o_set), P<int>(c->o_pos)};
+      launch_blockgather(ex, B, a); }
+    { ElemBlkArgs a{v, P<u32>(c->o_set), set_blk0, set_pos0, P<u32>(c->elem_blk)}; launch_elemblk(ex, B, a); }
+    int ebits = bits_for(2ull * c->nmax);
+    { EndKeyArgs a{v, P<u32>(c->o_depth), P<u32>(c->o_set), P<int>(c->o_pos), set_blk0, set_pos0, P<u32>(c->elem_blk),
+                   P<u64>(c->keysA), P<u32>(c->valsA), ebits};
+      launch_endkey(ex, E, a); }
+    TRY(sort_pairs(c, E, 0, ebits + bits_for((u64)c->M - 1)));
+    { SegHeadArgs a{P<u64>(c->keysA), P<u32>(c->seghead), ebits}; launch_seghead(ex, E, a); }
+    TRY((scan_u32<ScanMax, true>(ex, c->ps, P<u32>(c->seghead), P<u32>(c->seghead), E)));
+    TRY(dev_fill_ff(ex, c->succ_lo.p, nb));
+    TRY(dev_zero(ex, c->succ_hi.p, nb));
+    { LinkArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->seghead), P<u32>(c->o_depth), ebits, P<u32>(c->succ_lo), P<u32>(c->succ_hi)};
+      launch_link(ex, E, a); }
+    { GapArgs a{v, P<u32>(c->succ_lo), P<u32>(c->succ_hi), P<u32>(c->o_depth), P<u32>(c->o_set), P<int>(c->o_pos), set_blk0, set_pos0,
+                max_interval, P<int>(c->next), P<int>(c->gap)};
+      launch_gap(ex, B, a); }
+    TRY(dev_zero(ex, c->size.p, nb)); TRY(dev_zero(ex, c->total.p, nb)); TRY(dev_zero(ex, c->interval.p, nb));
+    { ChainArgs a{set_blk0, P<u32>(c->o_depth), P<int>(c->next), P<int>(c->gap), P<int>(c->size), P<int>(c->total), P<int>(c->interval),
+                  P<u32>(c->set_nchains), P<u32>(c->set_flags)};
+      launch_chain(ex, nsets, a); }
+    { SizeKeyArgs a{P<u32>(c->o_set), P<int>(c->size), P<u64>(c->keysA), P<u32>(c->valsA)}; launch_sizekey(ex, B, a); }
+    TRY(sort_pairs(c, B, 0, 32 + bits_for((u64)c->nsets - 1)));
+    { InvArgs a{P<u32>(c->valsA), P<u32>(c->inv)}; launch_inv(ex, B, a); }
+    { FinalArgs a{v, P<u32>(c->valsA), P<u32>(c->inv), P<u32>(c->o_depth), P<u32>(c->o_set), P<int>(c->o_pos), P<int>(c->size),
+                  P<int>(c->total), P<int>(c->interval), P<int>(c->next), set_blk0, set_pos0, P<int>(c->f_depth), P<int>(c->f_size),
+                  P<int>(c->f_total), P<int>(c->f_interval), P<int>(c->f_next), P<int>(c->f_pos)};
+      launch_final(ex, B, a); }
+    return 0;
+}
+
+extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flags) {
+    (void)flags;
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (!c->uploaded) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_run before csa_gpu_batch_upload");
+#ifndef CSA_EMU
+    CUDA_TRY(cudaSetDevice(c->device));
+#endif
+    Exec &ex = c->ex;
+    ex.launches = 0;
+    c->ran = false;
+    u32 N = c->N;
+    int nsets = c->nsets;
+    size_t n4 = sizeof(u32) * (size_t)N;
+    TRY(dev_alloc(c->keysA, 2 * n4)); TRY(dev_alloc(c->keysB, 2 * n4));
+    TRY(dev_alloc(c->valsA, n4)); TRY(dev_alloc(c->valsB, n4)); TRY(dev_alloc(c->sa, n4));
+    TRY(dev_alloc(c->t0, n4)); TRY(dev_alloc(c->t1, n4)); TRY(dev_alloc(c->t2, n4)); TRY(dev_alloc(c->t3, n4)); TRY(dev_alloc(c->t4, n4));
+    TRY(dev_alloc(c->counter, 64));
+    DevMem *perset[] = {&c->set_nblocks, &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax};
+    for (DevMem *m : perset) TRY(dev_alloc(*m, sizeof(u32) * (nsets + 1)));
+    TRY(dev_alloc(c->rotations, sizeof(int) * (size_t)c->M));
+    BatchView v = view_of(c);
+
+    mark(c, 0);
+    { EncodeArgs a{v, P<unsigned char>(c->raw)}; launch_encode(ex, N, a); }
+    { PackArgs a{v}; launch_pack(ex, (long long)c->TW, a); }
+    TRY(stage_suffix_array(c, v));
+    mark(c, 1);
+    { LcpArgs a{v, P<u32>(c->sa), P<u32>(c->t2)}; launch_lcp(ex, N, a); }
+    mark(c, 2);
+    TRY(dev_zero(ex, c->set_flags.p, sizeof(u32) * nsets));
+    TRY(stage_common_blocks(c, v));
+    mark(c, 3);
+    TRY(stage_block_order(c, v));
+    mark(c, 4);
+    TRY(stage_chain(c, v, max_interval));
+    { RotArgs a{v, P<u32>(c->set_blk0), P<u32>(c->set_pos0), P<int>(c->f_pos), P<int>(c->f_next), P<int>(c->rotations), P<u32>(c->set_cyclic)};
+      launch_rot(ex, nsets, a); }
+    mark(c, 5);
+    TRY(exec_sync(ex));
+#ifndef CSA_EMU
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) CSA_FAIL(CSA_GPU_ECUDA, "kernel failure: %s", cudaGetErrorString(e));
+        for (int i = 0; i < 5; i++) cudaEventElapsedTime(&c->tm.ms[i], c->tm.ev[i], c->tm.ev[i + 1]);
+        cudaEventElapsedTime(&c->tm.ms[5], c->tm.ev[0], c->tm.ev[5]);
+    }
+#endif
+    c->launches = ex.launches;
+    c->ran = true;
+    return CSA_GPU_OK;
+}
+
+// ---- download ---------------------------------------------------------------------------------------
+extern "C" int csa_gpu_batch_download(csa_gpu_ctx *c, int *rotations, csa_gpu_set_info *info) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (!c->ran) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_download before csa_gpu_batch_run");
+    int nsets = c->nsets;
+    Exec &ex = c->ex;
+    c->h_set_flags.assign(nsets, 0); c->h_set_nchains.assign(nsets, 0); c->h_set_cyclic.assign(nsets, 0);
+    TRY(d2h(ex, c->h_set_flags.data(), c->set_flags.p, sizeof(u32) * nsets));
+    TRY(d2h(ex, c->h_set_nchains.data(), c->set_nchains.p, sizeof(u32) * nsets));
+    TRY(d2h(ex, c->h_set_cyclic.data(), c->set_cyclic.p, sizeof(u32) * nsets));
+    if (rotations) TRY(d2h(ex, rotations, c->rotations.p, sizeof(int) * (size_t)c->M));
+    for (int s = 0; s < nsets; s++) {
+        int status = CSA_SET_OK;
+        u32 fl = c->h_set_flags[s];
+        // the order of the reference's exits: the tree walk (csamsa.c:64) comes before the counts
+        if (fl & 1u) status = CSA_SET_DEGENERATE;
+        else if (c->h_set_nblocks[s] == 0) status = CSA_SET_NO_UNIQUE;
+        else if (fl & 2u) status = CSA_SET_NONTERMINATING;
+        if (rotations && status != CSA_SET_OK)
+            for (u32 k = c->h_set_seq0[s]; k < c->h_set_seq0[s + 1]; k++) rotations[k] = 0;
+        if (info) {
+            csa_gpu_set_info &o = info[s];
+            o.status = status;
+            o.nseqs = (int)(c->h_set_seq0[s + 1] - c->h_set_seq0[s]);
+            o.count_collected = -1;
+            o.count_suffixfree = -1;
+            o.count_unique = (int)c->h_set_nblocks[s];
+            o.count_chains = (int)c->h_set_nchains[s];
+            o.nblocks = (int)c->h_set_nblocks[s];
+            o.chain_is_cyclic = (int)c->h_set_cyclic[s];
+            o.block_offset = c->h_set_blk0[s];
+        }
+    }
+    return CSA_GPU_OK;
+}
+
+extern "C" long long csa_gpu_batch_num_blocks(csa_gpu_ctx *c) { return (c && c->ran) ? (long long)c->B : -1; }
+extern "C" long long csa_gpu_batch_num_positions(csa_gpu_ctx *c) { return (c && c->ran) ? (long long)c->E : -1; }
+
+extern "C" int csa_gpu_batch_blocks(csa_gpu_ctx *c, int *depth, int *size, int *totalsize, int *interval, int *next,
+                                    int *positions) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (!c->ran) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_blocks before csa_gpu_batch_run");
+    Exec &ex = c->ex;
+    size_t nb = sizeof(int) * (size_t)c->B;
+    if (c->B == 0) return CSA_GPU_OK;
+    if (depth) TRY(d2h(ex, depth, c->f_depth.p, nb));
+    if (size) TRY(d2h(ex, size, c->f_size.p, nb));
+    if (totalsize) TRY(d2h(ex, totalsize, c->f_total.p, nb));
+    if (interval) TRY(d2h(ex, interval, c->f_interval.p, nb));
+    if (next) TRY(d2h(ex, next, c->f_next.p, nb));
+    if (positions) TRY(d2h(ex, positions, c->f_pos.p, sizeof(int) * (size_t)c->E));
+    return CSA_GPU_OK;
+}
+
+extern "C" int csa_gpu_batch_rotations(csa_gpu_ctx *c, int nsets, const int *set_start, const char *const *texts,
+                                       const int *textsizes, int max_interval, unsigned flags, int *rotations,
+                                       csa_gpu_set_info *info) {
+    TRY(csa_gpu_batch_upload(c, nsets, set_start, texts, textsizes));
+    TRY(csa_gpu_batch_run(c, max_interval, flags));
+    return csa_gpu_batch_download(c, rotations, info);
+}
+
+extern "C" int csa_gpu_find_rotations(csa_gpu_ctx *c, int numberofseqs, const char *const *texts, const int *textsizes,
+                                      int max_interval, unsigned flags, int *rotations, csa_gpu_set_info *info) {
+    int set_start[2] = {0, numberofseqs};
+    return csa_gpu_batch_rotations(c, 1, set_start, texts, textsizes, max_interval, flags, rotations, info);
+}
+
+// ---- introspection -----------------------------------------------------------------------------------
+extern "C" long long csa_gpu_batch_num_suffixes(csa_gpu_ctx *c) { return (c && c->uploaded) ? (long long)c->N : -1; }
+
+extern "C" int csa_gpu_batch_suffix_array(csa_gpu_ctx *c, unsigned *sa, int *lcp) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (!c->ran) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_suffix_array before csa_gpu_batch_run");
+    if (sa) TRY(d2h(c->ex, sa, c->sa.p, sizeof(u32) * (size_t)c->N));
+    if (lcp) TRY(d2h(c->ex, lcp, c->t2.p, sizeof(u32) * (size_t)c->N));
+    return CSA_GPU_OK;
+}
+
+extern "C" int csa_gpu_batch_timings(csa_gpu_ctx *c, float ms[6], long long *launches) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (!c->ran) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_timings before csa_gpu_batch_run");
+    if (ms) for (int i = 0; i < 6; i++) ms[i] = c->tm.ms[i];
+    if (launches) *launches = c->launches;
+    return CSA_GPU_OK;
+}

@@ -1,0 +1,689 @@
+// pipeline.cuh -- the rotation-finding path of fjdf/CSA (`./CSA R`) as device kernels.
+//
+// Reference path replaced (see include/csa_gpu.h and DESIGN.md):
+//   buildGeneralizedTree   gencycsuffixtrees.c:418   -> stage 1+2: generalized cyclic suffix array + LCP
+//   collectNodes           csamsa.c:64               -> stage 3: LCP intervals holding every sequence
+//   removeSuffixNodes      csamsa.c:80               ->          ... that cannot be extended to the left
+//   removeNonUniqueNodes   csamsa.c:283              ->          ... of exactly m suffixes
+//   insertSortedItem       nodeslinkedlists.c:36     -> stage 4: block order (depth, DFS visiting order)
+//   collectNodeChains      csamsa.c:135              -> stage 5: block chaining
+//   sortList/getRotations  nodeslinkedlists.c:59, csamsa.c:311 -> stage 5: chain order, cut points
+//
+// A batch holds many independent sequence sets.  All suffixes (= rotations) of the batch live
+// in ONE index space g = seq_off[k] + p; the set number is the most significant part of every
+// sort key, so suffixes of different sets never mix and one launch serves the whole batch.
+#pragma once
+#include "prims.cuh"
+
+#define CSA_K0 13          // letters in the initial sort key
+#define CSA_LETTER_BITS 3  // A C G T other -> 0..4
+#define CSA_K0_BITS (CSA_K0 * CSA_LETTER_BITS)
+#define CSA_NONE 0xFFFFFFFFu
+
+struct BatchView {
+    int nsets;
+    u32 M;                     // sequences
+    u32 N;                     // bases == suffixes
+    const u32 *seq_off;        // [M+1] first base of sequence k
+    const u32 *seq_set;        // [M]   set of sequence k
+    const u32 *set_seq0;       // [nsets+1] first sequence of set s
+    const u32 *set_base0;      // [nsets+1] first base (== first SA index) of set s
+    const u32 *set_nmin;       // [nsets] shortest sequence of set s
+    const u64 *dbl_off;        // [M+1] first base of sequence k in the doubled, packed text
+    u32 *seqof;                // [N] sequence of base g
+    unsigned char *code;       // [N] letter codes 0..4
+    u64 *p2;                   // doubled text, 2 bits per base, 32 bases per word
+    u32 *pm;                   // doubled text, 1 bit per base: letter is not A/C/G/T
+};
+
+// gencycsuffixtrees.c:283/297: every letter that is not A/C/G/T is one fifth letter
+HD unsigned code_of_letter(unsigned char c) {
+    return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+}
+
+HD u32 upper_bound_u32(const u32 *a, u32 n, u32 x) { // first index with a[idx] > x
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        if (LDG(a + mid) <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+HD u32 upper_bound_u64(const u64 *a, u32 n, u64 x) {
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        if (LDG(a + mid) <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// position h letters further round the circle
+HD u32 cyc_add(const BatchView &v, u32 g, u32 h) {
+    u32 k = LDG(v.seqof + g);
+    u32 off = LDG(v.seq_off + k), n = LDG(v.seq_off + k + 1) - off;
+    u32 p = g - off;
+    if (h >= n) h %= n;
+    u32 q = p + h; // < 2n <= 2^32 is guaranteed by N < 2^31
+    if (q >= n) q -= n;
+    return off + q;
+}
+
+// ---- stage 0: encode + pack ------------------------------------------------------------------
+struct EncodeArgs { BatchView v; const unsigned char *raw; };
+HD void encode_body(long long i, const EncodeArgs &a) {
+    u32 g = (u32)i;
+    a.v.code[g] = (unsigned char)code_of_letter(a.raw[g]);
+    a.v.seqof[g] = upper_bound_u32(a.v.seq_off, a.v.M + 1, g) - 1;
+}
+MAP_KERNEL(encode, EncodeArgs)
+
+// one thread per 32-base word of the doubled text: sequence k occupies bases
+// [dbl_off[k], dbl_off[k+1]) = s_k s_k s_k... so that any window p..p+n+63 reads without wrap
+struct PackArgs { BatchView v; };
+HD void pack_body(long long w, const PackArgs &a) {
+    u64 x0 = (u64)w * 32;
+    u32 k = upper_bound_u64(a.v.dbl_off, a.v.M + 1, x0) - 1;
+    if (k >= a.v.M) { a.v.p2[w] = 0; a.v.pm[w] = 0; return; } // the two guard words at the end
+    u32 off = LDG(a.v.seq_off + k), n = LDG(a.v.seq_off + k + 1) - off;
+    u32 p = (u32)((x0 - LDG(a.v.dbl_off + k)) % n);
+    u64 w2 = 0;
+    u32 wm = 0;
+    for (int t = 0; t < 32; t++) {
+        unsigned c = a.v.code[off + p];
+        if (c > 3) wm |= 1u << t; else w2 |= (u64)c << (2 * t);
+        if (++p == n) p = 0;
+    }
+    a.v.p2[w] = w2;
+    a.v.pm[w] = wm;
+}
+MAP_KERNEL(pack, PackArgs)
+
+// ---- stage 1: suffix array by prefix doubling --------------------------------------------------
+struct InitKeyArgs { BatchView v; u64 *keys; u32 *vals; };
+HD void initkey_body(long long i, const InitKeyArgs &a) {
+    u32 g = (u32)i;
+    u32 k = LDG(a.v.seqof + g);
+    u32 off = LDG(a.v.seq_off + k), n = LDG(a.v.seq_off + k + 1) - off;
+    u32 p = g - off;
+    u64 key = LDG(a.v.seq_set + k);
+    for (int t = 0; t < CSA_K0; t++) {
+        key = (key << CSA_LETTER_BITS) | a.v.code[off + p];
+        if (++p == n) p = 0;
+    }
+    a.keys[g] = key;
+    a.vals[g] = g;
+}
+MAP_KERNEL(initkey, InitKeyArgs)
+
+// head[i] = i where a new group of equal keys starts, else 0 (max-scanned afterwards)
+struct FlagArgs { const u64 *keys; u32 *head; u32 *ngroups; };
+HD void flag_body(long long i, const FlagArgs &a) {
+    bool f = (i == 0) || a.keys[i] != a.keys[i - 1];
+    a.head[i] = f ? (u32)i : 0u;
+    if (f) ATOMIC_ADD(a.ngroups, 1u);
+}
+MAP_KERNEL(flag, FlagArgs)
+
+struct SetRankArgs { const u32 *sa; const u32 *head; u32 *rank; };
+HD void setrank_body(long long i, const SetRankArgs &a) { a.rank[a.sa[i]] = a.head[i]; }
+MAP_KERNEL(setrank, SetRankArgs)
+
+// key of the doubling round: (rank of the first h letters, rank of the next h letters)
+struct Key2Args { BatchView v; const u32 *sa; const u32 *rank; u64 *keys; u32 h; int nbits; };
+HD void key2_body(long long i, const Key2Args &a) {
+    u32 g = a.sa[i];
+    u32 r1 = LDG(a.rank + g), r2 = LDG(a.rank + cyc_add(a.v, g, a.h));
+    a.keys[i] = ((u64)r1 << a.nbits) | r2;
+}
+MAP_KERNEL(key2, Key2Args)
+
+// ---- stage 2: LCP of neighbouring suffixes, capped at the shorter rotation -------------------------
+// gencycsuffixtrees.c:500: a path of the tree ends after textsize letters.
+HD u64 fetch2(const u64 *p2, u64 x) { // 32 bases starting at doubled base x
+    u64 j = x >> 5;
+    unsigned s = (unsigned)(x & 31) * 2;
+    u64 lo = LDG(p2 + j);
+    if (s == 0) return lo;
+    return (lo >> s) | (LDG(p2 + j + 1) << (64 - s));
+}
+HD u32 fetchm(const u32 *pm, u64 x) {
+    u64 j = x >> 5;
+    unsigned s = (unsigned)(x & 31);
+    u32 lo = LDG(pm + j);
+    if (s == 0) return lo;
+    return (lo >> s) | (LDG(pm + j + 1) << (32 - s));
+}
+HD int ctz64(u64 x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+HD int ctz32(u32 x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
+struct LcpArgs { BatchView v; const u32 *sa; u32 *lcp; };
+HD void lcp_body(long long i, const LcpArgs &a) {
+    if (i == 0) { a.lcp[0] = 0; return; }
+    u32 ga = a.sa[i - 1], gb = a.sa[i];
+    u32 ka = LDG(a.v.seqof + ga), kb = LDG(a.v.seqof + gb);
+    if (LDG(a.v.seq_set + ka) != LDG(a.v.seq_set + kb)) { a.lcp[i] = 0; return; }
+    u32 oa = LDG(a.v.seq_off + ka), ob = LDG(a.v.seq_off + kb);
+    u32 na = LDG(a.v.seq_off + ka + 1) - oa, nb = LDG(a.v.seq_off + kb + 1) - ob;
+    u32 cap = na < nb ? na : nb;
+    u64 xa = LDG(a.v.dbl_off + ka) + (ga - oa), xb = LDG(a.v.dbl_off + kb) + (gb - ob);
+    u32 t = 0;
+    while (t < cap) {
+        u64 d2 = fetch2(a.v.p2, xa + t) ^ fetch2(a.v.p2, xb + t);
+        u32 dm = fetchm(a.v.pm, xa + t) ^ fetchm(a.v.pm, xb + t);
+        int f = 32;
+        if (d2) f = ctz64(d2) >> 1;
+        if (dm) { int f2 = ctz32(dm); if (f2 < f) f = f2; }
+        if (f < 32) { t += (u32)f; break; }
+        t += 32;
+    }
+    a.lcp[i] = t < cap ? t : cap;
+}
+MAP_KERNEL(lcp, LcpArgs)
+
+// ---- stage 3: common blocks ------------------------------------------------------------------------
+// R[l] = smallest r such that SA[l..r] holds a suffix of every sequence of the set (>= end of the
+// set when there is none).  An LCP interval [lb,rb] "belongs to all the sequences"
+// (node->fromseqs == allseqsmask, gencycsuffixtrees.c:34) iff rb >= R[lb].
+//   R[l] = max( last first-occurrence of any colour, max_{j<l} next index of j's colour )
+// The colour lists come from one stable radix pass of the SA indices by sequence-in-set.
+struct ColorKeyArgs { BatchView v; const u32 *sa; u64 *keys; u32 *vals; };
+HD void colorkey_body(long long i, const ColorKeyArgs &a) {
+    u32 k = LDG(a.v.seqof + a.sa[i]);
+    a.keys[i] = k - LDG(a.v.set_seq0 + LDG(a.v.seq_set + k));
+    a.vals[i] = (u32)i;
+}
+MAP_KERNEL(colorkey, ColorKeyArgs)
+
+// after the sort: vals = SA indices ordered by (colour, index).  cover[i] (read at i+1) = next
+// index of the same sequence; cover[set start] collects the latest first occurrence.
+struct NextArgs { BatchView v; const u32 *sa; const u32 *vals; u32 *nxt; u32 *firstmax; };
+HD void next_body(long long j, const NextArgs &a) {
+    u32 i = a.vals[j];
+    u32 k = LDG(a.v.seqof + a.sa[i]);
+    u32 s = LDG(a.v.seq_set + k);
+    u32 send = LDG(a.v.set_base0 + s + 1);
+    u32 nx = send;
+    if ((u32)j + 1 < a.v.N) {
+        u32 i2 = a.vals[j + 1];
+        if (LDG(a.v.seqof + a.sa[i2]) == k) nx = i2;
+    }
+    a.nxt[i] = nx;
+    bool first = (j == 0) || LDG(a.v.seqof + a.sa[a.vals[j - 1]]) != k;
+    if (first) ATOMIC_MAX(a.firstmax + s, i);
+}
+MAP_KERNEL(next, NextArgs)
+
+struct CoverArgs { BatchView v; const u32 *sa; const u32 *nxt; const u32 *firstmax; u32 *cover; };
+HD void cover_body(long long i, const CoverArgs &a) {
+    u32 s = LDG(a.v.seq_set + LDG(a.v.seqof + a.sa[i]));
+    u32 s0 = LDG(a.v.set_base0 + s);
+    a.cover[i] = ((u32)i == s0) ? a.firstmax[s] : a.nxt[i - 1];
+}
+MAP_KERNEL(cover, CoverArgs)
+
+// blocks: LCP intervals of exactly m suffixes, one of every sequence, that cannot be extended to
+// the left by one and the same letter (csamsa.c:64,80,283).  One thread per left border.
+struct BlockFindArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *isblock; u32 *depth; };
+HD void blockfind_body(long long i, const BlockFindArgs &a) {
+    u32 lb = (u32)i;
+    a.isblock[lb] = 0;
+    u32 k0 = LDG(a.v.seqof + a.sa[lb]);
+    u32 s = LDG(a.v.seq_set + k0);
+    u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
+    u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
+    if (lb + m > s1 || m < 2) return;
+    u32 rb = lb + m - 1;
+    if (a.R[lb] != rb) return; // m suffixes holding all m sequences: each exactly once
+    long long outer_l = (lb == s0) ? -1 : (long long)a.lcp[lb];
+    long long outer_r = (rb + 1 == s1) ? -1 : (long long)a.lcp[rb + 1];
+    long long outer = outer_l > outer_r ? outer_l : outer_r;
+    u32 inner = 0xFFFFFFFFu;
+    for (u32 j = lb + 1; j <= rb; j++) { u32 l = a.lcp[j]; if (l < inner) inner = l; }
+    if ((long long)inner <= outer) return; // not an LCP interval
+    // removeSuffixNodes: every occurrence preceded by one and the same letter -> a longer block
+    // holds it (csamsa.c:85 leaves a list holding only the root alone: depth 0)
+    if (inner > 0) {
+        bool same = true;
+        unsigned c0 = 0;
+        for (u32 j = lb; j <= rb && same; j++) {
+            u32 g = a.sa[j];
+            u32 k = LDG(a.v.seqof + g);
+            u32 off = LDG(a.v.seq_off + k), n = LDG(a.v.seq_off + k + 1) - off;
+            u32 p = g - off;
+            unsigned c = a.v.code[off + (p == 0 ? n - 1 : p - 1)];
+            if (j == lb) c0 = c; else if (c != c0) same = false;
+        }
+        if (same) return;
+    }
+    a.isblock[lb] = 1;
+    a.depth[lb] = inner;
+}
+MAP_KERNEL(blockfind, BlockFindArgs)
+
+// a whole rotation of the shortest sequence occurs in every sequence: the reference walks off its
+// tree (undefined behaviour).  Maximal runs of lcp >= nmin that hold every sequence.
+struct DegenArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *set_flags; };
+HD void degen_body(long long i, const DegenArgs &a) {
+    u32 lb = (u32)i;
+    u32 s = LDG(a.v.seq_set + LDG(a.v.seqof + a.sa[lb]));
+    u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
+    u32 nmin = LDG(a.v.set_nmin + s);
+    if (lb + 1 >= s1 || a.lcp[lb + 1] < nmin) return;
+    if (lb != s0 && a.lcp[lb] >= nmin) return; // not the head of the run
+    u32 rb = lb + 1;
+    while (rb + 1 < s1 && a.lcp[rb + 1] >= nmin) rb++;
+    if (rb >= a.R[lb]) ATOMIC_MAX(a.set_flags + s, 1u);
+}
+MAP_KERNEL(degen, DegenArgs)
+
+// compaction of the block borders; blocks come out in SA order, i.e. grouped by set
+struct BlockEmitArgs {
+    BatchView v; const u32 *sa; const u32 *isblock; const u32 *bidx; const u32 *depth;
+    u32 *blk_lb; u32 *blk_depth; u32 *blk_set; u32 *set_nblocks;
+};
+HD void blockemit_body(long long i, const BlockEmitArgs &a) {
+    if (!a.isblock[i]) return;
+    u32 b = a.bidx[i];
+    u32 s = LDG(a.v.seq_set + LDG(a.v.seqof + a.sa[i]));
+    a.blk_lb[b] = (u32)i;
+    a.blk_depth[b] = a.depth[i];
+    a.blk_set[b] = s;
+    ATOMIC_ADD(a.set_nblocks + s, 1u);
+}
+MAP_KERNEL(blockemit, BlockEmitArgs)
+
+// ---- stage 4: order of the block list ----------------------------------------------------------------
+// insertSortedItem (nodeslinkedlists.c:36) keeps the list by depth, descending, and puts a block
+// BEFORE the blocks of equal depth met earlier; blocks are met in the DFS order of the tree,
+// whose children are in creation order (addBranch, gencycsuffixtrees.c:193) == the order of the
+// first occurrence, in sequence 0 of the set, of the child's string.  The DFS number of every
+// rotation of sequence 0 is computed on the LCP-interval tree of sequence 0 alone:
+//   dfs(leaf) = sum over the nodes v on the path leaf..root of before(v),
+//   before(v) = leaves under the siblings of v whose first occurrence precedes v's.
+struct Seq0FlagArgs { BatchView v; const u32 *sa; u32 *flag; };
+HD void seq0flag_body(long long i, const Seq0FlagArgs &a) {
+    u32 k = LDG(a.v.seqof + a.sa[i]);
+    a.flag[i] = (k == LDG(a.v.set_seq0 + LDG(a.v.seq_set + k))) ? 1u : 0u;
+}
+MAP_KERNEL(seq0flag, Seq0FlagArgs)
+
+struct Seq0EmitArgs { BatchView v; const u32 *sa; const u32 *flag; const u32 *idx0; u32 *sa0; u32 *saidx0; u32 *leaf_set; };
+HD void seq0emit_body(long long i, const Seq0EmitArgs &a) {
+    if (!a.flag[i]) return;
+    u32 t = a.idx0[i];
+    u32 g = a.sa[i];
+    u32 k = LDG(a.v.seqof + g);
+    a.sa0[t] = g - LDG(a.v.seq_off + k);
+    a.saidx0[t] = (u32)i;
+    a.leaf_set[t] = LDG(a.v.seq_set + k);
+}
+MAP_KERNEL(seq0emit, Seq0EmitArgs)
+
+struct Seq0View {
+    u32 N0;
+    const u32 *z0;       // [nsets+1] first leaf of set s
+    const u32 *leaf_set; // [N0]
+    const u32 *lcp0;     // [N0] lcp of leaves t-1,t (undefined at the first leaf of a set)
+};
+
+struct Lcp0Args { const u32 *lcp; const u32 *saidx0; const u32 *leaf_set; const u32 *z0; u32 *lcp0; };
+HD void lcp0_body(long long t, const Lcp0Args &a) {
+    u32 s = a.leaf_set[t];
+    if ((u32)t == LDG(a.z0 + s)) { a.lcp0[t] = 0; return; }
+    u32 mn = 0xFFFFFFFFu;
+    for (u32 j = a.saidx0[t - 1] + 1; j <= a.saidx0[t]; j++) { u32 l = a.lcp[j]; if (l < mn) mn = l; }
+    a.lcp0[t] = mn;
+}
+MAP_KERNEL(lcp0, Lcp0Args)
+
+// nearest smaller / smaller-or-equal values around every border t (z0 < t < z1) of the set
+struct AnsvArgs { Seq0View q; u32 *psv; u32 *nsv; u32 *pse; };
+HD void ansv_body(long long ti, const AnsvArgs &a) {
+    u32 t = (u32)ti;
+    u32 s = a.q.leaf_set[t];
+    u32 z0 = LDG(a.q.z0 + s), z1 = LDG(a.q.z0 + s + 1);
+    if (t == z0) { a.psv[t] = z0; a.nsv[t] = z1; a.pse[t] = z0; return; }
+    u32 v = a.q.lcp0[t];
+    u32 j = t - 1;
+    while (j > z0 && a.q.lcp0[j] > v) j--;
+    a.pse[t] = j; // z0 = none
+    while (j > z0 && a.q.lcp0[j] >= v) j--;
+    a.psv[t] = j;
+    j = t + 1;
+    while (j < z1 && a.q.lcp0[j] >= v) j++;
+    a.nsv[t] = j; // z1 = none
+}
+MAP_KERNEL(ansv, AnsvArgs)
+
+// Node numbering: internal node = its representative border t (the leftmost border of the node
+// whose value is the node's depth), leaf t = N0 + t.  parent[] of both kinds; the root points at
+// itself.  size[] = leaves below, minpos[] = first occurrence in sequence 0.
+HD u32 rep_of(const u32 *psv, const u32 *pse, u32 t) {
+    while (pse[t] != psv[t]) t = pse[t];
+    return t;
+}
+HD u32 parent_of_span(const Seq0View &q, const u32 *psv, const u32 *pse, u32 z0, u32 z1, u32 lb, u32 rb, u32 self) {
+    long long vl = (lb == z0) ? -1 : (long long)q.lcp0[lb];
+    long long vr = (rb + 1 == z1) ? -1 : (long long)q.lcp0[rb + 1];
+    if (vl < 0 && vr < 0) return self; // the root
+    if (vl >= vr) return rep_of(psv, pse, lb);
+    return rb + 1;
+}
+struct TreeArgs { Seq0View q; const u32 *psv; const u32 *nsv; const u32 *pse; const u32 *sa0; u32 *parent; u32 *size; u32 *minpos; };
+HD void tree_body(long long x, const TreeArgs &a) {
+    u32 N0 = a.q.N0;
+    if ((u32)x < N0) { // border x: an internal node iff x is a representative
+        u32 t = (u32)x;
+        u32 s = a.q.leaf_set[t];
+        u32 z0 = LDG(a.q.z0 + s), z1 = LDG(a.q.z0 + s + 1);
+        a.minpos[t] = 0xFFFFFFFFu;
+        if (t == z0 || a.pse[t] != a.psv[t]) { a.parent[t] = CSA_NONE; a.size[t] = 0; return; }
+        u32 lb = a.psv[t], rb = a.nsv[t] - 1;
+        a.parent[t] = parent_of_span(a.q, a.psv, a.pse, z0, z1, lb, rb, t);
+        a.size[t] = rb - lb + 1;
+    } else {
+        u32 t = (u32)x - N0;
+        u32 s = a.q.leaf_set[t];
+        u32 z0 = LDG(a.q.z0 + s), z1 = LDG(a.q.z0 + s + 1);
+        a.parent[x] = parent_of_span(a.q, a.psv, a.pse, z0, z1, t, t, (u32)x);
+        a.size[x] = 1;
+        a.minpos[x] = a.sa0[t];
+    }
+}
+MAP_KERNEL(tree, TreeArgs)
+
+// first occurrence of every node: each leaf climbs while it lowers the minimum
+struct MinposArgs { u32 N0; const u32 *parent; u32 *minpos; };
+HD void minpos_body(long long t, const MinposArgs &a) {
+    u32 x = a.N0 + (u32)t;
+    u32 val = a.minpos[x];
+    u32 p = a.parent[x];
+    while (p != x) {
+        u32 old = ATOMIC_MIN(a.minpos + p, val);
+        if (old <= val) break;
+        x = p;
+        p = a.parent[x];
+    }
+}
+MAP_KERNEL(minpos, MinposArgs)
+
+// children grouped by parent and ordered by first occurrence: sort key (parent, minpos)
+struct ChildKeyArgs { u32 N0; const u32 *parent; const u32 *minpos; u64 *keys; u32 *vals; };
+HD void childkey_body(long long x, const ChildKeyArgs &a) {
+    u32 p = a.parent[x];
+    // borders that are no node, and roots, sort to the end
+    bool live = (p != CSA_NONE) && (p != (u32)x);
+    a.keys[x] = live ? (((u64)p << 32) | a.minpos[x]) : ~0ull;
+    a.vals[x] = (u32)x;
+}
+MAP_KERNEL(childkey, ChildKeyArgs)
+
+struct BeforeArgs { const u64 *keys; const u32 *vals; const u32 *size; u32 *val; u32 *up; const u32 *parent; };
+HD void before_body(long long j, const BeforeArgs &a) {
+    u64 key = a.keys[j];
+    u32 x = a.vals[j];
+    if (key == ~0ull) { a.val[x] = 0; a.up[x] = (a.parent[x] == CSA_NONE) ? x : a.parent[x]; return; }
+    u32 p = (u32)(key >> 32);
+    u32 sum = 0;
+    for (long long q = j - 1; q >= 0 && (u32)(a.keys[q] >> 32) == p && a.keys[q] != ~0ull; q--) sum += a.size[a.vals[q]];
+    a.val[x] = sum;
+    a.up[x] = p;
+}
+MAP_KERNEL(before, BeforeArgs)
+
+struct JumpArgs { const u32 *val; const u32 *up; u32 *val2; u32 *up2; };
+HD void jump_body(long long x, const JumpArgs &a) {
+    u32 u = a.up[x];
+    a.val2[x] = a.val[x] + a.val[u];
+    a.up2[x] = a.up[u];
+}
+MAP_KERNEL(jump, JumpArgs)
+
+// per block: its sort keys and its positions (one per sequence of the set)
+struct BlockKeyArgs {
+    BatchView v; const u32 *sa; const u32 *idx0; const u32 *flag0; const u32 *dfs; u32 N0;
+    const u32 *blk_lb; const u32 *blk_depth; const u32 *blk_set;
+    u64 *keys; u32 *vals; int pass; // pass 0: dfs descending; pass 1: (set, depth descending)
+};
+HD void blockkey_body(long long b, const BlockKeyArgs &a) {
+    if (a.pass == 0) {
+        u32 lb = a.blk_lb[b];
+        u32 s = a.blk_set[b];
+        u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
+        u32 d = 0;
+        for (u32 j = lb; j < lb + m; j++)
+            if (a.flag0[j]) d = a.dfs[a.N0 + a.idx0[j]];
+        a.keys[b] = 0xFFFFFFFFu - d;
+        a.vals[b] = (u32)b;
+    } else {
+        u32 ob = a.vals[b];
+        a.keys[b] = ((u64)a.blk_set[ob] << 32) | (0xFFFFFFFFu - a.blk_depth[ob]);
+    }
+}
+MAP_KERNEL(blockkey, BlockKeyArgs)
+
+// blocks in list order: gather fields, write positions
+struct BlockGatherArgs {
+    BatchView v; const u32 *sa; const u32 *order; const u32 *blk_lb; const u32 *blk_depth; const u32 *blk_set;
+    const u32 *set_blk0; const u32 *set_pos0;
+    u32 *o_depth; u32 *o_set; int *o_pos;
+};
+HD u32 pos_offset(const u32 *set_blk0, const u32 *set_pos0, u32 s, u32 m, u32 b) {
+    return LDG(set_pos0 + s) + (b - LDG(set_blk0 + s)) * m;
+}
+HD void blockgather_body(long long b, const BlockGatherArgs &a) {
+    u32 ob = a.order[b];
+    u32 s = a.blk_set[ob];
+    u32 q0 = LDG(a.v.set_seq0 + s);
+    u32 m = LDG(a.v.set_seq0 + s + 1) - q0;
+    a.o_depth[b] = a.blk_depth[ob];
+    a.o_set[b] = s;
+    u32 po = pos_offset(a.set_blk0, a.set_pos0, s, m, (u32)b);
+    u32 lb = a.blk_lb[ob];
+    for (u32 j = lb; j < lb + m; j++) {
+        u32 g = a.sa[j];
+        u32 k = LDG(a.v.seqof + g);
+        a.o_pos[po + (k - q0)] = (int)(g - LDG(a.v.seq_off + k));
+    }
+}
+MAP_KERNEL(blockgather, BlockGatherArgs)
+
+// ---- stage 5: chaining (collectNodeChains, csamsa.c:135-279) -----------------------------------------
+// csamsa.c:147-183 walks every sequence round the circle and notes which block follows which; a
+// block is noticed where it ENDS (position+depth, unrolled).  Two blocks are linked when the same
+// successor follows in every sequence that has one.  Sorting the block ends of every sequence
+// gives the same successor relation.
+struct EndKeyArgs {
+    BatchView v; const u32 *o_depth; const u32 *o_set; const int *o_pos; const u32 *set_blk0; const u32 *set_pos0;
+    const u32 *elem_blk; // [E] block of element x (E = sum over blocks of m)
+    u64 *keys; u32 *vals; int ebits;
+};
+HD void endkey_body(long long x, const EndKeyArgs &a) {
+    u32 b = a.elem_blk[x];
+    u32 s = a.o_set[b];
+    u32 q0 = LDG(a.v.set_seq0 + s);
+    u32 m = LDG(a.v.set_seq0 + s + 1) - q0;
+    u32 po = pos_offset(a.set_blk0, a.set_pos0, s, m, b);
+    u32 k = (u32)x - po;
+    u32 e = (u32)a.o_pos[x] + a.o_depth[b];
+    a.keys[x] = ((u64)(q0 + k) << a.ebits) | e;
+    a.vals[x] = b;
+}
+MAP_KERNEL(endkey, EndKeyArgs)
+
+struct ElemBlkArgs { BatchView v; const u32 *o_set; const u32 *set_blk0; const u32 *set_pos0; u32 *elem_blk; };
+HD void elemblk_body(long long b, const ElemBlkArgs &a) {
+    u32 s = a.o_set[b];
+    u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
+    u32 po = pos_offset(a.set_blk0, a.set_pos0, s, m, (u32)b);
+    for (u32 k = 0; k < m; k++) a.elem_blk[po + k] = (u32)b;
+}
+MAP_KERNEL(elemblk, ElemBlkArgs)
+
+struct SegHeadArgs { const u64 *keys; u32 *seghead; int ebits; };
+HD void seghead_body(long long j, const SegHeadArgs &a) {
+    bool f = (j == 0) || (a.keys[j] >> a.ebits) != (a.keys[j - 1] >> a.ebits);
+    a.seghead[j] = f ? (u32)j : 0u;
+}
+MAP_KERNEL(seghead, SegHeadArgs)
+
+struct LinkArgs {
+    BatchView v; const u64 *keys; const u32 *vals; const u32 *seghead; const u32 *o_depth; int ebits;
+    u32 *succ_lo; u32 *succ_hi;
+};
+HD void link_body(long long j, const LinkArgs &a) {
+    u32 f = a.seghead[j];
+    if ((u32)j == f) return;
+    u64 mask = (1ull << a.ebits) - 1;
+    u32 k = (u32)(a.keys[j] >> a.ebits);
+    u32 n = LDG(a.v.seq_off + k + 1) - LDG(a.v.seq_off + k);
+    u64 e0 = a.keys[f] & mask;
+    if (e0 >= n) return; // csamsa.c:160: no block noticed in the first turn
+    u64 limit = (u64)n + (e0 - a.o_depth[a.vals[f]]); // csamsa.c:168
+    u64 e = a.keys[j] & mask;
+    if (e >= limit) return;
+    u32 prev = a.vals[j - 1], cur = a.vals[j];
+    ATOMIC_MIN(a.succ_lo + prev, cur);
+    ATOMIC_MAX(a.succ_hi + prev, cur);
+}
+MAP_KERNEL(link, LinkArgs)
+
+// next block and the gap to it: the smallest gap over the sequences (csamsa.c:199-207)
+struct GapArgs {
+    BatchView v; const u32 *succ_lo; const u32 *succ_hi; const u32 *o_depth; const u32 *o_set; const int *o_pos;
+    const u32 *set_blk0; const u32 *set_pos0; int max_interval; int *next; int *gap;
+};
+HD void gap_body(long long b, const GapArgs &a) {
+    u32 lo = a.succ_lo[b], hi = a.succ_hi[b];
+    a.gap[b] = 0;
+    if (lo == CSA_NONE || lo != hi) { a.next[b] = -1; return; }
+    u32 cur = lo;
+    u32 s = a.o_set[b];
+    u32 q0 = LDG(a.v.set_seq0 + s);
+    u32 m = LDG(a.v.set_seq0 + s + 1) - q0;
+    u32 pp = pos_offset(a.set_blk0, a.set_pos0, s, m, (u32)b), pc = pos_offset(a.set_blk0, a.set_pos0, s, m, cur);
+    long long iv = LLONG_MAX;
+    for (u32 k = 0; k < m; k++) {
+        long long count = 0;
+        int posc = a.o_pos[pc + k], posp = a.o_pos[pp + k];
+        if (posc < posp) count += (long long)(LDG(a.v.seq_off + q0 + k + 1) - LDG(a.v.seq_off + q0 + k));
+        count += (long long)posc - ((long long)posp + (long long)a.o_depth[b]);
+        if (count < iv) iv = count;
+    }
+    if (iv > (long long)a.max_interval) { a.next[b] = -1; return; }
+    a.next[b] = (int)cur;
+    a.gap[b] = (int)iv;
+}
+MAP_KERNEL(gap, GapArgs)
+
+// csamsa.c:185-233, literally, one thread per set (the walk is a chain of dependent steps)
+struct ChainArgs {
+    const u32 *set_blk0; const u32 *o_depth; const int *next; const int *gap;
+    int *size; int *total; int *interval; u32 *set_nchains; u32 *set_flags;
+};
+HD void chain_body(long long s, const ChainArgs &a) {
+    u32 b0 = a.set_blk0[s], b1 = a.set_blk0[s + 1];
+    u32 B = b1 - b0;
+    u32 mcs = B;
+    long long guard_max = 4ll * B + 16;
+    bool hang = false;
+    for (u32 b = b0; b < b1 && !hang; b++) {
+        if (a.total[b] == -1) continue;
+        a.size[b] = (int)a.o_depth[b];
+        u32 prev = b;
+        int cur = a.next[b];
+        long long guard = 0;
+        while (cur != -1) {
+            if (++guard > guard_max) { hang = true; break; }
+            int iv = a.gap[prev];
+            if (a.total[cur] > 0) {
+                a.size[b] += a.size[cur];
+                a.total[b] += a.total[cur];
+                a.interval[prev] = iv;
+                a.total[b] += iv;
+                a.size[cur] = (int)a.o_depth[cur];
+                a.total[cur] = -1;
+                mcs--;
+                break;
+            }
+            a.size[cur] = (int)a.o_depth[cur];
+            a.size[b] += a.size[cur];
+            a.interval[prev] = iv;
+            a.total[b] += iv;
+            a.total[cur] = -1;
+            mcs--;
+            prev = (u32)cur;
+            cur = a.next[cur];
+        }
+        a.total[b] += a.size[b];
+    }
+    a.set_nchains[s] = mcs;
+    if (hang) ATOMIC_MAX(a.set_flags + s, 2u);
+}
+MAP_KERNEL(chain, ChainArgs)
+
+// sortList (nodeslinkedlists.c:59): stable, by chain size, descending
+struct SizeKeyArgs { const u32 *o_set; const int *size; u64 *keys; u32 *vals; };
+HD void sizekey_body(long long b, const SizeKeyArgs &a) {
+    a.keys[b] = ((u64)a.o_set[b] << 32) | (u32)(0x7FFFFFFF - a.size[b]);
+    a.vals[b] = (u32)b;
+}
+MAP_KERNEL(sizekey, SizeKeyArgs)
+
+struct InvArgs { const u32 *order; u32 *inv; };
+HD void inv_body(long long i, const InvArgs &a) { a.inv[a.order[i]] = (u32)i; }
+MAP_KERNEL(inv, InvArgs)
+
+struct FinalArgs {
+    BatchView v; const u32 *order; const u32 *inv; const u32 *o_depth; const u32 *o_set; const int *o_pos;
+    const int *size; const int *total; const int *interval; const int *next;
+    const u32 *set_blk0; const u32 *set_pos0;
+    int *f_depth; int *f_size; int *f_total; int *f_interval; int *f_next; int *f_pos;
+};
+HD void final_body(long long i, const FinalArgs &a) {
+    u32 b = a.order[i];
+    u32 s = a.o_set[b];
+    u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
+    a.f_depth[i] = (int)a.o_depth[b];
+    a.f_size[i] = a.size[b];
+    a.f_total[i] = a.total[b];
+    a.f_interval[i] = a.interval[b];
+    int nx = a.next[b];
+    a.f_next[i] = nx < 0 ? -1 : (int)(a.inv[nx] - LDG(a.set_blk0 + s));
+    u32 src = pos_offset(a.set_blk0, a.set_pos0, s, m, b), dst = pos_offset(a.set_blk0, a.set_pos0, s, m, (u32)i);
+    for (u32 k = 0; k < m; k++) a.f_pos[dst + k] = a.o_pos[src + k];
+}
+MAP_KERNEL(final, FinalArgs)
+
+// getRotations (csamsa.c:311): the positions of the head of the sorted list; plus whether the
+// head chain bites its own tail (the reference then overruns blockLabel, nodeslinkedlists.c:161)
+struct RotArgs {
+    BatchView v; const u32 *set_blk0; const u32 *set_pos0; const int *f_pos; const int *f_next;
+    int *rotations; u32 *set_cyclic;
+};
+HD void rot_body(long long s, const RotArgs &a) {
+    u32 q0 = a.v.set_seq0[s], q1 = a.v.set_seq0[s + 1];
+    u32 b0 = a.set_blk0[s], b1 = a.set_blk0[s + 1];
+    a.set_cyclic[s] = 0;
+    if (b0 == b1) { for (u32 k = q0; k < q1; k++) a.rotations[k] = 0; return; }
+    u32 po = a.set_pos0[s];
+    for (u32 k = q0; k < q1; k++) a.rotations[k] = a.f_pos[po + (k - q0)];
+    u32 B = b1 - b0, steps = 0;
+    int cur = 0;
+    while (cur != -1 && steps <= B) { cur = a.f_next[b0 + cur]; steps++; }
+    if (cur != -1) a.set_cyclic[s] = 1;
+}
+MAP_KERNEL(rot, RotArgs)

@@ -1,0 +1,254 @@
+// prims.cuh -- hand-written device-wide primitives for sm_100a: prefix scans (sum / max over
+// u32) and a stable LSD radix sort of (u64 key, u32 value) pairs.  No CUB/Thrust.
+//
+// Radix sort pass (8-bit digit), HBM traffic per element: histogram reads the key (8 B), the
+// scatter reads key+value (12 B) and writes them (12 B) = 32 B.  Local ranks inside a 2048-key
+// tile come from warp match-any ballots (stable), per-warp digit counters live in shared memory.
+#pragma once
+#include "csa_common.cuh"
+
+struct ScanSum { HDM u32 id() { return 0u; } HDM u32 op(u32 a, u32 b) { return a + b; } };
+struct ScanMax { HDM u32 id() { return 0u; } HDM u32 op(u32 a, u32 b) { return a > b ? a : b; } };
+
+// scratch owned by the context; grown on demand
+struct PrimScratch {
+    DevMem block_sums[4]; // scan recursion levels
+    DevMem counts;        // radix digit counters [256][nblocks]
+};
+
+#ifdef CSA_EMU
+// ------------------------------- CPU emulation (tests only) -------------------------------
+template <class Op, bool INCLUSIVE>
+static int scan_u32(Exec &, PrimScratch &, const u32 *in, u32 *out, long long n, int = 0) {
+    Op o;
+    u32 run = o.id();
+    for (long long i = 0; i < n; i++) {
+        u32 v = in[i];
+        if (INCLUSIVE) { run = o.op(run, v); out[i] = run; }
+        else { out[i] = run; run = o.op(run, v); }
+    }
+    return 0;
+}
+
+static int radix_sort_pairs(Exec &, PrimScratch &, u64 *&keys, u32 *&vals, u64 *&keys_alt, u32 *&vals_alt,
+                            long long n, int begin_bit, int end_bit) {
+    if (n <= 1 || end_bit <= begin_bit) return 0;
+    u64 mask = (end_bit - begin_bit >= 64) ? ~0ull : (((1ull << (end_bit - begin_bit)) - 1) << begin_bit);
+    std::vector<long long> idx(n);
+    for (long long i = 0; i < n; i++) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](long long a, long long b) { return (keys[a] & mask) < (keys[b] & mask); });
+    for (long long i = 0; i < n; i++) { keys_alt[i] = keys[idx[i]]; vals_alt[i] = vals[idx[i]]; }
+    std::swap(keys, keys_alt);
+    std::swap(vals, vals_alt);
+    return 0;
+}
+#else
+// ------------------------------------ CUDA ----------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+template <class Op>
+__device__ __forceinline__ u32 warp_scan_incl(u32 v, Op o) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v = o.op(t, v);
+    }
+    return v;
+}
+
+// exclusive prefix of per-thread aggregates across the block; returns block total in `total`
+template <class Op>
+__device__ __forceinline__ u32 block_scan_excl(u32 agg, u32 &total, Op o, u32 *smem /*>=33*/) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = warp_scan_incl(agg, o);
+    if (lane == 31) smem[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = (lane < (SCAN_THREADS / 32)) ? smem[lane] : o.id();
+        u32 wi = warp_scan_incl(w, o);
+        smem[lane] = wi;
+    }
+    __syncthreads();
+    u32 warp_prefix = warp ? smem[warp - 1] : o.id();
+    total = smem[SCAN_THREADS / 32 - 1];
+    u32 excl_in_warp = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl_in_warp = o.id();
+    __syncthreads();
+    return o.op(warp_prefix, excl_in_warp);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const u32 *__restrict__ in, u32 *__restrict__ sums, long long n) {
+    __shared__ u32 sm[33];
+    Op o;
+    long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    u32 agg = o.id();
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++)
+        if (base + j < n) agg = o.op(agg, in[base + j]);
+    u32 total;
+    block_scan_excl(agg, total, o, sm);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+template <class Op, bool INCLUSIVE>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const u32 *in, u32 *out, // in may alias out
+                                                             const u32 *__restrict__ block_prefix, long long n) {
+    __shared__ u32 sm[33];
+    Op o;
+    long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    u32 v[SCAN_ITEMS];
+    u32 agg = o.id();
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        v[j] = (base + j < n) ? in[base + j] : o.id();
+        agg = o.op(agg, v[j]);
+    }
+    u32 total;
+    u32 excl = block_scan_excl(agg, total, o, sm);
+    u32 run = block_prefix ? o.op(block_prefix[blockIdx.x], excl) : excl;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        if (INCLUSIVE) { run = o.op(run, v[j]); if (base + j < n) out[base + j] = run; }
+        else { if (base + j < n) out[base + j] = run; run = o.op(run, v[j]); }
+    }
+}
+
+// out may alias in
+template <class Op, bool INCLUSIVE>
+static int scan_u32(Exec &ex, PrimScratch &ps, const u32 *in, u32 *out, long long n, int level = 0) {
+    if (n <= 0) return 0;
+    long long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (nb == 1) {
+        k_scan_apply<Op, INCLUSIVE><<<1, SCAN_THREADS, 0, ex.stream>>>(in, out, nullptr, n);
+        ex.launches++;
+        return 0;
+    }
+    if (level >= 4) CSA_FAIL(-2, "scan too large");
+    int rc = dev_alloc(ps.block_sums[level], sizeof(u32) * (size_t)nb);
+    if (rc) return rc;
+    u32 *sums = (u32 *)ps.block_sums[level].p;
+    k_scan_reduce<Op><<<(unsigned)nb, SCAN_THREADS, 0, ex.stream>>>(in, sums, n);
+    ex.launches++;
+    rc = scan_u32<Op, false>(ex, ps, sums, sums, nb, level + 1);
+    if (rc) return rc;
+    k_scan_apply<Op, INCLUSIVE><<<(unsigned)nb, SCAN_THREADS, 0, ex.stream>>>(in, out, sums, n);
+    ex.launches++;
+    return 0;
+}
+
+// ---- radix sort -----------------------------------------------------------------------------
+#define RS_THREADS 256
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_ITEMS 8
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+#define RS_BITS 8
+#define RS_BINS 256
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64 *__restrict__ keys, u32 *__restrict__ counts,
+                                                        long long n, int shift, unsigned nblocks) {
+    __shared__ u32 h[RS_WARPS][RS_BINS];
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long base = (long long)blockIdx.x * RS_TILE + (long long)warp * (RS_ITEMS * 32) + lane;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        long long i = base + j * 32;
+        if (i < n) {
+            unsigned d = (unsigned)(keys[i] >> shift) & (RS_BINS - 1);
+            atomicAdd(&h[warp][d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
+        u32 s = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) s += h[w][d];
+        counts[(size_t)d * nblocks + blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict__ keys, const u32 *__restrict__ vals,
+                                                           u64 *__restrict__ keys_out, u32 *__restrict__ vals_out,
+                                                           const u32 *__restrict__ offsets, long long n, int shift,
+                                                           unsigned nblocks) {
+    __shared__ u32 h[RS_WARPS][RS_BINS];
+    __shared__ u32 gbase[RS_BINS];
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    long long base = (long long)blockIdx.x * RS_TILE + (long long)warp * (RS_ITEMS * 32) + lane;
+    u64 k[RS_ITEMS];
+    u32 v[RS_ITEMS];
+    u32 rank[RS_ITEMS];
+    unsigned dig[RS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        long long i = base + j * 32;
+        bool ok = i < n;
+        k[j] = ok ? keys[i] : 0;
+        v[j] = ok ? vals[i] : 0;
+        dig[j] = ok ? ((unsigned)(k[j] >> shift) & (RS_BINS - 1)) : RS_BINS; // RS_BINS = "no key"
+    }
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        unsigned d = dig[j];
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        u32 before = 0;
+        if (d < RS_BINS) before = h[warp][d];
+        __syncwarp();
+        if (d < RS_BINS && (peers & lt) == 0) h[warp][d] = before + __popc(peers);
+        __syncwarp();
+        rank[j] = before + __popc(peers & lt);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            u32 t = h[w][d];
+            h[w][d] = run;
+            run += t;
+        }
+        gbase[d] = offsets[(size_t)d * nblocks + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        unsigned d = dig[j];
+        if (d < RS_BINS) {
+            u32 pos = gbase[d] + h[warp][d] + rank[j];
+            keys_out[pos] = k[j];
+            vals_out[pos] = v[j];
+        }
+    }
+}
+
+// Stable LSD sort on key bits [begin_bit, end_bit).  keys/vals and the _alt buffers are swapped
+// as passes go; on return keys/vals point at the sorted data.
+static int radix_sort_pairs(Exec &ex, PrimScratch &ps, u64 *&keys, u32 *&vals, u64 *&keys_alt, u32 *&vals_alt,
+                            long long n, int begin_bit, int end_bit) {
+    if (n <= 1 || end_bit <= begin_bit) return 0;
+    if (n >= (1ll << 32)) CSA_FAIL(-2, "radix sort: more than 2^32 elements");
+    unsigned nb = (unsigned)((n + RS_TILE - 1) / RS_TILE);
+    int rc = dev_alloc(ps.counts, sizeof(u32) * (size_t)RS_BINS * nb);
+    if (rc) return rc;
+    u32 *counts = (u32 *)ps.counts.p;
+    for (int shift = begin_bit; shift < end_bit; shift += RS_BITS) {
+        k_rs_hist<<<nb, RS_THREADS, 0, ex.stream>>>(keys, counts, n, shift, nb);
+        ex.launches++;
+        rc = scan_u32<ScanSum, false>(ex, ps, counts, counts, (long long)RS_BINS * nb);
+        if (rc) return rc;
+        k_rs_scatter<<<nb, RS_THREADS, 0, ex.stream>>>(keys, vals, keys_alt, vals_alt, counts, n, shift, nb);
+        ex.launches++;
+        u64 *tk = keys; keys = keys_alt; keys_alt = tk;
+        u32 *tv = vals; vals = vals_alt; vals_alt = tv;
+    }
+    return 0;
+}
+#endif

@@ -1,0 +1,121 @@
+/*
+ * csa_gpu.h -- C ABI of the B200 rotation finder (libcsa_gpu.so).
+ *
+ * Drop-in boundary for fjdf/CSA's `./CSA R <multi-fasta>` hot path.  In the reference that
+ * path is two calls on globals (csamsa.c:599 and :610):
+ *
+ *     tree = buildGeneralizedTree();   // gencycsuffixtrees.c:418  generalized cyclic suffix tree
+ *     analyzeTree();                   // csamsa.c:324  collectNodes / removeSuffixNodes /
+ *                                      //   removeNonUniqueNodes / collectNodeChains / getRotations
+ *
+ * whose inputs are `numberofseqs`, `texts`, `textsizes` (csamsa.h:8-11) and whose outputs are
+ * `rotations` (csamsa.h:12) and the sorted `blockslist` (csamsa.c:30) that
+ * saveRotatedSequences (csamsa.c:421) and createImageAndShowResults (csamsa.c:361) print.
+ * csa_gpu_find_rotations() below replaces exactly those two calls; the batch entry points
+ * run many independent sequence sets in one pass and are what bench.py and the sharded
+ * (one process per GPU) driver use.  INTEGRATION.md shows the patch to csamsa.c.
+ *
+ * Plain pointers and sizes only.  Every function returns CSA_GPU_OK (0) or a negative
+ * CSA_GPU_E* code; csa_gpu_last_error() gives the text.  There is no CPU fallback: without
+ * a CUDA device csa_gpu_create fails with CSA_GPU_ENODEV.
+ */
+#ifndef CSA_GPU_H
+#define CSA_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSA_GPU_ABI_VERSION 1
+
+/* return codes */
+#define CSA_GPU_OK 0
+#define CSA_GPU_ENODEV (-1)   /* no usable CUDA device                      */
+#define CSA_GPU_EINVAL (-2)   /* bad argument                               */
+#define CSA_GPU_ENOMEM (-3)   /* device or host allocation failed           */
+#define CSA_GPU_ECUDA (-4)    /* a CUDA call or kernel failed               */
+#define CSA_GPU_ESTATE (-5)   /* call order (run before upload, ...)        */
+
+/* per-set status (csa_gpu_set_info.status).  The first three mirror the reference's exits. */
+#define CSA_SET_OK 0
+#define CSA_SET_NO_COMMON 1      /* csamsa.c:330 "No common subsequences found"              */
+#define CSA_SET_NO_UNIQUE 2      /* csamsa.c:346 "No unique subsequences found"              */
+#define CSA_SET_DEGENERATE 3     /* a whole rotation of one sequence occurs in all the others:
+                                    the reference walks off its tree there (undefined)       */
+#define CSA_SET_NONTERMINATING 4 /* the reference loops forever in collectNodeChains
+                                    (csamsa.c:197) on a block cycle whose gaps sum to <= 0   */
+
+/* flags for csa_gpu_batch_run */
+#define CSA_GPU_FLAG_STATS 1u /* also count "nodes found"/"nodes left" (csamsa.c:332,338)    */
+
+typedef struct csa_gpu_ctx csa_gpu_ctx;
+
+typedef struct csa_gpu_set_info {
+    int status;           /* CSA_SET_*                                                       */
+    int nseqs;            /* sequences in the set                                            */
+    int count_collected;  /* csamsa.c:332 (-1 unless CSA_GPU_FLAG_STATS)                     */
+    int count_suffixfree; /* csamsa.c:338 (-1 unless CSA_GPU_FLAG_STATS)                     */
+    int count_unique;     /* csamsa.c:348 == nblocks                                         */
+    int count_chains;     /* csamsa.c:354                                                    */
+    int nblocks;          /* blocks in the final sorted blockslist                           */
+    int chain_is_cyclic;  /* 1: the head chain loops back on itself; the reference then
+                             overruns blockLabel's buffer (nodeslinkedlists.c:161) after it
+                             has written -Rotated.fasta                                      */
+    long long block_offset; /* first block of this set in the batch-wide block arrays        */
+} csa_gpu_set_info;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int csa_gpu_create(int device, csa_gpu_ctx **ctx);
+void csa_gpu_destroy(csa_gpu_ctx *ctx);
+const char *csa_gpu_last_error(void);
+int csa_gpu_abi_version(void);
+
+/* ---- batch of independent sequence sets ---------------------------------------------- */
+/* Sequences are given flat: sequence i has texts[i][0..textsizes[i]) -- upper-case IUPAC
+ * letters exactly as the reference loader stores them (csamsa.c:517-523); anything that is
+ * not A/C/G/T is one and the same fifth letter (gencycsuffixtrees.c:283).  Set s owns
+ * sequences [set_start[s], set_start[s+1]).  Sequences that are rotations of an earlier one
+ * must already have been dropped (the host layer does it, as gencycsuffixtrees.c:518). */
+int csa_gpu_batch_upload(csa_gpu_ctx *ctx, int nsets, const int *set_start,
+                         const char *const *texts, const int *textsizes);
+/* same, from one contiguous buffer: sequence i is text[text_start[i] .. text_start[i+1]) */
+int csa_gpu_batch_upload_flat(csa_gpu_ctx *ctx, int nsets, const int *set_start,
+                              const char *text, const long long *text_start);
+/* all kernels; inputs and outputs stay in HBM.  max_interval: csamsa.c:27 (INT_MAX on R). */
+int csa_gpu_batch_run(csa_gpu_ctx *ctx, int max_interval, unsigned flags);
+/* rotations: one int per sequence of the batch (csamsa.h:12); info: one per set. */
+int csa_gpu_batch_download(csa_gpu_ctx *ctx, int *rotations, csa_gpu_set_info *info);
+/* total number of blocks of the last run, for sizing the arrays below */
+long long csa_gpu_batch_num_blocks(csa_gpu_ctx *ctx);
+/* the sorted blockslist of every set (set s: blocks [block_offset, block_offset+nblocks)):
+ * depth/size/totalsize/interval as in nodeslinkedlists.h:4-13, next = index of nextblock
+ * within the set's list or -1, positions: per block, one int per sequence of its set, stored
+ * at positions[position_offset(block)] where position_offset is the running sum of nseqs.
+ * Any pointer may be NULL. */
+int csa_gpu_batch_blocks(csa_gpu_ctx *ctx, int *depth, int *size, int *totalsize, int *interval,
+                         int *next, int *positions);
+/* upload + run + download in one call with host buffers (what bench.py times as e2e) */
+int csa_gpu_batch_rotations(csa_gpu_ctx *ctx, int nsets, const int *set_start,
+                            const char *const *texts, const int *textsizes, int max_interval,
+                            unsigned flags, int *rotations, csa_gpu_set_info *info);
+
+/* ---- the reference's call, one set ---------------------------------------------------- */
+/* Replaces buildGeneralizedTree()+analyzeTree(): fills rotations[numberofseqs] and *info. */
+int csa_gpu_find_rotations(csa_gpu_ctx *ctx, int numberofseqs, const char *const *texts,
+                           const int *textsizes, int max_interval, unsigned flags, int *rotations,
+                           csa_gpu_set_info *info);
+
+/* ---- introspection used by tests and bench.py ----------------------------------------- */
+/* generalized cyclic suffix array + LCP of the last run, global suffix index = offset of the
+ * sequence in the batch + position; n = total number of bases.  Either pointer may be NULL. */
+long long csa_gpu_batch_num_suffixes(csa_gpu_ctx *ctx);
+int csa_gpu_batch_suffix_array(csa_gpu_ctx *ctx, unsigned *sa, int *lcp);
+/* device time of the stages of the last run, in milliseconds (CUDA events on the run's
+ * stream): [0] suffix sort, [1] LCP, [2] block discovery, [3] block order, [4] chaining,
+ * [5] whole run; launches = kernels launched by the last run. */
+int csa_gpu_batch_timings(csa_gpu_ctx *ctx, float ms[6], long long *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
