@@ -62,6 +62,7 @@ def _load(path):
     lib.csa_gpu_destroy.argtypes = [vp]
     lib.csa_gpu_destroy.restype = None
     lib.csa_gpu_last_error.restype = C.c_char_p
+    lib.csa_gpu_set_stream.argtypes = [vp, vp]
     lib.csa_gpu_batch_upload_flat.argtypes = [vp, i, ip, C.c_char_p, C.POINTER(C.c_longlong)]
     lib.csa_gpu_batch_run.argtypes = [vp, i, C.c_uint]
     lib.csa_gpu_batch_download.argtypes = [vp, ip, C.POINTER(SetInfo)]
@@ -74,6 +75,10 @@ def _load(path):
     lib.csa_gpu_batch_num_suffixes.restype = C.c_longlong
     lib.csa_gpu_batch_suffix_array.argtypes = [vp, C.POINTER(C.c_uint), ip]
     lib.csa_gpu_batch_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
+    lib.csa_gpu_profile_enable.argtypes = [vp, i]
+    lib.csa_gpu_profile_count.argtypes = [vp]
+    lib.csa_gpu_profile_get.argtypes = [vp, i, C.c_char_p, i, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double)]
     return lib
 
 
@@ -129,6 +134,9 @@ class RotationFinder:
         except Exception:
             pass
 
+    def set_stream(self, cuda_stream_handle: int):
+        self._check(self.lib.csa_gpu_set_stream(self.ctx, C.c_void_p(cuda_stream_handle)))
+
     def _check(self, rc):
         if rc != 0:
             raise CsaGpuError(rc, self.lib.csa_gpu_last_error().decode(errors="replace"))
@@ -170,6 +178,19 @@ class RotationFinder:
         launches = C.c_longlong()
         self._check(self.lib.csa_gpu_batch_timings(self.ctx, ms, C.byref(launches)))
         return list(ms), launches.value
+
+    def profile_enable(self, on: bool):
+        self._check(self.lib.csa_gpu_profile_enable(self.ctx, int(on)))
+
+    def profile(self):
+        """rows of (kernel, launches, ms, algorithmic bytes) of the last profiled run"""
+        rows = []
+        for j in range(self.lib.csa_gpu_profile_count(self.ctx)):
+            name = C.create_string_buffer(64)
+            n, ms, by = C.c_longlong(), C.c_double(), C.c_double()
+            self._check(self.lib.csa_gpu_profile_get(self.ctx, j, name, 64, C.byref(n), C.byref(ms), C.byref(by)))
+            rows.append((name.value.decode(), n.value, ms.value, by.value))
+        return rows
 
     # ---- whole calls ----
     def find_rotations_batch(self, sets: Sequence[Sequence[bytes]], max_interval: int = INT_MAX,

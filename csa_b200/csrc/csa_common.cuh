@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <climits>
+#include <vector>
 
 typedef uint32_t u32;
 typedef uint64_t u64;
@@ -70,10 +71,52 @@ extern thread_local char g_csa_err[512];
 #endif
 
 // ---- execution context ------------------------------------------------------------------
+// Optional per-kernel timing: when Exec::prof is set every launch is bracketed by two CUDA events
+// on the launching stream; csa_gpu_profile_* reports, per kernel name, launches, device time and
+// the ALGORITHMIC bytes the launches moved (items x the per-item figure in DESIGN.md).  bench.py
+// turns it on for a separate pass after the timed steps (roofline.achieved), never inside them.
+struct ProfRec {
+    const char *name;
+    double bytes;
+#ifndef CSA_EMU
+    cudaEvent_t a, b;
+#endif
+};
+struct Profiler {
+#ifdef CSA_EMU
+    int unused;
+#else
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t pool_used = 0;
+    cudaEvent_t get() {
+        if (pool_used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[pool_used++];
+    }
+#endif
+};
 struct Exec {
     csaStream_t stream;
     long long launches; // kernels launched since the last reset (reported as gpu_launches)
+    Profiler *prof;
 };
+#ifdef CSA_EMU
+#define PROF_BEGIN(ex, nm, by) do { (void)(ex); } while (0)
+#define PROF_END(ex) do { (void)(ex); } while (0)
+#else
+#define PROF_BEGIN(ex, nm, by)                                                    \
+    do {                                                                          \
+        if ((ex).prof) {                                                          \
+            ProfRec r__;                                                          \
+            r__.name = (nm); r__.bytes = (double)(by);                            \
+            r__.a = (ex).prof->get(); r__.b = (ex).prof->get();                   \
+            cudaEventRecord(r__.a, (ex).stream);                                  \
+            (ex).prof->recs.push_back(r__);                                       \
+        }                                                                         \
+    } while (0)
+#define PROF_END(ex)                                                              \
+    do { if ((ex).prof) cudaEventRecord((ex).prof->recs.back().b, (ex).stream); } while (0)
+#endif
 
 // ---- device memory ----------------------------------------------------------------------
 struct DevMem {
@@ -179,20 +222,22 @@ static inline int exec_sync(Exec &ex) {
 // MAP_KERNEL(name, Args) turns `name_body(long long i, const Args &a)` into a named __global__
 // kernel k_name (so ncu lists it by name) plus launch_name(ex, n, args).
 #ifdef CSA_EMU
-#define MAP_KERNEL(name, Args)                                          \
+#define MAP_KERNEL(name, Args, BYTES_PER_ITEM)                          \
     static inline void launch_##name(Exec &ex, long long n, Args a) {   \
         (void)ex;                                                       \
         for (long long i = 0; i < n; i++) name##_body(i, a);            \
     }
 #else
-#define MAP_KERNEL(name, Args)                                                            \
+#define MAP_KERNEL(name, Args, BYTES_PER_ITEM)                                            \
     __global__ void __launch_bounds__(256) k_##name(long long n, Args a) {                \
         long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;                   \
         if (i < n) name##_body(i, a);                                                     \
     }                                                                                     \
     static inline void launch_##name(Exec &ex, long long n, Args a) {                     \
         if (n <= 0) return;                                                               \
+        PROF_BEGIN(ex, "k_" #name, (double)n * (BYTES_PER_ITEM));                         \
         k_##name<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);               \
+        PROF_END(ex);                                                                     \
         ex.launches++;                                                                    \
     }
 #endif

@@ -5,6 +5,7 @@
 #include "pipeline.cuh"
 #include "../../include/csa_gpu.h"
 #include <vector>
+#include <string>
 #include <new>
 
 thread_local char g_csa_err[512] = "";
@@ -28,6 +29,7 @@ struct StageTimer {
 struct csa_gpu_ctx {
     int device = 0;
     Exec ex{};
+    csaStream_t own_stream{};
     PrimScratch ps;
     StageTimer tm;
     // ---- batch description (host) ----
@@ -50,6 +52,10 @@ struct csa_gpu_ctx {
     DevMem next, gap, size, total, interval, inv, f_depth, f_size, f_total, f_interval, f_next, f_pos, rotations;
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    // per-kernel profile of the last run (csa_gpu_profile_*)
+    Profiler prof;
+    struct ProfSum { std::string name; long long launches; double ms, bytes; };
+    std::vector<ProfSum> prof_sum;
 };
 
 template <class T> static inline T *P(DevMem &m) { return (T *)m.p; }
@@ -84,11 +90,24 @@ extern "C" int csa_gpu_create(int device, csa_gpu_ctx **out) {
     if (!c) CSA_FAIL(CSA_GPU_ENOMEM, "out of host memory");
     c->device = device;
 #ifndef CSA_EMU
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->ex.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->ex.stream = c->own_stream;
     for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreate(&c->tm.ev[i]));
     c->tm.ok = true;
 #endif
     *out = c;
+    return CSA_GPU_OK;
+}
+
+// run on the caller's stream (e.g. torch's current stream) instead of the context's own
+extern "C" int csa_gpu_set_stream(csa_gpu_ctx *c, void *stream) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+#ifndef CSA_EMU
+    CUDA_TRY(cudaStreamSynchronize(c->ex.stream));
+    c->ex.stream = stream ? (cudaStream_t)stream : c->own_stream;
+#else
+    (void)stream;
+#endif
     return CSA_GPU_OK;
 }
 
@@ -112,7 +131,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
 #ifndef CSA_EMU
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->tm.ok) for (int i = 0; i < 8; i++) cudaEventDestroy(c->tm.ev[i]);
-    cudaStreamDestroy(c->ex.stream);
+    cudaStreamDestroy(c->own_stream);
 #else
     free(c->pinned);
 #endif
@@ -449,6 +468,40 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
 #endif
     c->launches = ex.launches;
     c->ran = true;
+#ifndef CSA_EMU
+    if (ex.prof) { // fold the event pairs of this run into per-kernel sums
+        c->prof_sum.clear();
+        for (ProfRec &r : c->prof.recs) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            size_t j = 0;
+            while (j < c->prof_sum.size() && c->prof_sum[j].name != r.name) j++;
+            if (j == c->prof_sum.size()) c->prof_sum.push_back({r.name, 0, 0.0, 0.0});
+            c->prof_sum[j].launches++; c->prof_sum[j].ms += ms; c->prof_sum[j].bytes += r.bytes;
+        }
+        c->prof.recs.clear();
+        c->prof.pool_used = 0;
+    }
+#endif
+    return CSA_GPU_OK;
+}
+
+extern "C" int csa_gpu_profile_enable(csa_gpu_ctx *c, int on) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    c->ex.prof = on ? &c->prof : nullptr;
+    if (!on) c->prof_sum.clear();
+    return CSA_GPU_OK;
+}
+
+extern "C" int csa_gpu_profile_count(csa_gpu_ctx *c) { return c ? (int)c->prof_sum.size() : 0; }
+
+extern "C" int csa_gpu_profile_get(csa_gpu_ctx *c, int i, char *name, int name_cap, long long *launches, double *ms,
+                                   double *bytes) {
+    if (!c || i < 0 || i >= (int)c->prof_sum.size()) CSA_FAIL(CSA_GPU_EINVAL, "no such profile row");
+    if (name && name_cap > 0) snprintf(name, (size_t)name_cap, "%s", c->prof_sum[i].name.c_str());
+    if (launches) *launches = c->prof_sum[i].launches;
+    if (ms) *ms = c->prof_sum[i].ms;
+    if (bytes) *bytes = c->prof_sum[i].bytes;
     return CSA_GPU_OK;
 }
 

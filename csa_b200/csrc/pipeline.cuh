@@ -76,7 +76,7 @@ HD void encode_body(long long i, const EncodeArgs &a) {
     a.v.code[g] = (unsigned char)code_of_letter(a.raw[g]);
     a.v.seqof[g] = upper_bound_u32(a.v.seq_off, a.v.M + 1, g) - 1;
 }
-MAP_KERNEL(encode, EncodeArgs)
+MAP_KERNEL(encode, EncodeArgs, 6)
 
 // one thread per 32-base word of the doubled text: sequence k occupies bases
 // [dbl_off[k], dbl_off[k+1]) = s_k s_k s_k... so that any window p..p+n+63 reads without wrap
@@ -97,7 +97,7 @@ HD void pack_body(long long w, const PackArgs &a) {
     a.v.p2[w] = w2;
     a.v.pm[w] = wm;
 }
-MAP_KERNEL(pack, PackArgs)
+MAP_KERNEL(pack, PackArgs, 44)
 
 // ---- stage 1: suffix array by prefix doubling --------------------------------------------------
 struct InitKeyArgs { BatchView v; u64 *keys; u32 *vals; };
@@ -114,7 +114,7 @@ HD void initkey_body(long long i, const InitKeyArgs &a) {
     a.keys[g] = key;
     a.vals[g] = g;
 }
-MAP_KERNEL(initkey, InitKeyArgs)
+MAP_KERNEL(initkey, InitKeyArgs, 29)
 
 // head[i] = i where a new group of equal keys starts, else 0 (max-scanned afterwards)
 struct FlagArgs { const u64 *keys; u32 *head; u32 *ngroups; };
@@ -123,11 +123,11 @@ HD void flag_body(long long i, const FlagArgs &a) {
     a.head[i] = f ? (u32)i : 0u;
     if (f) ATOMIC_ADD(a.ngroups, 1u);
 }
-MAP_KERNEL(flag, FlagArgs)
+MAP_KERNEL(flag, FlagArgs, 12)
 
 struct SetRankArgs { const u32 *sa; const u32 *head; u32 *rank; };
 HD void setrank_body(long long i, const SetRankArgs &a) { a.rank[a.sa[i]] = a.head[i]; }
-MAP_KERNEL(setrank, SetRankArgs)
+MAP_KERNEL(setrank, SetRankArgs, 12)
 
 // key of the doubling round: (rank of the first h letters, rank of the next h letters)
 struct Key2Args { BatchView v; const u32 *sa; const u32 *rank; u64 *keys; u32 h; int nbits; };
@@ -136,7 +136,7 @@ HD void key2_body(long long i, const Key2Args &a) {
     u32 r1 = LDG(a.rank + g), r2 = LDG(a.rank + cyc_add(a.v, g, a.h));
     a.keys[i] = ((u64)r1 << a.nbits) | r2;
 }
-MAP_KERNEL(key2, Key2Args)
+MAP_KERNEL(key2, Key2Args, 24)
 
 // ---- stage 2: LCP of neighbouring suffixes, capped at the shorter rotation -------------------------
 // gencycsuffixtrees.c:500: a path of the tree ends after textsize letters.
@@ -191,7 +191,7 @@ HD void lcp_body(long long i, const LcpArgs &a) {
     }
     a.lcp[i] = t < cap ? t : cap;
 }
-MAP_KERNEL(lcp, LcpArgs)
+MAP_KERNEL(lcp, LcpArgs, 12)
 
 // ---- stage 3: common blocks ------------------------------------------------------------------------
 // R[l] = smallest r such that SA[l..r] holds a suffix of every sequence of the set (>= end of the
@@ -205,7 +205,7 @@ HD void colorkey_body(long long i, const ColorKeyArgs &a) {
     a.keys[i] = k - LDG(a.v.set_seq0 + LDG(a.v.seq_set + k));
     a.vals[i] = (u32)i;
 }
-MAP_KERNEL(colorkey, ColorKeyArgs)
+MAP_KERNEL(colorkey, ColorKeyArgs, 20)
 
 // after the sort: vals = SA indices ordered by (colour, index).  cover[i] (read at i+1) = next
 // index of the same sequence; cover[set start] collects the latest first occurrence.
@@ -224,7 +224,7 @@ HD void next_body(long long j, const NextArgs &a) {
     bool first = (j == 0) || LDG(a.v.seqof + a.sa[a.vals[j - 1]]) != k;
     if (first) ATOMIC_MAX(a.firstmax + s, i);
 }
-MAP_KERNEL(next, NextArgs)
+MAP_KERNEL(next, NextArgs, 16)
 
 struct CoverArgs { BatchView v; const u32 *sa; const u32 *nxt; const u32 *firstmax; u32 *cover; };
 HD void cover_body(long long i, const CoverArgs &a) {
@@ -232,7 +232,7 @@ HD void cover_body(long long i, const CoverArgs &a) {
     u32 s0 = LDG(a.v.set_base0 + s);
     a.cover[i] = ((u32)i == s0) ? a.firstmax[s] : a.nxt[i - 1];
 }
-MAP_KERNEL(cover, CoverArgs)
+MAP_KERNEL(cover, CoverArgs, 16)
 
 // blocks: LCP intervals of exactly m suffixes, one of every sequence, that cannot be extended to
 // the left by one and the same letter (csamsa.c:64,80,283).  One thread per left border.
@@ -271,7 +271,7 @@ HD void blockfind_body(long long i, const BlockFindArgs &a) {
     a.isblock[lb] = 1;
     a.depth[lb] = inner;
 }
-MAP_KERNEL(blockfind, BlockFindArgs)
+MAP_KERNEL(blockfind, BlockFindArgs, 16)
 
 // a whole rotation of the shortest sequence occurs in every sequence: the reference walks off its
 // tree (undefined behaviour).  Maximal runs of lcp >= nmin that hold every sequence.
@@ -287,7 +287,7 @@ HD void degen_body(long long i, const DegenArgs &a) {
     while (rb + 1 < s1 && a.lcp[rb + 1] >= nmin) rb++;
     if (rb >= a.R[lb]) ATOMIC_MAX(a.set_flags + s, 1u);
 }
-MAP_KERNEL(degen, DegenArgs)
+MAP_KERNEL(degen, DegenArgs, 12)
 
 // compaction of the block borders; blocks come out in SA order, i.e. grouped by set
 struct BlockEmitArgs {
@@ -303,7 +303,7 @@ HD void blockemit_body(long long i, const BlockEmitArgs &a) {
     a.blk_set[b] = s;
     ATOMIC_ADD(a.set_nblocks + s, 1u);
 }
-MAP_KERNEL(blockemit, BlockEmitArgs)
+MAP_KERNEL(blockemit, BlockEmitArgs, 8)
 
 // ---- stage 4: order of the block list ----------------------------------------------------------------
 // insertSortedItem (nodeslinkedlists.c:36) keeps the list by depth, descending, and puts a block
@@ -318,7 +318,7 @@ HD void seq0flag_body(long long i, const Seq0FlagArgs &a) {
     u32 k = LDG(a.v.seqof + a.sa[i]);
     a.flag[i] = (k == LDG(a.v.set_seq0 + LDG(a.v.seq_set + k))) ? 1u : 0u;
 }
-MAP_KERNEL(seq0flag, Seq0FlagArgs)
+MAP_KERNEL(seq0flag, Seq0FlagArgs, 12)
 
 struct Seq0EmitArgs { BatchView v; const u32 *sa; const u32 *flag; const u32 *idx0; u32 *sa0; u32 *saidx0; u32 *leaf_set; };
 HD void seq0emit_body(long long i, const Seq0EmitArgs &a) {
@@ -330,7 +330,7 @@ HD void seq0emit_body(long long i, const Seq0EmitArgs &a) {
     a.saidx0[t] = (u32)i;
     a.leaf_set[t] = LDG(a.v.seq_set + k);
 }
-MAP_KERNEL(seq0emit, Seq0EmitArgs)
+MAP_KERNEL(seq0emit, Seq0EmitArgs, 8)
 
 struct Seq0View {
     u32 N0;
@@ -347,7 +347,7 @@ HD void lcp0_body(long long t, const Lcp0Args &a) {
     for (u32 j = a.saidx0[t - 1] + 1; j <= a.saidx0[t]; j++) { u32 l = a.lcp[j]; if (l < mn) mn = l; }
     a.lcp0[t] = mn;
 }
-MAP_KERNEL(lcp0, Lcp0Args)
+MAP_KERNEL(lcp0, Lcp0Args, 12)
 
 // nearest smaller / smaller-or-equal values around every border t (z0 < t < z1) of the set
 struct AnsvArgs { Seq0View q; u32 *psv; u32 *nsv; u32 *pse; };
@@ -366,7 +366,7 @@ HD void ansv_body(long long ti, const AnsvArgs &a) {
     while (j < z1 && a.q.lcp0[j] >= v) j++;
     a.nsv[t] = j; // z1 = none
 }
-MAP_KERNEL(ansv, AnsvArgs)
+MAP_KERNEL(ansv, AnsvArgs, 16)
 
 // Node numbering: internal node = its representative border t (the leftmost border of the node
 // whose value is the node's depth), leaf t = N0 + t.  parent[] of both kinds; the root points at
@@ -403,7 +403,7 @@ HD void tree_body(long long x, const TreeArgs &a) {
         a.minpos[x] = a.sa0[t];
     }
 }
-MAP_KERNEL(tree, TreeArgs)
+MAP_KERNEL(tree, TreeArgs, 24)
 
 // first occurrence of every node: each leaf climbs while it lowers the minimum
 struct MinposArgs { u32 N0; const u32 *parent; u32 *minpos; };
@@ -418,7 +418,7 @@ HD void minpos_body(long long t, const MinposArgs &a) {
         p = a.parent[x];
     }
 }
-MAP_KERNEL(minpos, MinposArgs)
+MAP_KERNEL(minpos, MinposArgs, 12)
 
 // children grouped by parent and ordered by first occurrence: sort key (parent, minpos)
 struct ChildKeyArgs { u32 N0; const u32 *parent; const u32 *minpos; u64 *keys; u32 *vals; };
@@ -429,7 +429,7 @@ HD void childkey_body(long long x, const ChildKeyArgs &a) {
     a.keys[x] = live ? (((u64)p << 32) | a.minpos[x]) : ~0ull;
     a.vals[x] = (u32)x;
 }
-MAP_KERNEL(childkey, ChildKeyArgs)
+MAP_KERNEL(childkey, ChildKeyArgs, 20)
 
 struct BeforeArgs { const u64 *keys; const u32 *vals; const u32 *size; u32 *val; u32 *up; const u32 *parent; };
 HD void before_body(long long j, const BeforeArgs &a) {
@@ -442,7 +442,7 @@ HD void before_body(long long j, const BeforeArgs &a) {
     a.val[x] = sum;
     a.up[x] = p;
 }
-MAP_KERNEL(before, BeforeArgs)
+MAP_KERNEL(before, BeforeArgs, 24)
 
 struct JumpArgs { const u32 *val; const u32 *up; u32 *val2; u32 *up2; };
 HD void jump_body(long long x, const JumpArgs &a) {
@@ -450,7 +450,7 @@ HD void jump_body(long long x, const JumpArgs &a) {
     a.val2[x] = a.val[x] + a.val[u];
     a.up2[x] = a.up[u];
 }
-MAP_KERNEL(jump, JumpArgs)
+MAP_KERNEL(jump, JumpArgs, 16)
 
 // per block: its sort keys and its positions (one per sequence of the set)
 struct BlockKeyArgs {
@@ -473,7 +473,7 @@ HD void blockkey_body(long long b, const BlockKeyArgs &a) {
         a.keys[b] = ((u64)a.blk_set[ob] << 32) | (0xFFFFFFFFu - a.blk_depth[ob]);
     }
 }
-MAP_KERNEL(blockkey, BlockKeyArgs)
+MAP_KERNEL(blockkey, BlockKeyArgs, 16)
 
 // blocks in list order: gather fields, write positions
 struct BlockGatherArgs {
@@ -499,7 +499,7 @@ HD void blockgather_body(long long b, const BlockGatherArgs &a) {
         a.o_pos[po + (k - q0)] = (int)(g - LDG(a.v.seq_off + k));
     }
 }
-MAP_KERNEL(blockgather, BlockGatherArgs)
+MAP_KERNEL(blockgather, BlockGatherArgs, 16)
 
 // ---- stage 5: chaining (collectNodeChains, csamsa.c:135-279) -----------------------------------------
 // csamsa.c:147-183 walks every sequence round the circle and notes which block follows which; a
@@ -522,7 +522,7 @@ HD void endkey_body(long long x, const EndKeyArgs &a) {
     a.keys[x] = ((u64)(q0 + k) << a.ebits) | e;
     a.vals[x] = b;
 }
-MAP_KERNEL(endkey, EndKeyArgs)
+MAP_KERNEL(endkey, EndKeyArgs, 24)
 
 struct ElemBlkArgs { BatchView v; const u32 *o_set; const u32 *set_blk0; const u32 *set_pos0; u32 *elem_blk; };
 HD void elemblk_body(long long b, const ElemBlkArgs &a) {
@@ -531,14 +531,14 @@ HD void elemblk_body(long long b, const ElemBlkArgs &a) {
     u32 po = pos_offset(a.set_blk0, a.set_pos0, s, m, (u32)b);
     for (u32 k = 0; k < m; k++) a.elem_blk[po + k] = (u32)b;
 }
-MAP_KERNEL(elemblk, ElemBlkArgs)
+MAP_KERNEL(elemblk, ElemBlkArgs, 8)
 
 struct SegHeadArgs { const u64 *keys; u32 *seghead; int ebits; };
 HD void seghead_body(long long j, const SegHeadArgs &a) {
     bool f = (j == 0) || (a.keys[j] >> a.ebits) != (a.keys[j - 1] >> a.ebits);
     a.seghead[j] = f ? (u32)j : 0u;
 }
-MAP_KERNEL(seghead, SegHeadArgs)
+MAP_KERNEL(seghead, SegHeadArgs, 12)
 
 struct LinkArgs {
     BatchView v; const u64 *keys; const u32 *vals; const u32 *seghead; const u32 *o_depth; int ebits;
@@ -559,7 +559,7 @@ HD void link_body(long long j, const LinkArgs &a) {
     ATOMIC_MIN(a.succ_lo + prev, cur);
     ATOMIC_MAX(a.succ_hi + prev, cur);
 }
-MAP_KERNEL(link, LinkArgs)
+MAP_KERNEL(link, LinkArgs, 20)
 
 // next block and the gap to it: the smallest gap over the sequences (csamsa.c:199-207)
 struct GapArgs {
@@ -587,7 +587,7 @@ HD void gap_body(long long b, const GapArgs &a) {
     a.next[b] = (int)cur;
     a.gap[b] = (int)iv;
 }
-MAP_KERNEL(gap, GapArgs)
+MAP_KERNEL(gap, GapArgs, 16)
 
 // csamsa.c:185-233, literally, one thread per set (the walk is a chain of dependent steps)
 struct ChainArgs {
@@ -633,7 +633,7 @@ HD void chain_body(long long s, const ChainArgs &a) {
     a.set_nchains[s] = mcs;
     if (hang) ATOMIC_MAX(a.set_flags + s, 2u);
 }
-MAP_KERNEL(chain, ChainArgs)
+MAP_KERNEL(chain, ChainArgs, 16)
 
 // sortList (nodeslinkedlists.c:59): stable, by chain size, descending
 struct SizeKeyArgs { const u32 *o_set; const int *size; u64 *keys; u32 *vals; };
@@ -641,11 +641,11 @@ HD void sizekey_body(long long b, const SizeKeyArgs &a) {
     a.keys[b] = ((u64)a.o_set[b] << 32) | (u32)(0x7FFFFFFF - a.size[b]);
     a.vals[b] = (u32)b;
 }
-MAP_KERNEL(sizekey, SizeKeyArgs)
+MAP_KERNEL(sizekey, SizeKeyArgs, 20)
 
 struct InvArgs { const u32 *order; u32 *inv; };
 HD void inv_body(long long i, const InvArgs &a) { a.inv[a.order[i]] = (u32)i; }
-MAP_KERNEL(inv, InvArgs)
+MAP_KERNEL(inv, InvArgs, 8)
 
 struct FinalArgs {
     BatchView v; const u32 *order; const u32 *inv; const u32 *o_depth; const u32 *o_set; const int *o_pos;
@@ -666,7 +666,7 @@ HD void final_body(long long i, const FinalArgs &a) {
     u32 src = pos_offset(a.set_blk0, a.set_pos0, s, m, b), dst = pos_offset(a.set_blk0, a.set_pos0, s, m, (u32)i);
     for (u32 k = 0; k < m; k++) a.f_pos[dst + k] = a.o_pos[src + k];
 }
-MAP_KERNEL(final, FinalArgs)
+MAP_KERNEL(final, FinalArgs, 48)
 
 // getRotations (csamsa.c:311): the positions of the head of the sorted list; plus whether the
 // head chain bites its own tail (the reference then overruns blockLabel, nodeslinkedlists.c:161)
@@ -686,4 +686,4 @@ HD void rot_body(long long s, const RotArgs &a) {
     while (cur != -1 && steps <= B) { cur = a.f_next[b0 + cur]; steps++; }
     if (cur != -1) a.set_cyclic[s] = 1;
 }
-MAP_KERNEL(rot, RotArgs)
+MAP_KERNEL(rot, RotArgs, 8)

@@ -123,7 +123,9 @@ static int scan_u32(Exec &ex, PrimScratch &ps, const u32 *in, u32 *out, long lon
     if (n <= 0) return 0;
     long long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (nb == 1) {
+        PROF_BEGIN(ex, "k_scan_apply", 8.0 * n);
         k_scan_apply<Op, INCLUSIVE><<<1, SCAN_THREADS, 0, ex.stream>>>(in, out, nullptr, n);
+        PROF_END(ex);
         ex.launches++;
         return 0;
     }
@@ -131,11 +133,15 @@ static int scan_u32(Exec &ex, PrimScratch &ps, const u32 *in, u32 *out, long lon
     int rc = dev_alloc(ps.block_sums[level], sizeof(u32) * (size_t)nb);
     if (rc) return rc;
     u32 *sums = (u32 *)ps.block_sums[level].p;
+    PROF_BEGIN(ex, "k_scan_reduce", 4.0 * n);
     k_scan_reduce<Op><<<(unsigned)nb, SCAN_THREADS, 0, ex.stream>>>(in, sums, n);
+    PROF_END(ex);
     ex.launches++;
     rc = scan_u32<Op, false>(ex, ps, sums, sums, nb, level + 1);
     if (rc) return rc;
+    PROF_BEGIN(ex, "k_scan_apply", 8.0 * n);
     k_scan_apply<Op, INCLUSIVE><<<(unsigned)nb, SCAN_THREADS, 0, ex.stream>>>(in, out, sums, n);
+    PROF_END(ex);
     ex.launches++;
     return 0;
 }
@@ -240,11 +246,15 @@ static int radix_sort_pairs(Exec &ex, PrimScratch &ps, u64 *&keys, u32 *&vals, u
     if (rc) return rc;
     u32 *counts = (u32 *)ps.counts.p;
     for (int shift = begin_bit; shift < end_bit; shift += RS_BITS) {
+        PROF_BEGIN(ex, "k_rs_hist", 8.0 * n);
         k_rs_hist<<<nb, RS_THREADS, 0, ex.stream>>>(keys, counts, n, shift, nb);
+        PROF_END(ex);
         ex.launches++;
         rc = scan_u32<ScanSum, false>(ex, ps, counts, counts, (long long)RS_BINS * nb);
         if (rc) return rc;
+        PROF_BEGIN(ex, "k_rs_scatter", 24.0 * n);
         k_rs_scatter<<<nb, RS_THREADS, 0, ex.stream>>>(keys, vals, keys_alt, vals_alt, counts, n, shift, nb);
+        PROF_END(ex);
         ex.launches++;
         u64 *tk = keys; keys = keys_alt; keys_alt = tk;
         u32 *tv = vals; vals = vals_alt; vals_alt = tv;

@@ -69,6 +69,9 @@ int csa_gpu_create(int device, csa_gpu_ctx **ctx);
 void csa_gpu_destroy(csa_gpu_ctx *ctx);
 const char *csa_gpu_last_error(void);
 int csa_gpu_abi_version(void);
+/* run on the caller's CUDA stream (a cudaStream_t, e.g. the host framework's current stream)
+ * instead of the context's own; NULL goes back to the context's stream */
+int csa_gpu_set_stream(csa_gpu_ctx *ctx, void *cuda_stream);
 
 /* ---- batch of independent sequence sets ---------------------------------------------- */
 /* Sequences are given flat: sequence i has texts[i][0..textsizes[i]) -- upper-case IUPAC
@@ -85,8 +88,10 @@ int csa_gpu_batch_upload_flat(csa_gpu_ctx *ctx, int nsets, const int *set_start,
 int csa_gpu_batch_run(csa_gpu_ctx *ctx, int max_interval, unsigned flags);
 /* rotations: one int per sequence of the batch (csamsa.h:12); info: one per set. */
 int csa_gpu_batch_download(csa_gpu_ctx *ctx, int *rotations, csa_gpu_set_info *info);
-/* total number of blocks of the last run, for sizing the arrays below */
+/* total number of blocks of the last run, and of block positions (sum over blocks of the number
+ * of sequences of the block's set), for sizing the arrays below */
 long long csa_gpu_batch_num_blocks(csa_gpu_ctx *ctx);
+long long csa_gpu_batch_num_positions(csa_gpu_ctx *ctx);
 /* the sorted blockslist of every set (set s: blocks [block_offset, block_offset+nblocks)):
  * depth/size/totalsize/interval as in nodeslinkedlists.h:4-13, next = index of nextblock
  * within the set's list or -1, positions: per block, one int per sequence of its set, stored
@@ -114,6 +119,14 @@ int csa_gpu_batch_suffix_array(csa_gpu_ctx *ctx, unsigned *sa, int *lcp);
  * stream): [0] suffix sort, [1] LCP, [2] block discovery, [3] block order, [4] chaining,
  * [5] whole run; launches = kernels launched by the last run. */
 int csa_gpu_batch_timings(csa_gpu_ctx *ctx, float ms[6], long long *launches);
+/* per-kernel profile: with it enabled every launch of the next runs is bracketed by CUDA events on
+ * the run's stream; after a run row i gives the kernel's name, its launches, their summed device
+ * time (ms) and the ALGORITHMIC bytes they moved (DESIGN.md lists the per-item figures).  Off by
+ * default; bench.py enables it for a separate pass, never inside the timed steps. */
+int csa_gpu_profile_enable(csa_gpu_ctx *ctx, int on);
+int csa_gpu_profile_count(csa_gpu_ctx *ctx);
+int csa_gpu_profile_get(csa_gpu_ctx *ctx, int i, char *name, int name_cap, long long *launches, double *ms,
+                        double *bytes);
 
 #ifdef __cplusplus
 }

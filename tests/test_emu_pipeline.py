@@ -1,0 +1,47 @@
+"""Kernel LOGIC on the CPU: the bodies of csa_b200/csrc/pipeline.cuh single-stepped by tests/emu
+against the oracle and the reference's golden vectors.  (The CUDA build is checked by the -m gpu
+tests; this file keeps the algorithm honest on a box without a GPU.)"""
+import random
+
+import numpy as np
+import pytest
+
+from common import compare_with_oracle, gen_case, oracle_gsa, oracle_run
+from csa_b200 import host
+
+
+def test_emu_golden_vectors(emu_finder, golden):
+    for case in golden:
+        seqs = [s.encode() for s in case["seqs"]]
+        r = emu_finder.find_rotations(seqs)
+        assert r.status == 0
+        assert [r.count_unique, r.count_chains] == case["counts"][2:], case["name"]
+        assert list(r.rotations) == case["rotations"], case["name"]
+        assert host.blocks_csv(r, seqs) == case["blocks_csv"], case["name"]
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_emu_seeded_cases(emu_finder, seed):
+    rng = random.Random(seed)
+    for i in range(120):
+        kind, seqs = gen_case(rng, max_n=1500)
+        compare_with_oracle(emu_finder.find_rotations(seqs), oracle_run(seqs), seqs, f"seed {seed} case {i} {kind}")
+
+
+def test_emu_batch_of_sets(emu_finder):
+    rng = random.Random(77)
+    sets = [gen_case(rng, max_n=500)[1] for _ in range(37)]
+    res = emu_finder.find_rotations_batch(sets)
+    for i, (r, s) in enumerate(zip(res, sets)):
+        compare_with_oracle(r, oracle_run(s), s, f"set {i}")
+
+
+def test_emu_suffix_array_and_lcp(emu_finder):
+    rng = random.Random(5)
+    for i in range(20):
+        _, seqs = gen_case(rng, max_n=800)
+        emu_finder.find_rotations(seqs)
+        sa, lcp = emu_finder.suffix_array()
+        osa, olcp = oracle_gsa(seqs)
+        assert np.array_equal(sa.astype(np.int64), osa.astype(np.int64)), f"case {i}: suffix array"
+        assert np.array_equal(lcp[1:], olcp[1:]), f"case {i}: lcp"

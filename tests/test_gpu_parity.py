@@ -1,0 +1,117 @@
+"""-m gpu: the product (libcsa_gpu.so on cuda:0, through the C ABI) against the oracle and the
+reference's golden vectors.  Bit-exact: rotations, the whole sorted block list, counts, status."""
+import random
+
+import numpy as np
+import pytest
+
+from common import compare_with_oracle, gen_case, oracle_gsa, oracle_run
+from csa_b200 import host
+from csa_b200.workloads import batch_sets, workload_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_golden_vectors(gpu_finder, golden):
+    """BASELINE.json configs[0] (Primates.txt) and configs[1] (Mammals.txt) + 80 synthetic sets:
+    outputs of the unmodified reference binary"""
+    sets = [[s.encode() for s in c["seqs"]] for c in golden]
+    res = gpu_finder.find_rotations_batch(sets)
+    for c, seqs, r in zip(golden, sets, res):
+        assert r.status == 0, c["name"]
+        assert [r.count_unique, r.count_chains] == c["counts"][2:], c["name"]
+        assert list(r.rotations) == c["rotations"], c["name"]
+        assert host.blocks_csv(r, seqs) == c["blocks_csv"], c["name"]
+    # and one set at a time (the reference's own call shape)
+    for c, seqs in list(zip(golden, sets))[:6]:
+        r = gpu_finder.find_rotations(seqs)
+        assert list(r.rotations) == c["rotations"], c["name"]
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23, 24])
+def test_gpu_seeded_sets_vs_oracle(gpu_finder, seed):
+    rng = random.Random(seed)
+    cases = [gen_case(rng, max_n=2500) for _ in range(150)]
+    sets = [c[1] for c in cases]
+    res = gpu_finder.find_rotations_batch(sets)
+    for i, (r, s) in enumerate(zip(res, sets)):
+        compare_with_oracle(r, oracle_run(s), s, f"seed {seed} set {i} {cases[i][0]}")
+
+
+def test_gpu_suffix_array_and_lcp(gpu_finder):
+    rng = random.Random(5)
+    for i in range(12):
+        _, seqs = gen_case(rng, max_n=2500)
+        gpu_finder.find_rotations(seqs)
+        sa, lcp = gpu_finder.suffix_array()
+        osa, olcp = oracle_gsa(seqs)
+        assert np.array_equal(sa.astype(np.int64), osa.astype(np.int64)), f"case {i}: suffix array"
+        assert np.array_equal(lcp[1:], olcp[1:]), f"case {i}: lcp"
+
+
+def check_block_properties(seqs, r):
+    """size-independent properties of a correct answer: every block occurs at its position in every
+    sequence, the blocks of the head chain are in one circular order everywhere, and the cut points
+    are the positions of the head block"""
+    assert r.status == 0
+    m = len(seqs)
+    for b in range(len(r.depth)):
+        d = int(r.depth[b])
+        ref = None
+        for k in range(m):
+            p, s = int(r.positions[b][k]), seqs[k]
+            w = (s + s)[p:p + d]
+            norm = bytes(c if c in b"ACGT" else 45 for c in w)
+            ref = norm if ref is None else ref
+            assert norm == ref, f"block {b} differs in sequence {k}"
+    assert list(r.rotations) == [int(x) for x in r.positions[0]]
+
+
+@pytest.mark.parametrize("name,nsets,oracle_sets", [("mammals", 24, 24), ("sets32", 6, 2), ("variants256", 1, 0)])
+def test_gpu_baseline_shapes(gpu_finder, name, nsets, oracle_sets):
+    """the shapes of BASELINE.json configs[1..3] at full sequence length: properties on every set,
+    the oracle on as many sets as it finishes in seconds"""
+    batch = workload_batch(name, nsets, seed=99)
+    sets = batch_sets(batch)
+    res = gpu_finder.find_rotations_batch(batch)
+    for i, (r, s) in enumerate(zip(res, sets)):
+        check_block_properties(s, r)
+        if i < oracle_sets:
+            compare_with_oracle(r, oracle_run(s), s, f"{name} set {i}")
+
+
+def test_gpu_rotation_equivariance(gpu_finder):
+    """rotating the inputs moves the cut points with them (mod n) when no tie-break is involved"""
+    batch = workload_batch("sets32", 1, seed=5)
+    seqs = batch_sets(batch)[0]
+    r0 = gpu_finder.find_rotations(seqs)
+    rng = random.Random(1)
+    shifts = [rng.randrange(len(s)) for s in seqs]
+    moved = [s[sh:] + s[:sh] for s, sh in zip(seqs, shifts)]
+    r1 = gpu_finder.find_rotations(moved)
+    assert sorted(r0.depth) == sorted(r1.depth)
+    head0 = [(s + s)[p:p + int(r0.depth[0])] for s, p in zip(seqs, r0.rotations)]
+    head1 = [(s + s)[p:p + int(r1.depth[0])] for s, p in zip(moved, r1.rotations)]
+    if head0[0] == head1[0]:
+        assert [(int(p) + sh) % len(s) for p, sh, s in zip(r1.rotations, shifts, seqs)] == [int(p) for p in r0.rotations]
+
+
+def test_gpu_edge_cases(gpu_finder):
+    cases = [
+        [b"ACGTACGTTT", b"ACGTACGAAT"],                      # tiny
+        [b"AC", b"CA" + b"G"],                                  # shortest allowed
+        [b"ACGTN" * 7 + b"A", b"ACGTN" * 7 + b"C"],             # IUPAC letters
+        [b"A" * 50 + b"C", b"A" * 40 + b"CG"],                  # low complexity
+        [b"ACGGTCA" * 9, b"TTGACCA" * 8, b"GGGTTTCA" * 5],      # periodic, ragged lengths
+    ]
+    res = gpu_finder.find_rotations_batch(cases)
+    for i, (r, s) in enumerate(zip(res, cases)):
+        compare_with_oracle(r, oracle_run(s), s, f"edge {i}")
+
+
+def test_gpu_errors(gpu_finder):
+    from csa_b200.api import CsaGpuError
+    with pytest.raises(CsaGpuError):
+        gpu_finder.find_rotations([b"ACGT"])  # one sequence: the path needs two (csamsa.c:533)
+    with pytest.raises(CsaGpuError):
+        gpu_finder.find_rotations([b"ACGT", b""])
