@@ -75,6 +75,7 @@ def _load(path):
     lib.csa_gpu_batch_num_suffixes.restype = C.c_longlong
     lib.csa_gpu_batch_suffix_array.argtypes = [vp, C.POINTER(C.c_uint), ip]
     lib.csa_gpu_batch_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
+    lib.csa_gpu_debug_rounds.argtypes = [vp, i, ip]
     lib.csa_gpu_profile_enable.argtypes = [vp, i]
     lib.csa_gpu_profile_count.argtypes = [vp]
     lib.csa_gpu_profile_get.argtypes = [vp, i, C.c_char_p, i, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
@@ -178,6 +179,11 @@ class RotationFinder:
         launches = C.c_longlong()
         self._check(self.lib.csa_gpu_batch_timings(self.ctx, ms, C.byref(launches)))
         return list(ms), launches.value
+
+    def debug_rounds(self, force_global: int = -1):
+        r = (C.c_int * 2)()
+        self._check(self.lib.csa_gpu_debug_rounds(self.ctx, force_global, r))
+        return r[0], r[1]
 
     def profile_enable(self, on: bool):
         self._check(self.lib.csa_gpu_profile_enable(self.ctx, int(on)))

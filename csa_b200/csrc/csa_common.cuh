@@ -27,6 +27,7 @@ template <class T> static inline T emu_atomic_add(T *p, T v) { T o = *p; *p = (T
 template <class T> static inline T emu_atomic_min(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> static inline T emu_atomic_max(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
 #define ATOMIC_ADD(p, v) emu_atomic_add(p, v)
+#define COUNT_IF(p, flag) do { if (flag) (*(p))++; } while (0)
 #define ATOMIC_MIN(p, v) emu_atomic_min(p, v)
 #define ATOMIC_MAX(p, v) emu_atomic_max(p, v)
 #define LDG(p) (*(p))
@@ -45,6 +46,13 @@ typedef int csaStream_t;
 #define LDG(p) (*(p))
 #endif
 #define ATOMIC_ADD(p, v) atomicAdd(p, v)
+// *p += number of threads of the warp whose flag is set: one atomic per warp (ballot + popc)
+#define COUNT_IF(p, flag)                                                        \
+    do {                                                                         \
+        unsigned act__ = __activemask();                                         \
+        unsigned b__ = __ballot_sync(act__, (flag));                             \
+        if (b__ && (threadIdx.x & 31) == (unsigned)(__ffs(act__) - 1)) atomicAdd((p), (u32)__popc(b__)); \
+    } while (0)
 #define ATOMIC_MIN(p, v) atomicMin(p, v)
 #define ATOMIC_MAX(p, v) atomicMax(p, v)
 typedef cudaStream_t csaStream_t;

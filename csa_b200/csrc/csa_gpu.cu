@@ -45,9 +45,12 @@ struct csa_gpu_ctx {
     long long launches = 0;
     // ---- device ----
     DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, dbl_off, z0;
-    DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, counter;
+    DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, counter, tiles;
+    int rounds_tiled = 0, rounds_global = 0, force_global_rounds = 0;
     DevMem sa0, saidx0, leaf_set, lcp0, psv, nsv, pse, parent, nsize, minpos, val, up, val2, up2;
-    DevMem set_nblocks, set_blk0, set_pos0, set_flags, set_nchains, set_cyclic, firstmax;
+    DevMem set_nblocks, set_blk0, set_pos0, set_flags, set_nchains, set_cyclic, firstmax, set_collected, set_suffixfree;
+    bool have_stats = false;
+    std::vector<u32> h_set_collected, h_set_suffixfree;
     DevMem blk_lb, blk_depth, blk_set, order, o_depth, o_set, o_pos, elem_blk, seghead, succ_lo, succ_hi;
     DevMem next, gap, size, total, interval, inv, f_depth, f_size, f_total, f_interval, f_next, f_pos, rotations;
     void *pinned = nullptr;
@@ -119,9 +122,9 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
                      &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
-                     &c->t2, &c->t3, &c->t4, &c->counter, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
+                     &c->t2, &c->t3, &c->t4, &c->counter, &c->tiles, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
                      &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
-                     &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->blk_lb,
+                     &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
                      &c->succ_lo, &c->succ_hi, &c->next, &c->gap, &c->size, &c->total, &c->interval, &c->inv, &c->f_depth,
                      &c->f_size, &c->f_total, &c->f_interval, &c->f_next, &c->f_pos, &c->rotations};
@@ -265,26 +268,49 @@ static int sort_pairs(csa_gpu_ctx *c, long long n, int begin_bit, int end_bit) {
     return 0;
 }
 
+// head[]/rank[] from the sorted keys in keysA (device-wide path)
+static int heads_and_ranks(csa_gpu_ctx *c, u32 *head, u32 *rank, u32 *counter, u32 *ngroups) {
+    Exec &ex = c->ex;
+    u32 N = c->N;
+    TRY(dev_zero(ex, counter, sizeof(u32)));
+    { FlagArgs a{P<u64>(c->keysA), head, counter}; launch_flag(ex, N, a); }
+    TRY((scan_u32<ScanMax, true>(ex, c->ps, head, head, N)));
+    { SetRankArgs a{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, a); }
+    return read_u32(c, counter, ngroups);
+}
+
 static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
     u32 N = c->N;
-    u32 *head = P<u32>(c->t0), *rank = P<u32>(c->t1), *counter = P<u32>(c->counter);
+    u32 *head = P<u32>(c->t0), *rank = P<u32>(c->t1), *rank2 = P<u32>(c->t3), *counter = P<u32>(c->counter);
+    u32 ntiles = (N + RF_NOMINAL - 1) / RF_NOMINAL;
+    TRY(dev_alloc(c->tiles, sizeof(u32) * ((size_t)ntiles + 2)));
     { InitKeyArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA)}; launch_initkey(ex, N, a); }
     TRY(sort_pairs(c, N, 0, CSA_K0_BITS + bits_for((u64)c->nsets - 1)));
     int nbits = bits_for((u64)N - 1);
     u64 sorted_len = CSA_K0;
-    for (;;) {
-        TRY(dev_zero(ex, counter, sizeof(u32)));
-        { FlagArgs a{P<u64>(c->keysA), head, counter}; launch_flag(ex, N, a); }
-        TRY((scan_u32<ScanMax, true>(ex, c->ps, head, head, N)));
-        { SetRankArgs a{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, a); }
-        u32 ngroups = 0;
-        TRY(read_u32(c, counter, &ngroups));
-        // gencycsuffixtrees.c compares rotations letter by letter; two periodic strings that agree on
-        // n_a+n_b letters agree for ever, so 2*nmax sorted letters settle every comparison
-        if (ngroups == N || sorted_len >= 2ull * c->nmax) break;
-        { Key2Args a{v, P<u32>(c->valsA), rank, P<u64>(c->keysA), (u32)sorted_len, nbits}; launch_key2(ex, N, a); }
-        TRY(sort_pairs(c, N, 0, 2 * nbits));
+    u32 ngroups = 0;
+    TRY(heads_and_ranks(c, head, rank, counter, &ngroups));
+    c->rounds_tiled = c->rounds_global = 0;
+    // gencycsuffixtrees.c compares rotations letter by letter; two periodic strings that agree on
+    // n_a+n_b letters agree for ever, so 2*nmax sorted letters settle every comparison
+    while (ngroups != N && sorted_len < 2ull * c->nmax) {
+        TRY(dev_zero(ex, counter, 2 * sizeof(u32)));
+        { TileArgs a{head, P<u32>(c->tiles), counter + 1, N, ntiles}; launch_tile(ex, ntiles, a); }
+        u32 oversize = 0;
+        TRY(read_u32(c, counter + 1, &oversize));
+        if (!oversize && !c->force_global_rounds) {
+            RefineArgs a{v, P<u32>(c->valsA), head, rank, rank2, P<u32>(c->tiles), (u32)sorted_len, counter, ntiles};
+            launch_refine(ex, a);
+            std::swap(rank, rank2);
+            TRY(read_u32(c, counter, &ngroups));
+            c->rounds_tiled++;
+        } else { // a group larger than a tile: device-wide radix sort of (rank, rank h letters on)
+            { Key2Args a{v, P<u32>(c->valsA), rank, P<u64>(c->keysA), (u32)sorted_len, nbits}; launch_key2(ex, N, a); }
+            TRY(sort_pairs(c, N, 0, 2 * nbits));
+            TRY(heads_and_ranks(c, head, rank, counter, &ngroups));
+            c->rounds_global++;
+        }
         sorted_len *= 2;
     }
     TRY(d2d(ex, c->sa.p, c->valsA.p, sizeof(u32) * (size_t)N));
@@ -330,6 +356,27 @@ static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     c->E = (u32)e;
     TRY(h2d(ex, c->set_blk0.p, c->h_set_blk0.data(), sizeof(u32) * (nsets + 1)));
     TRY(h2d(ex, c->set_pos0.p, c->h_set_pos0.data(), sizeof(u32) * (nsets + 1)));
+    return 0;
+}
+
+// csamsa.c:332,338: how many nodes collectNodes finds and removeSuffixNodes leaves (optional)
+static int stage_stats(csa_gpu_ctx *c, const BatchView &v) {
+    Exec &ex = c->ex;
+    u32 N = c->N;
+    int nsets = c->nsets;
+    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t2), *R = P<u32>(c->t1), *dv = P<u32>(c->t4), *prevcl = P<u32>(c->t0);
+    int mbits = bits_for((u64)c->mmax - 1);
+    TRY(dev_zero(ex, c->set_collected.p, sizeof(u32) * nsets));
+    TRY(dev_zero(ex, c->set_suffixfree.p, sizeof(u32) * nsets));
+    { WinDepthArgs a{v, sa, lcp, R, dv}; launch_windepth(ex, N, a); }
+    { ClKeyArgs a{v, sa, P<u64>(c->keysA), P<u32>(c->valsA), mbits}; launch_clkey(ex, N, a); }
+    TRY(sort_pairs(c, N, 0, mbits + CSA_LETTER_BITS));
+    { PrevClArgs a{v, sa, P<u64>(c->keysA), P<u32>(c->valsA), prevcl, mbits}; launch_prevcl(ex, N, a); }
+    { PlateauArgs a{v, sa, lcp, R, dv, prevcl, P<u32>(c->set_collected), P<u32>(c->set_suffixfree)}; launch_plateau(ex, N, a); }
+    c->h_set_collected.assign(nsets, 0); c->h_set_suffixfree.assign(nsets, 0);
+    TRY(d2h(ex, c->h_set_collected.data(), c->set_collected.p, sizeof(u32) * nsets));
+    TRY(d2h(ex, c->h_set_suffixfree.data(), c->set_suffixfree.p, sizeof(u32) * nsets));
+    c->have_stats = true;
     return 0;
 }
 
@@ -420,7 +467,6 @@ static int stage_chain(csa_gpu_ctx *c, const BatchView &v, int max_interval) {
 }
 
 extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flags) {
-    (void)flags;
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
     if (!c->uploaded) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_run before csa_gpu_batch_upload");
 #ifndef CSA_EMU
@@ -436,7 +482,8 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
     TRY(dev_alloc(c->valsA, n4)); TRY(dev_alloc(c->valsB, n4)); TRY(dev_alloc(c->sa, n4));
     TRY(dev_alloc(c->t0, n4)); TRY(dev_alloc(c->t1, n4)); TRY(dev_alloc(c->t2, n4)); TRY(dev_alloc(c->t3, n4)); TRY(dev_alloc(c->t4, n4));
     TRY(dev_alloc(c->counter, 64));
-    DevMem *perset[] = {&c->set_nblocks, &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax};
+    DevMem *perset[] = {&c->set_nblocks, &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax,
+                        &c->set_collected, &c->set_suffixfree};
     for (DevMem *m : perset) TRY(dev_alloc(*m, sizeof(u32) * (nsets + 1)));
     TRY(dev_alloc(c->rotations, sizeof(int) * (size_t)c->M));
     BatchView v = view_of(c);
@@ -450,6 +497,8 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
     mark(c, 2);
     TRY(dev_zero(ex, c->set_flags.p, sizeof(u32) * nsets));
     TRY(stage_common_blocks(c, v));
+    c->have_stats = false;
+    if (flags & CSA_GPU_FLAG_STATS) TRY(stage_stats(c, v));
     mark(c, 3);
     TRY(stage_block_order(c, v));
     mark(c, 4);
@@ -483,6 +532,15 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
         c->prof.pool_used = 0;
     }
 #endif
+    return CSA_GPU_OK;
+}
+
+// tests: force every doubling round down the device-wide radix path (1) or let the tiles decide (0);
+// rounds[0], rounds[1] = rounds of the last run that took the tile path / the device-wide path
+extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds[2]) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (force_global >= 0) c->force_global_rounds = force_global;
+    if (rounds) { rounds[0] = c->rounds_tiled; rounds[1] = c->rounds_global; }
     return CSA_GPU_OK;
 }
 
@@ -529,8 +587,8 @@ extern "C" int csa_gpu_batch_download(csa_gpu_ctx *c, int *rotations, csa_gpu_se
             csa_gpu_set_info &o = info[s];
             o.status = status;
             o.nseqs = (int)(c->h_set_seq0[s + 1] - c->h_set_seq0[s]);
-            o.count_collected = -1;
-            o.count_suffixfree = -1;
+            o.count_collected = c->have_stats ? (int)c->h_set_collected[s] : -1;
+            o.count_suffixfree = c->have_stats ? (int)c->h_set_suffixfree[s] : -1;
             o.count_unique = (int)c->h_set_nblocks[s];
             o.count_chains = (int)c->h_set_nchains[s];
             o.nblocks = (int)c->h_set_nblocks[s];

@@ -118,12 +118,33 @@ MAP_KERNEL(initkey, InitKeyArgs, 29)
 
 // head[i] = i where a new group of equal keys starts, else 0 (max-scanned afterwards)
 struct FlagArgs { const u64 *keys; u32 *head; u32 *ngroups; };
+#ifdef CSA_EMU
 HD void flag_body(long long i, const FlagArgs &a) {
     bool f = (i == 0) || a.keys[i] != a.keys[i - 1];
     a.head[i] = f ? (u32)i : 0u;
-    if (f) ATOMIC_ADD(a.ngroups, 1u);
+    COUNT_IF(a.ngroups, f);
 }
 MAP_KERNEL(flag, FlagArgs, 12)
+#else
+// one atomic per CTA: same-address atomics serialise in L2 (one per warp cost 0.5 ms per launch)
+__global__ void __launch_bounds__(256) k_flag(long long n, FlagArgs a) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool f = false;
+    if (i < n) {
+        f = (i == 0) || a.keys[i] != a.keys[i - 1];
+        a.head[i] = f ? (u32)i : 0u;
+    }
+    int c = __syncthreads_count(f);
+    if (threadIdx.x == 0 && c) atomicAdd(a.ngroups, (u32)c);
+}
+static inline void launch_flag(Exec &ex, long long n, FlagArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_flag", 12.0 * n);
+    k_flag<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
 
 struct SetRankArgs { const u32 *sa; const u32 *head; u32 *rank; };
 HD void setrank_body(long long i, const SetRankArgs &a) { a.rank[a.sa[i]] = a.head[i]; }
@@ -687,3 +708,257 @@ HD void rot_body(long long s, const RotArgs &a) {
     if (cur != -1) a.set_cyclic[s] = 1;
 }
 MAP_KERNEL(rot, RotArgs, 8)
+
+// ---- optional: the counts the reference prints (csamsa.c:332 "nodes found", :338 "nodes left") ------------
+// collectNodes keeps the DEEPEST nodes that hold every sequence.  With W(l) = [l, R[l]] the shortest
+// window from l that holds every sequence and D(l) = min lcp over (l, R[l]] the depth of the
+// smallest LCP interval around it: the windows inside one node are consecutive l, and a node is a
+// deepest all-sequence node iff all of its windows have D == its depth.  So the collected nodes are
+// exactly the maximal runs of equal D(l) whose two neighbouring windows are shallower (or missing).
+struct WinDepthArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *dv; };
+HD void windepth_body(long long i, const WinDepthArgs &a) {
+    u32 l = (u32)i;
+    u32 s = LDG(a.v.seq_set + LDG(a.v.seqof + a.sa[l]));
+    u32 s1 = LDG(a.v.set_base0 + s + 1);
+    u32 r = a.R[l];
+    if (r >= s1) { a.dv[l] = 0; return; } // no window: sorts below every depth
+    u32 mn = 0xFFFFFFFEu;
+    for (u32 j = l + 1; j <= r; j++) { u32 x = a.lcp[j]; if (x < mn) mn = x; }
+    a.dv[l] = mn + 1;
+}
+MAP_KERNEL(windepth, WinDepthArgs, 12)
+
+// (letter before the suffix, sequence) lists: prevcl[i] = 1 + previous SA index of the same sequence
+// preceded by the same letter, 0 if none
+struct ClKeyArgs { BatchView v; const u32 *sa; u64 *keys; u32 *vals; int mbits; };
+HD unsigned letter_before(const BatchView &v, u32 g, u32 k) {
+    u32 off = LDG(v.seq_off + k), n = LDG(v.seq_off + k + 1) - off;
+    u32 p = g - off;
+    return v.code[off + (p == 0 ? n - 1 : p - 1)];
+}
+HD void clkey_body(long long i, const ClKeyArgs &a) {
+    u32 g = a.sa[i];
+    u32 k = LDG(a.v.seqof + g);
+    u32 color = k - LDG(a.v.set_seq0 + LDG(a.v.seq_set + k));
+    a.keys[i] = ((u64)letter_before(a.v, g, k) << a.mbits) | color;
+    a.vals[i] = (u32)i;
+}
+MAP_KERNEL(clkey, ClKeyArgs, 24)
+
+struct PrevClArgs { BatchView v; const u32 *sa; const u64 *keys; const u32 *vals; u32 *prevcl; int mbits; };
+HD void prevcl_body(long long j, const PrevClArgs &a) {
+    u32 i = a.vals[j];
+    u32 p = 0;
+    if (j > 0 && a.keys[j - 1] == a.keys[j]) {
+        u32 i0 = a.vals[j - 1];
+        if (LDG(a.v.seqof + a.sa[i0]) == LDG(a.v.seqof + a.sa[i])) p = i0 + 1;
+    }
+    a.prevcl[i] = p;
+}
+MAP_KERNEL(prevcl, PrevClArgs, 24)
+
+struct PlateauArgs {
+    BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; const u32 *dv; const u32 *prevcl;
+    u32 *set_collected; u32 *set_suffixfree;
+};
+HD void plateau_body(long long i, const PlateauArgs &a) {
+    u32 l = (u32)i;
+    u32 d1 = a.dv[l];
+    if (d1 == 0) return;
+    u32 k0 = LDG(a.v.seqof + a.sa[l]);
+    u32 s = LDG(a.v.seq_set + k0);
+    u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
+    if (l != s0) {
+        u32 dl = a.dv[l - 1];
+        if (dl >= d1) return; // not the first window of a run, or a deeper neighbour
+    }
+    u32 l2 = l;
+    while (l2 + 1 < s1 && a.dv[l2 + 1] == d1) l2++;
+    if (l2 + 1 < s1 && a.dv[l2 + 1] > d1) return;
+    ATOMIC_ADD(a.set_collected + s, 1u);
+    u32 d = d1 - 1;
+    if (d == 0) { ATOMIC_ADD(a.set_suffixfree + s, 1u); return; } // csamsa.c:85
+    u32 rb = a.R[l2];
+    while (rb + 1 < s1 && a.lcp[rb + 1] >= d) rb++;
+    // removeSuffixNodes (csamsa.c:80): some letter x precedes an occurrence in EVERY sequence
+    u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
+    u32 cnt[5] = {0, 0, 0, 0, 0};
+    for (u32 j = l; j <= rb; j++) {
+        if (a.prevcl[j] > l) continue; // an earlier suffix of this sequence in the node has the same letter
+        u32 g = a.sa[j];
+        cnt[letter_before(a.v, g, LDG(a.v.seqof + g))]++;
+    }
+    bool sfx = false;
+    for (int c = 0; c < 5; c++) if (cnt[c] == m) sfx = true;
+    if (!sfx) ATOMIC_ADD(a.set_suffixfree + s, 1u);
+}
+MAP_KERNEL(plateau, PlateauArgs, 16)
+
+// ---- stage 1, fast path: one doubling round as ONE pass over the suffix array ---------------------------
+// After the first sort the groups of equal h-prefix are small (about one suffix per sequence and
+// repeat copy), so a round does not need a device-wide sort: the array is cut into tiles that begin
+// at group borders (<= RF_CAP suffixes), each CTA stages its tile in shared memory, ranks every
+// suffix inside its own group by (rank of the next h letters, position) -- a stable counting rank --
+// and writes the tile back with the new group borders and ranks.  HBM traffic per suffix and round:
+// sa 4 B in + 4 B out, head 4 + 4, the two gathers seqof/rank 4 + 4, the new rank 4 = 28 B (the
+// device-wide radix path moves 7 x 32 B).  Ranks are double buffered: a round reads the ranks of
+// the previous round only.  A group larger than a tile sends the round down the device-wide path.
+#define RF_THREADS 256
+#define RF_NOMINAL 1024
+#define RF_CAP 2048
+#define RF_ITEMS (RF_CAP / RF_THREADS)
+
+struct TileArgs { const u32 *head; u32 *tb; u32 *oversize; u32 N; u32 ntiles; };
+HD u32 tile_start(const TileArgs &a, u32 t) {
+    if (t >= a.ntiles) return a.N;
+    u64 p = (u64)t * RF_NOMINAL;
+    u32 steps = 0;
+    while (p < a.N && a.head[p] != (u32)p) {
+        p++;
+        if (++steps > RF_CAP) break;
+    }
+    return p < a.N ? (u32)p : a.N;
+}
+HD void tile_body(long long t, const TileArgs &a) {
+    u32 b0 = tile_start(a, (u32)t), b1 = tile_start(a, (u32)t + 1);
+    a.tb[t] = b0;
+    if ((u32)t + 1 == a.ntiles) a.tb[t + 1] = a.N;
+    if (b1 - b0 > RF_CAP) ATOMIC_MAX(a.oversize, 1u);
+}
+MAP_KERNEL(tile, TileArgs, 8)
+
+struct RefineArgs {
+    BatchView v; u32 *sa; u32 *head; const u32 *rank; u32 *rank2; const u32 *tb; u32 h; u32 *ngroups; u32 ntiles;
+};
+
+#ifdef CSA_EMU
+static inline void launch_refine(Exec &, const RefineArgs &a) {
+    std::vector<std::pair<u32, u32>> seg; // (key2, suffix)
+    for (u32 t = 0; t < a.ntiles; t++) {
+        u32 base = a.tb[t], end = a.tb[t + 1];
+        u32 i = base;
+        while (i < end) {
+            u32 j = i + 1;
+            while (j < end && a.head[j] != j) j++;
+            seg.clear();
+            for (u32 x = i; x < j; x++) seg.push_back({a.rank[cyc_add(a.v, a.sa[x], a.h)], a.sa[x]});
+            std::stable_sort(seg.begin(), seg.end(), [](const std::pair<u32, u32> &p, const std::pair<u32, u32> &q) { return p.first < q.first; });
+            u32 hd = i;
+            for (u32 x = i; x < j; x++) {
+                if (x > i && seg[x - i].first != seg[x - i - 1].first) hd = x;
+                if (hd == x) (*a.ngroups)++;
+                a.sa[x] = seg[x - i].second;
+                a.head[x] = hd;
+                a.rank2[seg[x - i].second] = hd;
+            }
+            i = j;
+        }
+    }
+}
+#else
+__global__ void __launch_bounds__(RF_THREADS) k_refine(RefineArgs a) {
+    __shared__ u32 s_key[RF_CAP];  // rank of the next h letters | 1<<31 at the first suffix of a group
+    __shared__ u32 s_sa[RF_CAP];
+    __shared__ u32 s_okey[RF_CAP];
+    __shared__ u32 s_osa[RF_CAP];
+    __shared__ u32 s_scan[33];
+    __shared__ u32 s_count;
+    const u32 base = a.tb[blockIdx.x];
+    const u32 n = a.tb[blockIdx.x + 1] - base;
+    if (n == 0 || n > RF_CAP) return;
+    const u32 tid = threadIdx.x;
+    if (tid == 0) s_count = 0;
+    // 1. stage the tile: suffix, group border, rank of the suffix h letters on (gather)
+    for (u32 j = tid; j < n; j += RF_THREADS) {
+        u32 g = a.sa[base + j];
+        u32 hd = a.head[base + j];
+        u32 k2 = LDG(a.rank + cyc_add(a.v, g, a.h));
+        s_sa[j] = g;
+        s_key[j] = k2 | (hd == base + j ? 0x80000000u : 0u);
+    }
+    __syncthreads();
+    // 2. first suffix of the group of each of my RF_ITEMS consecutive suffixes (block max-scan)
+    const u32 j0 = tid * RF_ITEMS;
+    u32 mykey[RF_ITEMS], seg[RF_ITEMS];
+    u32 run = 0;
+#pragma unroll
+    for (int e = 0; e < RF_ITEMS; e++) {
+        u32 j = j0 + e;
+        u32 w = (j < n) ? s_key[j] : 0x80000000u;
+        mykey[e] = w & 0x7FFFFFFFu;
+        if (w >> 31) run = j;
+        seg[e] = run; // exact once the prefix from the threads before is added
+    }
+    u32 total;
+    u32 before = block_scan_excl(run, total, ScanMax(), s_scan);
+#pragma unroll
+    for (int e = 0; e < RF_ITEMS; e++) seg[e] = seg[e] > before ? seg[e] : before;
+    // 3. stable counting rank inside the group: one walk over the group serves all my suffixes in it
+    u32 cnt[RF_ITEMS];
+#pragma unroll
+    for (int e = 0; e < RF_ITEMS; e++) cnt[e] = 0;
+#pragma unroll
+    for (int e = 0; e < RF_ITEMS; e++) {
+        const bool first_of_run = (j0 + e < n) && (e == 0 || seg[e] != seg[e == 0 ? 0 : e - 1]);
+        if (first_of_run) {
+            const u32 s0 = seg[e];
+            for (u32 k = s0; k < n; k++) {
+                u32 w = s_key[k];
+                if (k > s0 && (w >> 31)) break;
+                u32 kk = w & 0x7FFFFFFFu;
+#pragma unroll
+                for (int x = e; x < RF_ITEMS; x++)
+                    if (seg[x] == s0 && j0 + x < n) cnt[x] += (kk < mykey[x] || (kk == mykey[x] && k < j0 + x)) ? 1u : 0u;
+            }
+        }
+    }
+    // 4. move to the sorted place; the suffix that lands on the group's first place carries the border
+#pragma unroll
+    for (int x = 0; x < RF_ITEMS; x++) {
+        u32 j = j0 + x;
+        if (j < n) {
+            u32 p = seg[x] + cnt[x];
+            s_osa[p] = s_sa[j];
+            s_okey[p] = mykey[x] | (p == seg[x] ? 0x80000000u : 0u);
+        }
+    }
+    __syncthreads();
+    // 5. new borders: an old border, or a change of the second rank; new heads by max-scan
+    u32 hd[RF_ITEMS];
+    u32 run2 = 0, nflag = 0;
+#pragma unroll
+    for (int x = 0; x < RF_ITEMS; x++) {
+        u32 j = j0 + x;
+        if (j < n) {
+            u32 w = s_okey[j];
+            bool f = (w >> 31) || j == 0 || (w & 0x7FFFFFFFu) != (s_okey[j - 1] & 0x7FFFFFFFu);
+            if (f) { run2 = j; nflag++; }
+        }
+        hd[x] = run2;
+    }
+    u32 total2;
+    u32 before2 = block_scan_excl(run2, total2, ScanMax(), s_scan);
+    if (nflag) atomicAdd(&s_count, nflag);
+#pragma unroll
+    for (int x = 0; x < RF_ITEMS; x++) {
+        u32 j = j0 + x;
+        if (j < n) s_key[j] = base + (hd[x] > before2 ? hd[x] : before2); // reuse s_key for the heads
+    }
+    __syncthreads();
+    // 6. write back, coalesced; the new rank of every suffix goes to the other rank buffer
+    for (u32 j = tid; j < n; j += RF_THREADS) {
+        u32 g = s_osa[j], h2 = s_key[j];
+        a.sa[base + j] = g;
+        a.head[base + j] = h2;
+        a.rank2[g] = h2;
+    }
+    if (tid == 0) atomicAdd(a.ngroups, s_count);
+}
+static inline void launch_refine(Exec &ex, const RefineArgs &a) {
+    if (a.ntiles == 0) return;
+    PROF_BEGIN(ex, "k_refine", 28.0 * a.v.N);
+    k_refine<<<a.ntiles, RF_THREADS, 0, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif

@@ -119,6 +119,10 @@ int csa_gpu_batch_suffix_array(csa_gpu_ctx *ctx, unsigned *sa, int *lcp);
  * stream): [0] suffix sort, [1] LCP, [2] block discovery, [3] block order, [4] chaining,
  * [5] whole run; launches = kernels launched by the last run. */
 int csa_gpu_batch_timings(csa_gpu_ctx *ctx, float ms[6], long long *launches);
+/* tests: force_global = 1 sends every prefix-doubling round down the device-wide radix-sort path,
+ * 0 lets the tile path take the rounds whose groups fit a tile, -1 leaves the setting; rounds[0..1]
+ * = rounds of the last run on the tile path / on the device-wide path */
+int csa_gpu_debug_rounds(csa_gpu_ctx *ctx, int force_global, int rounds[2]);
 /* per-kernel profile: with it enabled every launch of the next runs is bracketed by CUDA events on
  * the run's stream; after a run row i gives the kernel's name, its launches, their summed device
  * time (ms) and the ALGORITHMIC bytes they moved (DESIGN.md lists the per-item figures).  Off by

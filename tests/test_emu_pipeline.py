@@ -45,3 +45,26 @@ def test_emu_suffix_array_and_lcp(emu_finder):
         osa, olcp = oracle_gsa(seqs)
         assert np.array_equal(sa.astype(np.int64), osa.astype(np.int64)), f"case {i}: suffix array"
         assert np.array_equal(lcp[1:], olcp[1:]), f"case {i}: lcp"
+
+
+def test_emu_printed_counts(emu_finder, golden):
+    sets = [[s.encode() for s in c["seqs"]] for c in golden]
+    for c, r in zip(golden, emu_finder.find_rotations_batch(sets, flags=1)):
+        assert [r.count_collected, r.count_suffixfree, r.count_unique, r.count_chains] == c["counts"], c["name"]
+
+
+def test_emu_both_round_paths(emu_finder):
+    rng = random.Random(4)
+    sets = [gen_case(rng, max_n=1200)[1] for _ in range(25)]
+    try:
+        emu_finder.debug_rounds(1)
+        res_g = emu_finder.find_rotations_batch(sets)
+        assert emu_finder.debug_rounds()[0] == 0
+        emu_finder.debug_rounds(0)
+        res_t = emu_finder.find_rotations_batch(sets)
+    finally:
+        emu_finder.debug_rounds(0)
+    for i, (a, b, s) in enumerate(zip(res_t, res_g, sets)):
+        o = oracle_run(s)
+        compare_with_oracle(a, o, s, f"tile path set {i}")
+        compare_with_oracle(b, o, s, f"device-wide path set {i}")

@@ -115,3 +115,51 @@ def test_gpu_errors(gpu_finder):
         gpu_finder.find_rotations([b"ACGT"])  # one sequence: the path needs two (csamsa.c:533)
     with pytest.raises(CsaGpuError):
         gpu_finder.find_rotations([b"ACGT", b""])
+
+
+def test_gpu_tile_rounds_equal_device_wide_rounds(gpu_finder):
+    """the one-pass tile round (k_refine) and the device-wide radix round give the same suffix array"""
+    batch = workload_batch("sets32", 3, seed=3)
+    try:
+        gpu_finder.debug_rounds(0)
+        res_t = gpu_finder.find_rotations_batch(batch)
+        sa_t, lcp_t = gpu_finder.suffix_array()
+        tiled, _ = gpu_finder.debug_rounds()
+        gpu_finder.debug_rounds(1)
+        res_g = gpu_finder.find_rotations_batch(batch)
+        sa_g, lcp_g = gpu_finder.suffix_array()
+        t2, glob = gpu_finder.debug_rounds()
+    finally:
+        gpu_finder.debug_rounds(0)
+    assert tiled > 0 and t2 == 0 and glob > 0
+    assert np.array_equal(sa_t, sa_g) and np.array_equal(lcp_t, lcp_g)
+    for a, b in zip(res_t, res_g):
+        assert np.array_equal(a.rotations, b.rotations) and np.array_equal(a.positions, b.positions)
+
+
+def test_gpu_large_groups_fall_back(gpu_finder):
+    """low-complexity sequences make groups larger than a tile: those rounds take the device-wide path"""
+    rng = random.Random(8)
+    seqs = []
+    for _ in range(3):
+        s = bytearray(b"A" * 6000)
+        for _ in range(40):
+            s[rng.randrange(len(s))] = rng.choice(b"CGT")
+        seqs.append(bytes(s))
+    r = gpu_finder.find_rotations(seqs)
+    _, glob = gpu_finder.debug_rounds()
+    assert glob > 0
+    compare_with_oracle(r, oracle_run(seqs), seqs, "polyA")
+
+
+def test_gpu_printed_counts(gpu_finder, golden):
+    """csamsa.c:332,338: "nodes found" / "nodes left" (CSA_GPU_FLAG_STATS) against the reference's stdout"""
+    sets = [[s.encode() for s in c["seqs"]] for c in golden]
+    res = gpu_finder.find_rotations_batch(sets, flags=1)
+    for c, r in zip(golden, res):
+        assert [r.count_collected, r.count_suffixfree, r.count_unique, r.count_chains] == c["counts"], c["name"]
+    rng = random.Random(31)
+    cases = [gen_case(rng, max_n=2000)[1] for _ in range(120)]
+    for i, (r, s) in enumerate(zip(gpu_finder.find_rotations_batch(cases, flags=1), cases)):
+        assert r.count_collected >= 0
+        compare_with_oracle(r, oracle_run(s), s, f"stats case {i}")
