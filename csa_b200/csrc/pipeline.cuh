@@ -813,7 +813,7 @@ HD u32 tile_start(const TileArgs &a, u32 t) {
     if (t >= a.ntiles) return a.N;
     u64 p = (u64)t * RF_NOMINAL;
     u32 steps = 0;
-    while (p < a.N && a.head[p] != (u32)p) {
+    while (p < a.N && (a.head[p] & 0x7FFFFFFFu) != (u32)p) { // bit 31: settled (k_refine)
         p++;
         if (++steps > RF_CAP) break;
     }
@@ -839,7 +839,7 @@ static inline void launch_refine(Exec &, const RefineArgs &a) {
         u32 i = base;
         while (i < end) {
             u32 j = i + 1;
-            while (j < end && a.head[j] != j) j++;
+            while (j < end && (a.head[j] & 0x7FFFFFFFu) != j) j++;
             seg.clear();
             for (u32 x = i; x < j; x++) seg.push_back({a.rank[cyc_add(a.v, a.sa[x], a.h)], a.sa[x]});
             std::stable_sort(seg.begin(), seg.end(), [](const std::pair<u32, u32> &p, const std::pair<u32, u32> &q) { return p.first < q.first; });
@@ -856,101 +856,141 @@ static inline void launch_refine(Exec &, const RefineArgs &a) {
     }
 }
 #else
+#define HEAD_SETTLED 0x80000000u
 __global__ void __launch_bounds__(RF_THREADS) k_refine(RefineArgs a) {
-    __shared__ u32 s_key[RF_CAP];  // rank of the next h letters | 1<<31 at the first suffix of a group
+    // composite sort key of a suffix: (first place of its group in the tile : 11 bits, rank of the
+    // next h letters : 31, place in the tile : 11).  It is unique and orders the whole tile, so the
+    // number of smaller composites from the first group a thread touches onwards IS the sorted
+    // place -- the counting loop needs no test for group membership.
+    __shared__ u64 s_ck[RF_CAP];
     __shared__ u32 s_sa[RF_CAP];
-    __shared__ u32 s_okey[RF_CAP];
+    __shared__ u32 s_k2[RF_CAP];   // rank h letters on | 1<<31 on the first suffix of a group; later the new heads
     __shared__ u32 s_osa[RF_CAP];
+    __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled
     __shared__ u32 s_scan[33];
     __shared__ u32 s_count;
+    u32 *s_okey = (u32 *)s_ck;     // sorted keys; s_ck is dead (and fenced) by then
     const u32 base = a.tb[blockIdx.x];
     const u32 n = a.tb[blockIdx.x + 1] - base;
     if (n == 0 || n > RF_CAP) return;
     const u32 tid = threadIdx.x;
     if (tid == 0) s_count = 0;
-    // 1. stage the tile: suffix, group border, rank of the suffix h letters on (gather)
+    // 1. borders.  A settled suffix is a singleton whose rank is already in BOTH rank buffers.
+    int all_settled = 1;
     for (u32 j = tid; j < n; j += RF_THREADS) {
-        u32 g = a.sa[base + j];
         u32 hd = a.head[base + j];
-        u32 k2 = LDG(a.rank + cyc_add(a.v, g, a.h));
-        s_sa[j] = g;
-        s_key[j] = k2 | (hd == base + j ? 0x80000000u : 0u);
+        u32 fl = ((hd & ~HEAD_SETTLED) == base + j ? 1u : 0u) | ((hd >> 31) << 1);
+        s_fl[j] = (unsigned char)fl;
+        all_settled &= (int)(fl >> 1);
+    }
+    if (__syncthreads_and(all_settled)) { // every suffix of the tile has its final place
+        if (tid == 0) atomicAdd(a.ngroups, n);
+        return;
+    }
+    // 2. stage the suffixes; only those that still share a group pay for the two gathers
+    for (u32 j = tid; j < n; j += RF_THREADS) {
+        u32 fl = s_fl[j];
+        bool single = (fl & 1u) && (j + 1 == n || (s_fl[j + 1] & 1u));
+        u32 k2 = 0;
+        if (!(single && (fl & 2u))) {
+            u32 g = a.sa[base + j];
+            s_sa[j] = g;
+            if (!single) k2 = LDG(a.rank + cyc_add(a.v, g, a.h));
+        }
+        s_k2[j] = k2 | ((fl & 1u) << 31);
     }
     __syncthreads();
-    // 2. first suffix of the group of each of my RF_ITEMS consecutive suffixes (block max-scan)
+    // 3. first place of the group of each of my RF_ITEMS consecutive suffixes (block max-scan)
     const u32 j0 = tid * RF_ITEMS;
-    u32 mykey[RF_ITEMS], seg[RF_ITEMS];
+    u64 myck[RF_ITEMS];
+    u32 seg[RF_ITEMS];
     u32 run = 0;
+    bool lonely = true; // all of mine stand alone: nothing to count
 #pragma unroll
     for (int e = 0; e < RF_ITEMS; e++) {
         u32 j = j0 + e;
-        u32 w = (j < n) ? s_key[j] : 0x80000000u;
-        mykey[e] = w & 0x7FFFFFFFu;
+        u32 w = (j < n) ? s_k2[j] : 0x80000000u;
         if (w >> 31) run = j;
-        seg[e] = run; // exact once the prefix from the threads before is added
+        seg[e] = run;
+        myck[e] = (u64)(w & 0x7FFFFFFFu);
+        if (j < n && !((w >> 31) && (j + 1 == n || (s_k2[j + 1] >> 31)))) lonely = false;
     }
     u32 total;
     u32 before = block_scan_excl(run, total, ScanMax(), s_scan);
-#pragma unroll
-    for (int e = 0; e < RF_ITEMS; e++) seg[e] = seg[e] > before ? seg[e] : before;
-    // 3. stable counting rank inside the group: one walk over the group serves all my suffixes in it
-    u32 cnt[RF_ITEMS];
-#pragma unroll
-    for (int e = 0; e < RF_ITEMS; e++) cnt[e] = 0;
+    u32 seg_last = 0;
 #pragma unroll
     for (int e = 0; e < RF_ITEMS; e++) {
-        const bool first_of_run = (j0 + e < n) && (e == 0 || seg[e] != seg[e == 0 ? 0 : e - 1]);
-        if (first_of_run) {
-            const u32 s0 = seg[e];
-            for (u32 k = s0; k < n; k++) {
-                u32 w = s_key[k];
-                if (k > s0 && (w >> 31)) break;
-                u32 kk = w & 0x7FFFFFFFu;
+        u32 j = j0 + e;
+        seg[e] = seg[e] > before ? seg[e] : before;
+        myck[e] = ((u64)seg[e] << 42) | (myck[e] << 11) | j;
+        if (j < n) { s_ck[j] = myck[e]; seg_last = seg[e]; }
+    }
+    __syncthreads();
+    // 4. sorted place = first place of my first group + number of smaller composites from there on
+    u32 cnt[RF_ITEMS];
 #pragma unroll
-                for (int x = e; x < RF_ITEMS; x++)
-                    if (seg[x] == s0 && j0 + x < n) cnt[x] += (kk < mykey[x] || (kk == mykey[x] && k < j0 + x)) ? 1u : 0u;
-            }
+    for (int e = 0; e < RF_ITEMS; e++) cnt[e] = j0 + e - seg[0];
+    if (!lonely) {
+#pragma unroll
+        for (int e = 0; e < RF_ITEMS; e++) cnt[e] = 0;
+        for (u32 k = seg[0]; k < n; k++) {
+            u64 ck = s_ck[k];
+            if ((u32)(ck >> 42) > seg_last) break;
+#pragma unroll
+            for (int e = 0; e < RF_ITEMS; e++) cnt[e] += (ck < myck[e]) ? 1u : 0u;
         }
     }
-    // 4. move to the sorted place; the suffix that lands on the group's first place carries the border
+    __syncthreads(); // s_ck is dead from here: s_okey may overwrite it
+    // 5. move; the suffix that lands on its group's first place carries the border
 #pragma unroll
-    for (int x = 0; x < RF_ITEMS; x++) {
-        u32 j = j0 + x;
+    for (int e = 0; e < RF_ITEMS; e++) {
+        u32 j = j0 + e;
         if (j < n) {
-            u32 p = seg[x] + cnt[x];
+            u32 p = seg[0] + cnt[e];
             s_osa[p] = s_sa[j];
-            s_okey[p] = mykey[x] | (p == seg[x] ? 0x80000000u : 0u);
+            s_okey[p] = ((u32)(myck[e] >> 11) & 0x7FFFFFFFu) | (p == seg[e] ? 0x80000000u : 0u);
         }
     }
     __syncthreads();
-    // 5. new borders: an old border, or a change of the second rank; new heads by max-scan
+    // 6. new borders: an old border, or a change of the second rank; new heads by max-scan
     u32 hd[RF_ITEMS];
     u32 run2 = 0, nflag = 0;
 #pragma unroll
-    for (int x = 0; x < RF_ITEMS; x++) {
-        u32 j = j0 + x;
+    for (int e = 0; e < RF_ITEMS; e++) {
+        u32 j = j0 + e;
         if (j < n) {
             u32 w = s_okey[j];
             bool f = (w >> 31) || j == 0 || (w & 0x7FFFFFFFu) != (s_okey[j - 1] & 0x7FFFFFFFu);
             if (f) { run2 = j; nflag++; }
         }
-        hd[x] = run2;
+        hd[e] = run2;
     }
     u32 total2;
     u32 before2 = block_scan_excl(run2, total2, ScanMax(), s_scan);
     if (nflag) atomicAdd(&s_count, nflag);
 #pragma unroll
-    for (int x = 0; x < RF_ITEMS; x++) {
-        u32 j = j0 + x;
-        if (j < n) s_key[j] = base + (hd[x] > before2 ? hd[x] : before2); // reuse s_key for the heads
+    for (int e = 0; e < RF_ITEMS; e++) {
+        u32 j = j0 + e;
+        if (j < n) s_k2[j] = base + (hd[e] > before2 ? hd[e] : before2);
     }
     __syncthreads();
-    // 6. write back, coalesced; the new rank of every suffix goes to the other rank buffer
+    // 7. write back, coalesced.  The new rank goes to the OTHER rank buffer (a round reads only the
+    //    ranks of the round before); a suffix that stood alone at the start keeps its place and is
+    //    settled from now on: its rank is in both buffers.
     for (u32 j = tid; j < n; j += RF_THREADS) {
-        u32 g = s_osa[j], h2 = s_key[j];
-        a.sa[base + j] = g;
-        a.head[base + j] = h2;
-        a.rank2[g] = h2;
+        u32 fl = s_fl[j];
+        bool single = (fl & 1u) && (j + 1 == n || (s_fl[j + 1] & 1u));
+        if (single) {
+            if (!(fl & 2u)) {
+                a.rank2[s_osa[j]] = base + j;
+                a.head[base + j] = (base + j) | HEAD_SETTLED;
+            }
+        } else {
+            u32 g = s_osa[j], h2 = s_k2[j];
+            a.sa[base + j] = g;
+            a.head[base + j] = h2;
+            a.rank2[g] = h2;
+        }
     }
     if (tid == 0) atomicAdd(a.ngroups, s_count);
 }
