@@ -489,11 +489,14 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
     BatchView v = view_of(c);
 
     mark(c, 0);
-    { EncodeArgs a{v, P<unsigned char>(c->raw)}; launch_encode(ex, N, a); }
+    u32 *any_other = P<u32>(c->counter) + 8;
+    TRY(dev_zero(ex, any_other, sizeof(u32)));
+    { EncodeArgs a{v, P<unsigned char>(c->raw), any_other}; launch_encode(ex, N, a); }
     { PackArgs a{v}; launch_pack(ex, (long long)c->TW, a); }
     TRY(stage_suffix_array(c, v));
     mark(c, 1);
-    { LcpArgs a{v, P<u32>(c->sa), P<u32>(c->t2)}; launch_lcp(ex, N, a); }
+    { IsaArgs a{P<u32>(c->sa), P<u32>(c->t1)}; launch_isa(ex, N, a); }
+    { LcpArgs a{v, P<u32>(c->sa), P<u32>(c->t1), P<u32>(c->t2), any_other}; launch_lcp(ex, ((long long)N + LCP_CHUNK - 1) / LCP_CHUNK, a); }
     mark(c, 2);
     TRY(dev_zero(ex, c->set_flags.p, sizeof(u32) * nsets));
     TRY(stage_common_blocks(c, v));

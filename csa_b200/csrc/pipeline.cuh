@@ -70,10 +70,12 @@ HD u32 cyc_add(const BatchView &v, u32 g, u32 h) {
 }
 
 // ---- stage 0: encode + pack ------------------------------------------------------------------
-struct EncodeArgs { BatchView v; const unsigned char *raw; };
+struct EncodeArgs { BatchView v; const unsigned char *raw; u32 *any_other; };
 HD void encode_body(long long i, const EncodeArgs &a) {
     u32 g = (u32)i;
-    a.v.code[g] = (unsigned char)code_of_letter(a.raw[g]);
+    unsigned c = code_of_letter(a.raw[g]);
+    a.v.code[g] = (unsigned char)c;
+    if (c > 3) *a.any_other = 1u; // same value from every writer
     a.v.seqof[g] = upper_bound_u32(a.v.seq_off, a.v.M + 1, g) - 1;
 }
 MAP_KERNEL(encode, EncodeArgs, 6)
@@ -190,29 +192,59 @@ HD int ctz32(u32 x) {
 #endif
 }
 
-struct LcpArgs { BatchView v; const u32 *sa; u32 *lcp; };
-HD void lcp_body(long long i, const LcpArgs &a) {
-    if (i == 0) { a.lcp[0] = 0; return; }
-    u32 ga = a.sa[i - 1], gb = a.sa[i];
-    u32 ka = LDG(a.v.seqof + ga), kb = LDG(a.v.seqof + gb);
-    if (LDG(a.v.seq_set + ka) != LDG(a.v.seq_set + kb)) { a.lcp[i] = 0; return; }
-    u32 oa = LDG(a.v.seq_off + ka), ob = LDG(a.v.seq_off + kb);
-    u32 na = LDG(a.v.seq_off + ka + 1) - oa, nb = LDG(a.v.seq_off + kb + 1) - ob;
-    u32 cap = na < nb ? na : nb;
-    u64 xa = LDG(a.v.dbl_off + ka) + (ga - oa), xb = LDG(a.v.dbl_off + kb) + (gb - ob);
-    u32 t = 0;
-    while (t < cap) {
-        u64 d2 = fetch2(a.v.p2, xa + t) ^ fetch2(a.v.p2, xb + t);
-        u32 dm = fetchm(a.v.pm, xa + t) ^ fetchm(a.v.pm, xb + t);
-        int f = 32;
-        if (d2) f = ctz64(d2) >> 1;
-        if (dm) { int f2 = ctz32(dm); if (f2 < f) f = f2; }
-        if (f < 32) { t += (u32)f; break; }
-        t += 32;
+// Text order (Kasai): if rotation p shares L letters with its SA predecessor, rotation p+1 shares at
+// least L-1 with its own, so a thread that walks LCP_CHUNK consecutive positions of a sequence
+// extends one running match instead of starting every comparison at letter 0.  Cost per suffix: the
+// inverse SA entry (coalesced), sa[r-1] and the predecessor's sequence (gathers), ~1-2 word compares
+// on the L2-resident packed text, one scattered 4 B store.
+#define LCP_CHUNK 32
+struct IsaArgs { const u32 *sa; u32 *isa; };
+HD void isa_body(long long i, const IsaArgs &a) { a.isa[a.sa[i]] = (u32)i; }
+MAP_KERNEL(isa, IsaArgs, 12)
+
+struct LcpArgs { BatchView v; const u32 *sa; const u32 *isa; u32 *lcp; const u32 *any_other; };
+HD void lcp_body(long long t, const LcpArgs &a) {
+    const u32 g0 = (u32)t * LCP_CHUNK;
+    const u32 g1 = (g0 + LCP_CHUNK < a.v.N) ? g0 + LCP_CHUNK : a.v.N;
+    const bool masks = *a.any_other != 0; // any letter outside ACGT in the batch?
+    u32 k = CSA_NONE, off = 0, n = 0, s0 = 0;
+    u64 dk = 0;
+    u32 h = 0;
+    for (u32 g = g0; g < g1; g++) {
+        u32 kg = LDG(a.v.seqof + g);
+        if (kg != k) { // a new sequence begins: nothing carries over
+            k = kg;
+            off = LDG(a.v.seq_off + k);
+            n = LDG(a.v.seq_off + k + 1) - off;
+            s0 = LDG(a.v.set_base0 + LDG(a.v.seq_set + k));
+            dk = LDG(a.v.dbl_off + k);
+            h = 0;
+        }
+        u32 r = a.isa[g];
+        if (r == s0) { a.lcp[r] = 0; h = 0; continue; } // first suffix of its set
+        u32 b = a.sa[r - 1];
+        u32 kb = LDG(a.v.seqof + b);
+        u32 ob = LDG(a.v.seq_off + kb), nb = LDG(a.v.seq_off + kb + 1) - ob;
+        u32 cap = n < nb ? n : nb;
+        if (h > cap) h = cap;
+        u64 xa = dk + (g - off), xb = LDG(a.v.dbl_off + kb) + (b - ob);
+        while (h < cap) {
+            u64 d2 = fetch2(a.v.p2, xa + h) ^ fetch2(a.v.p2, xb + h);
+            int f = 32;
+            if (d2) f = ctz64(d2) >> 1;
+            if (masks) {
+                u32 dm = fetchm(a.v.pm, xa + h) ^ fetchm(a.v.pm, xb + h);
+                if (dm) { int f2 = ctz32(dm); if (f2 < f) f = f2; }
+            }
+            if (f < 32) { h += (u32)f; break; }
+            h += 32;
+        }
+        if (h > cap) h = cap;
+        a.lcp[r] = h;
+        if (h > 0) h--;
     }
-    a.lcp[i] = t < cap ? t : cap;
 }
-MAP_KERNEL(lcp, LcpArgs, 12)
+MAP_KERNEL(lcp, LcpArgs, 20 * LCP_CHUNK)
 
 // ---- stage 3: common blocks ------------------------------------------------------------------------
 // R[l] = smallest r such that SA[l..r] holds a suffix of every sequence of the set (>= end of the
