@@ -167,6 +167,10 @@ def main():
                           "gpu_launches": 0}))
         return 0
 
+    # rank 0 prints ONE line on stdout: anything libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -268,7 +272,7 @@ def main():
     # ---- the reference on this box's host cores (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        k = a.cpu_sets or min(nsets, cores * 12)
+        k = a.cpu_sets or min(nsets, cores * 24)
         r = cpu_reference_rate(batch_sets(batch, 0, k), cores)
         if r is not None:
             cpu = {k2: r[k2] for k2 in ("value", "unit", "cores", "kind", "sample")}
@@ -286,7 +290,10 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / a.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     rf.close()
     if world > 1:
         dist.destroy_process_group()

@@ -889,7 +889,7 @@ static inline void launch_refine(Exec &, const RefineArgs &a) {
 }
 #else
 #define HEAD_SETTLED 0x80000000u
-__global__ void __launch_bounds__(RF_THREADS) k_refine(RefineArgs a) {
+__global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
     // composite sort key of a suffix: (first place of its group in the tile : 11 bits, rank of the
     // next h letters : 31, place in the tile : 11).  It is unique and orders the whole tile, so the
     // number of smaller composites from the first group a thread touches onwards IS the sorted
@@ -898,7 +898,8 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine(RefineArgs a) {
     __shared__ u32 s_sa[RF_CAP];
     __shared__ u32 s_k2[RF_CAP];   // rank h letters on | 1<<31 on the first suffix of a group; later the new heads
     __shared__ u32 s_osa[RF_CAP];
-    __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled
+    __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled, bit 2 (at a group's
+                                               // first place): some member's second rank differs
     __shared__ u32 s_scan[33];
     __shared__ u32 s_count;
     u32 *s_okey = (u32 *)s_ck;     // sorted keys; s_ck is dead (and fenced) by then
@@ -908,28 +909,72 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine(RefineArgs a) {
     const u32 tid = threadIdx.x;
     if (tid == 0) s_count = 0;
     // 1. borders.  A settled suffix is a singleton whose rank is already in BOTH rank buffers.
+    //    (every phase that loads from HBM issues all RF_ITEMS loads of a thread before using any:
+    //    the gathers below are chains of four dependent L2/HBM accesses and need the overlap)
     int all_settled = 1;
-    for (u32 j = tid; j < n; j += RF_THREADS) {
-        u32 hd = a.head[base + j];
-        u32 fl = ((hd & ~HEAD_SETTLED) == base + j ? 1u : 0u) | ((hd >> 31) << 1);
-        s_fl[j] = (unsigned char)fl;
-        all_settled &= (int)(fl >> 1);
+    {
+        u32 hdv[RF_ITEMS];
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            u32 j = tid + x * RF_THREADS;
+            hdv[x] = (j < n) ? a.head[base + j] : 0u;
+        }
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            u32 j = tid + x * RF_THREADS;
+            if (j < n) {
+                u32 fl = ((hdv[x] & ~HEAD_SETTLED) == base + j ? 1u : 0u) | ((hdv[x] >> 31) << 1);
+                s_fl[j] = (unsigned char)fl;
+                all_settled &= (int)(fl >> 1);
+            }
+        }
     }
     if (__syncthreads_and(all_settled)) { // every suffix of the tile has its final place
         if (tid == 0) atomicAdd(a.ngroups, n);
         return;
     }
-    // 2. stage the suffixes; only those that still share a group pay for the two gathers
-    for (u32 j = tid; j < n; j += RF_THREADS) {
-        u32 fl = s_fl[j];
-        bool single = (fl & 1u) && (j + 1 == n || (s_fl[j + 1] & 1u));
-        u32 k2 = 0;
-        if (!(single && (fl & 2u))) {
-            u32 g = a.sa[base + j];
-            s_sa[j] = g;
-            if (!single) k2 = LDG(a.rank + cyc_add(a.v, g, a.h));
+    // 2. stage the suffixes; only those that still share a group pay for the gathers
+    {
+        u32 gv[RF_ITEMS], kv[RF_ITEMS], ov[RF_ITEMS], nv[RF_ITEMS], k2v[RF_ITEMS];
+        unsigned need = 0, share = 0; // bit x: my x-th suffix must be staged / still shares its group
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            u32 j = tid + x * RF_THREADS;
+            if (j < n) {
+                u32 fl = s_fl[j];
+                bool single = (fl & 1u) && (j + 1 == n || (s_fl[j + 1] & 1u));
+                if (!(single && (fl & 2u))) need |= 1u << x;
+                if (!single) share |= 1u << x;
+            }
         }
-        s_k2[j] = k2 | ((fl & 1u) << 31);
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) gv[x] = (need >> x & 1u) ? a.sa[base + tid + x * RF_THREADS] : 0u;
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) kv[x] = (share >> x & 1u) ? LDG(a.v.seqof + gv[x]) : 0u;
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            ov[x] = (share >> x & 1u) ? LDG(a.v.seq_off + kv[x]) : 0u;
+            nv[x] = (share >> x & 1u) ? LDG(a.v.seq_off + kv[x] + 1) : 1u;
+        }
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            k2v[x] = 0;
+            if (share >> x & 1u) {
+                u32 len = nv[x] - ov[x], hh = a.h;
+                if (hh >= len) hh %= len;
+                u32 q = gv[x] - ov[x] + hh;
+                if (q >= len) q -= len;
+                k2v[x] = LDG(a.rank + ov[x] + q);
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            u32 j = tid + x * RF_THREADS;
+            if (j < n) {
+                if (need >> x & 1u) s_sa[j] = gv[x];
+                s_k2[j] = k2v[x] | ((u32)(s_fl[j] & 1u) << 31);
+            }
+        }
     }
     __syncthreads();
     // 3. first place of the group of each of my RF_ITEMS consecutive suffixes (block max-scan)
@@ -955,13 +1000,24 @@ __global__ void __launch_bounds__(RF_THREADS) k_refine(RefineArgs a) {
         u32 j = j0 + e;
         seg[e] = seg[e] > before ? seg[e] : before;
         myck[e] = ((u64)seg[e] << 42) | (myck[e] << 11) | j;
-        if (j < n) { s_ck[j] = myck[e]; seg_last = seg[e]; }
+        if (j < n) {
+            s_ck[j] = myck[e];
+            seg_last = seg[e];
+            // a group whose members all carry the same second rank keeps its order: nothing to count
+            if ((u32)(myck[e] >> 11 & 0x7FFFFFFFu) != (s_k2[seg[e]] & 0x7FFFFFFFu)) s_fl[seg[e]] |= 4; // same bit from every writer
+        }
     }
     __syncthreads();
     // 4. sorted place = first place of my first group + number of smaller composites from there on
     u32 cnt[RF_ITEMS];
 #pragma unroll
     for (int e = 0; e < RF_ITEMS; e++) cnt[e] = j0 + e - seg[0];
+    if (!lonely) {
+        lonely = true;
+#pragma unroll
+        for (int e = 0; e < RF_ITEMS; e++)
+            if (j0 + e < n && (s_fl[seg[e]] & 4)) lonely = false;
+    }
     if (!lonely) {
 #pragma unroll
         for (int e = 0; e < RF_ITEMS; e++) cnt[e] = 0;

@@ -183,7 +183,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict
                                                            const u32 *__restrict__ offsets, long long n, int shift,
                                                            unsigned nblocks) {
     __shared__ u32 h[RS_WARPS][RS_BINS];
-    __shared__ u32 gbase[RS_BINS];
+    __shared__ u32 tstart[RS_BINS], gdelta[RS_BINS];
+    __shared__ u64 s_keys[RS_TILE];
+    __shared__ u32 s_vals[RS_TILE];
+    __shared__ u32 s_scan[33];
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,7 +216,11 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict
         rank[j] = before + __popc(peers & lt);
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
+    // per digit: offsets of the warps inside the tile's run of that digit, the run's start inside the
+    // digit-sorted tile (exclusive scan over the 256 digit totals) and its start in the output
+    u32 tot = 0;
+    {
+        const int d = threadIdx.x; // RS_THREADS == RS_BINS
         u32 run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
@@ -221,17 +228,35 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict
             h[w][d] = run;
             run += t;
         }
-        gbase[d] = offsets[(size_t)d * nblocks + blockIdx.x];
+        tot = run;
     }
+    u32 total;
+    u32 dstart = block_scan_excl(tot, total, ScanSum(), s_scan);
+    tstart[threadIdx.x] = dstart;
+    // the element that ends up at place q of the sorted tile goes to out[gbase[d] + q - tstart[d]]:
+    // fold both into one word so the write-out loop needs a single lookup
+    gdelta[threadIdx.x] = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x] - dstart;
     __syncthreads();
+    // stage the tile in digit order in shared memory ...
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
         unsigned d = dig[j];
         if (d < RS_BINS) {
-            u32 pos = gbase[d] + h[warp][d] + rank[j];
-            keys_out[pos] = k[j];
-            vals_out[pos] = v[j];
+            u32 q = tstart[d] + h[warp][d] + rank[j];
+            s_keys[q] = k[j];
+            s_vals[q] = v[j];
         }
+    }
+    __syncthreads();
+    // ... and write it out in that order: neighbouring threads write neighbouring addresses inside
+    // every digit's run (coalesced), instead of 32 scattered sectors per warp store
+    const u32 cnt = (u32)(((long long)blockIdx.x * RS_TILE + RS_TILE <= n) ? RS_TILE : (n - (long long)blockIdx.x * RS_TILE));
+    for (u32 q = threadIdx.x; q < cnt; q += RS_THREADS) {
+        u64 kk = s_keys[q];
+        unsigned d = (unsigned)(kk >> shift) & (RS_BINS - 1);
+        u32 pos = gdelta[d] + q;
+        keys_out[pos] = kk;
+        vals_out[pos] = s_vals[q];
     }
 }
 
