@@ -47,7 +47,7 @@ struct csa_gpu_ctx {
     DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, dbl_off, z0;
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, counter, tiles;
     int rounds_tiled = 0, rounds_global = 0, force_global_rounds = 0;
-    DevMem sa0, saidx0, leaf_set, lcp0, psv, nsv, pse, parent, nsize, minpos, val, up, val2, up2;
+    DevMem pyr, sa0, saidx0, leaf_set, lcp0, psv, nsv, pse, parent, nsize, minpos, val, up, val2, up2;
     DevMem set_nblocks, set_blk0, set_pos0, set_flags, set_nchains, set_cyclic, firstmax, set_collected, set_suffixfree;
     bool have_stats = false;
     std::vector<u32> h_set_collected, h_set_suffixfree;
@@ -122,7 +122,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
                      &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
-                     &c->t2, &c->t3, &c->t4, &c->counter, &c->tiles, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
+                     &c->t2, &c->t3, &c->t4, &c->counter, &c->tiles, &c->pyr, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
                      &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
@@ -394,7 +394,23 @@ static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
     { Seq0EmitArgs a{v, sa, flag0, idx0, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0emit(ex, N, a); }
     { Lcp0Args a{lcp, P<u32>(c->saidx0), P<u32>(c->leaf_set), P<u32>(c->z0), P<u32>(c->lcp0)}; launch_lcp0(ex, N0, a); }
     Seq0View q{N0, P<u32>(c->z0), P<u32>(c->leaf_set), P<u32>(c->lcp0)};
-    { AnsvArgs a{q, P<u32>(c->psv), P<u32>(c->nsv), P<u32>(c->pse)}; launch_ansv(ex, N0, a); }
+    Pyramid py;
+    {   // block minima of lcp0, factor 32 per level, all levels in one buffer
+        size_t tot = 0;
+        for (u32 sz = N0; sz > 32;) { sz = (sz + 31) / 32; tot += sz; }
+        TRY(dev_alloc(c->pyr, sizeof(u32) * (tot + 32)));
+        py.nlev = 1; py.lev[0] = P<u32>(c->lcp0); py.size[0] = N0;
+        u32 *next = P<u32>(c->pyr);
+        while (py.size[py.nlev - 1] > 32 && py.nlev < PYR_MAX) {
+            u32 nin = py.size[py.nlev - 1], nout = (nin + 31) / 32;
+            PyrArgs a{py.lev[py.nlev - 1], next, nin};
+            launch_pyr(ex, nout, a);
+            py.lev[py.nlev] = next; py.size[py.nlev] = nout; py.nlev++;
+            next += nout;
+        }
+        for (int l = py.nlev; l < PYR_MAX; l++) { py.lev[l] = nullptr; py.size[l] = 0; }
+    }
+    { AnsvArgs a{q, py, P<u32>(c->psv), P<u32>(c->nsv), P<u32>(c->pse)}; launch_ansv(ex, N0, a); }
     { TreeArgs a{q, P<u32>(c->psv), P<u32>(c->nsv), P<u32>(c->pse), P<u32>(c->sa0), P<u32>(c->parent), P<u32>(c->nsize), P<u32>(c->minpos)};
       launch_tree(ex, 2ll * N0, a); }
     { MinposArgs a{N0, P<u32>(c->parent), P<u32>(c->minpos)}; launch_minpos(ex, N0, a); }

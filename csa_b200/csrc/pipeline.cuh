@@ -402,22 +402,92 @@ HD void lcp0_body(long long t, const Lcp0Args &a) {
 }
 MAP_KERNEL(lcp0, Lcp0Args, 12)
 
-// nearest smaller / smaller-or-equal values around every border t (z0 < t < z1) of the set
-struct AnsvArgs { Seq0View q; u32 *psv; u32 *nsv; u32 *pse; };
+// nearest smaller / smaller-or-equal values around every border t (z0 < t < z1) of the set.
+// A pyramid of block minima (factor 32) over lcp0 turns every search into O(32 log_32 N0) steps
+// instead of a walk as long as the node is wide (the root's children span a quarter of the set).
+// lcp0 is 0 at the first leaf of every set: a sentinel that stops searches at the set's borders.
+#define PYR_MAX 8
+struct Pyramid { const u32 *lev[PYR_MAX]; u32 size[PYR_MAX]; int nlev; };
+struct PyrArgs { const u32 *in; u32 *out; u32 nin; };
+HD void pyr_body(long long i, const PyrArgs &a) {
+    u32 b0 = (u32)i * 32, b1 = b0 + 32 < a.nin ? b0 + 32 : a.nin;
+    u32 mn = 0xFFFFFFFFu;
+    for (u32 j = b0; j < b1; j++) { u32 x = a.in[j]; if (x < mn) mn = x; }
+    a.out[i] = mn;
+}
+MAP_KERNEL(pyr, PyrArgs, 4)
+
+// largest index < i whose value is < v (strict) or <= v; CSA_NONE if there is none
+HD u32 prev_below(const Pyramid &py, u32 i, u32 v, bool or_equal) {
+    int level = 0;
+    u32 pos = i;
+    for (;;) {
+        u32 b0 = pos & ~31u;
+        u32 p = pos;
+        while (p > b0) {
+            u32 x = py.lev[level][p - 1];
+            if (or_equal ? x <= v : x < v) {
+                p--;
+                while (level > 0) { // walk down to the rightmost qualifying entry
+                    level--;
+                    u32 c1 = p * 32 + 32 < py.size[level] ? p * 32 + 32 : py.size[level];
+                    u32 c = c1;
+                    for (;;) {
+                        u32 y = py.lev[level][c - 1];
+                        if (or_equal ? y <= v : y < v) break;
+                        c--;
+                    }
+                    p = c - 1;
+                }
+                return p;
+            }
+            p--;
+        }
+        if (b0 == 0 || level + 1 >= py.nlev) return CSA_NONE;
+        pos = b0 >> 5;
+        level++;
+    }
+}
+// smallest index > i whose value is < v; CSA_NONE if there is none
+HD u32 next_below(const Pyramid &py, u32 i, u32 v) {
+    int level = 0;
+    u32 pos = i + 1; // first candidate
+    for (;;) {
+        u32 b1 = (pos + 31) & ~31u; // end of the block that holds pos (pos itself if it starts a block)
+        if (b1 > py.size[level]) b1 = py.size[level];
+        u32 p = pos;
+        while (p < b1) {
+            if (py.lev[level][p] < v) {
+                while (level > 0) {
+                    level--;
+                    u32 c = p * 32;
+                    while (!(py.lev[level][c] < v)) c++;
+                    p = c;
+                }
+                return p;
+            }
+            p++;
+        }
+        if (level + 1 >= py.nlev) return CSA_NONE;
+        pos = (pos + 31) >> 5; // first block to the right not yet looked at
+        level++;
+        if (pos >= py.size[level]) return CSA_NONE;
+    }
+}
+
+struct AnsvArgs { Seq0View q; Pyramid py; u32 *psv; u32 *nsv; u32 *pse; };
 HD void ansv_body(long long ti, const AnsvArgs &a) {
     u32 t = (u32)ti;
     u32 s = a.q.leaf_set[t];
     u32 z0 = LDG(a.q.z0 + s), z1 = LDG(a.q.z0 + s + 1);
     if (t == z0) { a.psv[t] = z0; a.nsv[t] = z1; a.pse[t] = z0; return; }
     u32 v = a.q.lcp0[t];
-    u32 j = t - 1;
-    while (j > z0 && a.q.lcp0[j] > v) j--;
-    a.pse[t] = j; // z0 = none
-    while (j > z0 && a.q.lcp0[j] >= v) j--;
-    a.psv[t] = j;
-    j = t + 1;
-    while (j < z1 && a.q.lcp0[j] >= v) j++;
-    a.nsv[t] = j; // z1 = none
+    u32 j = prev_below(a.py, t, v, true);
+    a.pse[t] = (j == CSA_NONE || j < z0) ? z0 : j; // z0 = none
+    j = prev_below(a.py, t, v, false);
+    a.psv[t] = (j == CSA_NONE || j < z0) ? z0 : j;
+    j = next_below(a.py, t, v);
+    a.nsv[t] = (j == CSA_NONE || j > z1) ? z1 : j; // z1 = none
 }
 MAP_KERNEL(ansv, AnsvArgs, 16)
 
