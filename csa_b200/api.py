@@ -64,6 +64,8 @@ def _load(path):
     lib.csa_gpu_last_error.restype = C.c_char_p
     lib.csa_gpu_set_stream.argtypes = [vp, vp]
     lib.csa_gpu_batch_upload_flat.argtypes = [vp, i, ip, C.c_char_p, C.POINTER(C.c_longlong)]
+    lib.csa_gpu_pin_host.argtypes = [vp, C.c_ulonglong]
+    lib.csa_gpu_unpin_host.argtypes = [vp]
     lib.csa_gpu_batch_run.argtypes = [vp, i, C.c_uint]
     lib.csa_gpu_batch_download.argtypes = [vp, ip, C.POINTER(SetInfo)]
     lib.csa_gpu_batch_num_blocks.argtypes = [vp]
@@ -141,6 +143,15 @@ class RotationFinder:
     def _check(self, rc):
         if rc != 0:
             raise CsaGpuError(rc, self.lib.csa_gpu_last_error().decode(errors="replace"))
+
+    def pin(self, batch: "Batch"):
+        """page-lock the batch's text so that upload() needs no staging copy"""
+        addr = C.cast(C.c_char_p(batch.text), C.c_void_p)
+        self._check(self.lib.csa_gpu_pin_host(addr, len(batch.text)))
+        return addr
+
+    def unpin(self, addr):
+        self._check(self.lib.csa_gpu_unpin_host(addr))
 
     # ---- the three steps, separately (bench.py times run() alone and all three together) ----
     def upload(self, batch: Batch):

@@ -159,7 +159,8 @@ static int pinned_reserve(csa_gpu_ctx *c, size_t bytes) {
 // ---- upload ----------------------------------------------------------------------------------------
 // describe the batch; `fill` copies the letters of sequence k into the staging buffer
 template <class Fill>
-static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const long long *lens, Fill fill) {
+static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const long long *lens, Fill fill,
+                         const char *direct = nullptr) {
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
     if (nsets < 1 || !set_start) CSA_FAIL(CSA_GPU_EINVAL, "batch needs at least one set");
     if (set_start[0] != 0) CSA_FAIL(CSA_GPU_EINVAL, "set_start[0] must be 0");
@@ -200,9 +201,20 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     c->h_set_seq0[nsets] = (u32)M; c->h_set_base0[nsets] = (u32)tot; c->h_z0[nsets] = z;
     c->N = (u32)tot; c->N0 = z; c->nmax = nmax; c->n0max = n0max; c->mmax = mmax; c->TW = dbl / 32 + 2;
     u32 N = c->N;
-    // stage the letters
-    TRY(pinned_reserve(c, (size_t)N));
-    for (long long k = 0; k < M; k++) fill((int)k, (char *)c->pinned + c->h_seq_off[k]);
+    // stage the letters in pinned memory -- unless the caller's buffer is one contiguous, page-locked
+    // block already (cudaHostRegister / csa_gpu_pin_host): then the copy engine reads it in place
+    const void *src = direct;
+#ifndef CSA_EMU
+    if (src) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); src = nullptr; }
+    }
+#endif
+    if (!src) {
+        TRY(pinned_reserve(c, (size_t)N));
+        for (long long k = 0; k < M; k++) fill((int)k, (char *)c->pinned + c->h_seq_off[k]);
+        src = c->pinned;
+    }
 #ifndef CSA_EMU
     CUDA_TRY(cudaSetDevice(c->device));
 #endif
@@ -213,7 +225,7 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     TRY(dev_alloc(c->set_seq0, sizeof(u32) * (nsets + 1))); TRY(dev_alloc(c->set_base0, sizeof(u32) * (nsets + 1)));
     TRY(dev_alloc(c->set_nmin, sizeof(u32) * nsets)); TRY(dev_alloc(c->dbl_off, sizeof(u64) * (M + 1)));
     TRY(dev_alloc(c->z0, sizeof(u32) * (nsets + 1)));
-    TRY(h2d(ex, c->raw.p, c->pinned, N));
+    TRY(h2d(ex, c->raw.p, src, N));
     TRY(h2d(ex, c->seq_off.p, c->h_seq_off.data(), sizeof(u32) * (M + 1)));
     TRY(h2d(ex, c->seq_set.p, c->h_seq_set.data(), sizeof(u32) * M));
     TRY(h2d(ex, c->set_seq0.p, c->h_set_seq0.data(), sizeof(u32) * (nsets + 1)));
@@ -245,7 +257,26 @@ extern "C" int csa_gpu_batch_upload_flat(csa_gpu_ctx *c, int nsets, const int *s
     std::vector<long long> lens((size_t)M);
     for (long long k = 0; k < M; k++) lens[k] = text_start[k + 1] - text_start[k];
     return upload_common(c, nsets, set_start, lens.data(),
-                         [&](int k, char *dst) { memcpy(dst, text + text_start[k], (size_t)(text_start[k + 1] - text_start[k])); });
+                         [&](int k, char *dst) { memcpy(dst, text + text_start[k], (size_t)(text_start[k + 1] - text_start[k])); },
+                         text + text_start[0]);
+}
+
+// page-lock a host buffer so that uploads from it need no staging copy (cudaHostRegister)
+extern "C" int csa_gpu_pin_host(const void *p, unsigned long long bytes) {
+#ifndef CSA_EMU
+    CUDA_TRY(cudaHostRegister(const_cast<void *>(p), (size_t)bytes, cudaHostRegisterDefault));
+#else
+    (void)p; (void)bytes;
+#endif
+    return CSA_GPU_OK;
+}
+extern "C" int csa_gpu_unpin_host(const void *p) {
+#ifndef CSA_EMU
+    CUDA_TRY(cudaHostUnregister(const_cast<void *>(p)));
+#else
+    (void)p;
+#endif
+    return CSA_GPU_OK;
 }
 
 // ---- run --------------------------------------------------------------------------------------------

@@ -84,6 +84,10 @@ int csa_gpu_batch_upload(csa_gpu_ctx *ctx, int nsets, const int *set_start,
 /* same, from one contiguous buffer: sequence i is text[text_start[i] .. text_start[i+1]) */
 int csa_gpu_batch_upload_flat(csa_gpu_ctx *ctx, int nsets, const int *set_start,
                               const char *text, const long long *text_start);
+/* page-lock / release a host buffer (cudaHostRegister): csa_gpu_batch_upload_flat copies straight
+ * from a page-locked `text`, without the staging copy it otherwise makes */
+int csa_gpu_pin_host(const void *p, unsigned long long bytes);
+int csa_gpu_unpin_host(const void *p);
 /* all kernels; inputs and outputs stay in HBM.  max_interval: csamsa.c:27 (INT_MAX on R). */
 int csa_gpu_batch_run(csa_gpu_ctx *ctx, int max_interval, unsigned flags);
 /* rotations: one int per sequence of the batch (csamsa.h:12); info: one per set. */

@@ -163,3 +163,16 @@ def test_gpu_printed_counts(gpu_finder, golden):
     for i, (r, s) in enumerate(zip(gpu_finder.find_rotations_batch(cases, flags=1), cases)):
         assert r.count_collected >= 0
         compare_with_oracle(r, oracle_run(s), s, f"stats case {i}")
+
+
+def test_gpu_upload_from_page_locked_buffer(gpu_finder):
+    """csa_gpu_pin_host: the upload reads the caller's page-locked buffer in place; same answers"""
+    batch = workload_batch("mammals", 5, seed=17)
+    r0 = gpu_finder.find_rotations_batch(batch)
+    h = gpu_finder.pin(batch)
+    try:
+        r1 = gpu_finder.find_rotations_batch(batch)
+    finally:
+        gpu_finder.unpin(h)
+    for a, b in zip(r0, r1):
+        assert a.status == b.status and np.array_equal(a.rotations, b.rotations) and np.array_equal(a.positions, b.positions)
