@@ -316,10 +316,13 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
     u32 *head = P<u32>(c->t0), *rank = P<u32>(c->t1), *rank2 = P<u32>(c->t3), *counter = P<u32>(c->counter);
     u32 ntiles = (N + RF_NOMINAL - 1) / RF_NOMINAL;
     TRY(dev_alloc(c->tiles, sizeof(u32) * ((size_t)ntiles + 2)));
-    { InitKeyArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA)}; launch_initkey(ex, N, a); }
-    TRY(sort_pairs(c, N, 0, CSA_K0_BITS + bits_for((u64)c->nsets - 1)));
+    u32 any_other = 1;
+    TRY(read_u32(c, counter + 8, &any_other)); // set by k_encode: a letter outside ACGT somewhere in the batch
+    const int letters = any_other ? CSA_K0 : 12, lbits = any_other ? CSA_LETTER_BITS : 2;
+    { InitKeyArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA), letters, lbits}; launch_initkey(ex, N, a); }
+    TRY(sort_pairs(c, N, 0, letters * lbits + bits_for((u64)c->nsets - 1)));
     int nbits = bits_for((u64)N - 1);
-    u64 sorted_len = CSA_K0;
+    u64 sorted_len = (u64)letters;
     u32 ngroups = 0;
     TRY(heads_and_ranks(c, head, rank, counter, &ngroups));
     c->rounds_tiled = c->rounds_global = 0;

@@ -102,15 +102,17 @@ HD void pack_body(long long w, const PackArgs &a) {
 MAP_KERNEL(pack, PackArgs, 44)
 
 // ---- stage 1: suffix array by prefix doubling --------------------------------------------------
-struct InitKeyArgs { BatchView v; u64 *keys; u32 *vals; };
+// letters/bits: 13 letters of 3 bits, or -- when the batch holds nothing but A,C,G,T -- 12 letters of
+// 2 bits, which with 8 bits of set number is a 32-bit key: four radix passes instead of six
+struct InitKeyArgs { BatchView v; u64 *keys; u32 *vals; int letters; int bits; };
 HD void initkey_body(long long i, const InitKeyArgs &a) {
     u32 g = (u32)i;
     u32 k = LDG(a.v.seqof + g);
     u32 off = LDG(a.v.seq_off + k), n = LDG(a.v.seq_off + k + 1) - off;
     u32 p = g - off;
     u64 key = LDG(a.v.seq_set + k);
-    for (int t = 0; t < CSA_K0; t++) {
-        key = (key << CSA_LETTER_BITS) | a.v.code[off + p];
+    for (int t = 0; t < a.letters; t++) {
+        key = (key << a.bits) | a.v.code[off + p];
         if (++p == n) p = 0;
     }
     a.keys[g] = key;
@@ -717,46 +719,97 @@ struct ChainArgs {
     const u32 *set_blk0; const u32 *o_depth; const int *next; const int *gap;
     int *size; int *total; int *interval; u32 *set_nchains; u32 *set_flags;
 };
-HD void chain_body(long long s, const ChainArgs &a) {
-    u32 b0 = a.set_blk0[s], b1 = a.set_blk0[s + 1];
-    u32 B = b1 - b0;
+// the walk over one set's blocks; arrays are indexed from the set's first block (b0), `next` holds
+// batch-wide block numbers
+HD void chain_walk(u32 b0, u32 B, const u32 *depth, const int *next, const int *gap, int *size, int *total,
+                   int *interval, u32 *nchains, bool *hangs) {
     u32 mcs = B;
     long long guard_max = 4ll * B + 16;
     bool hang = false;
-    for (u32 b = b0; b < b1 && !hang; b++) {
-        if (a.total[b] == -1) continue;
-        a.size[b] = (int)a.o_depth[b];
+    for (u32 b = 0; b < B && !hang; b++) {
+        if (total[b] == -1) continue;
+        size[b] = (int)depth[b];
         u32 prev = b;
-        int cur = a.next[b];
+        int cur = next[b];
         long long guard = 0;
         while (cur != -1) {
             if (++guard > guard_max) { hang = true; break; }
-            int iv = a.gap[prev];
-            if (a.total[cur] > 0) {
-                a.size[b] += a.size[cur];
-                a.total[b] += a.total[cur];
-                a.interval[prev] = iv;
-                a.total[b] += iv;
-                a.size[cur] = (int)a.o_depth[cur];
-                a.total[cur] = -1;
+            u32 c = (u32)cur - b0;
+            int iv = gap[prev];
+            if (total[c] > 0) {
+                size[b] += size[c];
+                total[b] += total[c];
+                interval[prev] = iv;
+                total[b] += iv;
+                size[c] = (int)depth[c];
+                total[c] = -1;
                 mcs--;
                 break;
             }
-            a.size[cur] = (int)a.o_depth[cur];
-            a.size[b] += a.size[cur];
-            a.interval[prev] = iv;
-            a.total[b] += iv;
-            a.total[cur] = -1;
+            size[c] = (int)depth[c];
+            size[b] += size[c];
+            interval[prev] = iv;
+            total[b] += iv;
+            total[c] = -1;
             mcs--;
-            prev = (u32)cur;
-            cur = a.next[cur];
+            prev = c;
+            cur = next[c];
         }
-        a.total[b] += a.size[b];
+        total[b] += size[b];
     }
+    *nchains = mcs;
+    *hangs = hang;
+}
+#ifdef CSA_EMU
+HD void chain_body(long long s, const ChainArgs &a) {
+    u32 b0 = a.set_blk0[s], B = a.set_blk0[s + 1] - b0;
+    u32 mcs;
+    bool hang;
+    chain_walk(b0, B, a.o_depth + b0, a.next + b0, a.gap + b0, a.size + b0, a.total + b0, a.interval + b0, &mcs, &hang);
     a.set_nchains[s] = mcs;
     if (hang) ATOMIC_MAX(a.set_flags + s, 2u);
 }
 MAP_KERNEL(chain, ChainArgs, 16)
+#else
+// one CTA per set: the walk is a chain of dependent loads, so the set's block arrays are brought
+// into shared memory first (a mitogenome set has a few hundred blocks) and one thread walks them
+// there; sets with more blocks than fit are walked in global memory
+#define CH_THREADS 128
+#define CH_CAP 1536
+__global__ void __launch_bounds__(CH_THREADS) k_chain(ChainArgs a) {
+    __shared__ u32 s_depth[CH_CAP];
+    __shared__ int s_next[CH_CAP], s_gap[CH_CAP], s_size[CH_CAP], s_total[CH_CAP], s_interval[CH_CAP];
+    const u32 s = blockIdx.x;
+    const u32 b0 = a.set_blk0[s], B = a.set_blk0[s + 1] - b0;
+    u32 mcs = 0;
+    bool hang = false;
+    if (B <= CH_CAP) {
+        for (u32 i = threadIdx.x; i < B; i += CH_THREADS) {
+            s_depth[i] = a.o_depth[b0 + i]; s_next[i] = a.next[b0 + i]; s_gap[i] = a.gap[b0 + i];
+            s_size[i] = 0; s_total[i] = 0; s_interval[i] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) chain_walk(b0, B, s_depth, s_next, s_gap, s_size, s_total, s_interval, &mcs, &hang);
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < B; i += CH_THREADS) {
+            a.size[b0 + i] = s_size[i]; a.total[b0 + i] = s_total[i]; a.interval[b0 + i] = s_interval[i];
+        }
+    } else if (threadIdx.x == 0) {
+        chain_walk(b0, B, a.o_depth + b0, a.next + b0, a.gap + b0, a.size + b0, a.total + b0, a.interval + b0, &mcs, &hang);
+    }
+    if (threadIdx.x == 0) {
+        a.set_nchains[s] = mcs;
+        if (hang) atomicMax(a.set_flags + s, 2u);
+    }
+}
+static inline void launch_chain(Exec &ex, long long nsets, ChainArgs a) {
+    if (nsets <= 0) return;
+    PROF_BEGIN(ex, "k_chain", 0.0);
+    k_chain<<<(unsigned)nsets, CH_THREADS, 0, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
 
 // sortList (nodeslinkedlists.c:59): stable, by chain size, descending
 struct SizeKeyArgs { const u32 *o_set; const int *size; u64 *keys; u32 *vals; };
