@@ -1024,13 +1024,13 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
     __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled, bit 2 (at a group's
                                                // first place): some member's second rank differs
     __shared__ u32 s_scan[33];
-    __shared__ u32 s_count;
+    __shared__ u32 s_count, s_big;
     u32 *s_okey = (u32 *)s_ck;     // sorted keys; s_ck is dead (and fenced) by then
     const u32 base = a.tb[blockIdx.x];
     const u32 n = a.tb[blockIdx.x + 1] - base;
     if (n == 0 || n > RF_CAP) return;
     const u32 tid = threadIdx.x;
-    if (tid == 0) s_count = 0;
+    if (tid == 0) { s_count = 0; s_big = 0; }
     // 1. borders.  A settled suffix is a singleton whose rank is already in BOTH rank buffers.
     //    (every phase that loads from HBM issues all RF_ITEMS loads of a thread before using any:
     //    the gathers below are chains of four dependent L2/HBM accesses and need the overlap)
@@ -1100,11 +1100,12 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
         }
     }
     __syncthreads();
-    // 3. first place of the group of each of my RF_ITEMS consecutive suffixes (block max-scan)
+    // 3. first place of the group of each of my RF_ITEMS consecutive suffixes (block max-scan), and the
+    //    list of the groups that still hold more than one suffix (block sum-scan)
     const u32 j0 = tid * RF_ITEMS;
     u64 myck[RF_ITEMS];
     u32 seg[RF_ITEMS];
-    u32 run = 0;
+    u32 run = 0, nlist = 0, listmask = 0;
     bool lonely = true; // all of mine stand alone: nothing to count
 #pragma unroll
     for (int e = 0; e < RF_ITEMS; e++) {
@@ -1113,15 +1114,84 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
         if (w >> 31) run = j;
         seg[e] = run;
         myck[e] = (u64)(w & 0x7FFFFFFFu);
-        if (j < n && !((w >> 31) && (j + 1 == n || (s_k2[j + 1] >> 31)))) lonely = false;
+        if (j < n && !((w >> 31) && (j + 1 == n || (s_k2[j + 1] >> 31)))) {
+            lonely = false;
+            if (w >> 31) { nlist++; listmask |= 1u << e; }
+        }
     }
     u32 total;
     u32 before = block_scan_excl(run, total, ScanMax(), s_scan);
-    u32 seg_last = 0;
+    bool big = false;
 #pragma unroll
     for (int e = 0; e < RF_ITEMS; e++) {
         u32 j = j0 + e;
         seg[e] = seg[e] > before ? seg[e] : before;
+        if (j < n && j - seg[e] >= 32u) big = true;
+    }
+    if (big) s_big = 1; // same value from every writer; read after the barriers of the scan below
+    u32 ngroups_listed;
+    u32 lbefore = block_scan_excl(nlist, ngroups_listed, ScanSum(), s_scan);
+    if (!s_big) {
+        // 3w. no group of the tile is longer than a warp: one warp per group, one suffix per lane.
+        //     Ranks come from repeated min-reductions over the group's second ranks: every distinct
+        //     value is one new group, its members keep their order (stable), and the new head falls
+        //     out of the same loop -- no composite keys, no counting loop, no second scan.
+        u32 *s_gstart = s_osa;
+#pragma unroll
+        for (int e = 0; e < RF_ITEMS; e++)
+            if (listmask >> e & 1u) s_gstart[lbefore++] = j0 + e;
+        __syncthreads();
+        const unsigned lane = tid & 31u, warp = tid >> 5, ltmask = (1u << lane) - 1u;
+        u32 made = 0;
+        for (u32 gi = warp; gi < ngroups_listed; gi += RF_THREADS / 32) {
+            const u32 S = s_gstart[gi];
+            const u32 j = S + lane;
+            const u32 w = (j < n) ? s_k2[j] : 0x80000000u;
+            const unsigned nextstart = __ballot_sync(0xffffffffu, lane > 0 && (w >> 31));
+            const u32 size = nextstart ? (u32)(__ffs((int)nextstart) - 1) : 32u;
+            const bool member = lane < size;
+            const u32 k2 = member ? (w & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+            const u32 g = member ? s_sa[j] : 0u;
+            unsigned rem = __ballot_sync(0xffffffffu, member);
+            u32 placed = 0, mynew = 0, myhead = 0;
+            while (rem) {
+                const u32 kk = (rem >> lane & 1u) ? k2 : 0xFFFFFFFFu;
+                const u32 mn = __reduce_min_sync(0xffffffffu, kk);
+                const unsigned eq = __ballot_sync(0xffffffffu, kk == mn) & rem;
+                if (eq >> lane & 1u) { mynew = placed + __popc(eq & ltmask); myhead = placed; }
+                placed += __popc(eq);
+                rem &= ~eq;
+                made++;
+            }
+            if (member) {
+                const u32 p = base + S + mynew, h2 = base + S + myhead;
+                a.sa[p] = g;
+                a.head[p] = h2;
+                a.rank2[g] = h2;
+            }
+        }
+        u32 nsingle = 0;
+        for (u32 j = tid; j < n; j += RF_THREADS) {
+            u32 fl = s_fl[j];
+            if ((fl & 1u) && (j + 1 == n || (s_fl[j + 1] & 1u))) {
+                nsingle++;
+                if (!(fl & 2u)) {
+                    a.rank2[s_sa[j]] = base + j;
+                    a.head[base + j] = (base + j) | HEAD_SETTLED;
+                }
+            }
+        }
+        if (lane == 0) nsingle += made;
+        if (nsingle) atomicAdd(&s_count, nsingle);
+        __syncthreads();
+        if (tid == 0) atomicAdd(a.ngroups, s_count);
+        return;
+    }
+    // 3c. a group longer than a warp: composite keys and a counting rank over shared memory
+    u32 seg_last = 0;
+#pragma unroll
+    for (int e = 0; e < RF_ITEMS; e++) {
+        u32 j = j0 + e;
         myck[e] = ((u64)seg[e] << 42) | (myck[e] << 11) | j;
         if (j < n) {
             s_ck[j] = myck[e];
