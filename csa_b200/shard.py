@@ -34,3 +34,27 @@ def find_rotations_sharded(finder: RotationFinder, sets: Sequence[Sequence[bytes
     if rank != 0:
         return None
     return [x for part in gathered for x in part]
+
+
+def batches_by_size(sets: Sequence[Sequence[bytes]], max_bases: int = 1 << 28):
+    """cut a long list of sets into batches of at most `max_bases` letters (one batch's index space
+    is 32 bit and ~56 B/base of HBM): yields (first set, list of sets)"""
+    start, cur, tot = 0, [], 0
+    for i, s in enumerate(sets):
+        nb = sum(len(x) for x in s)
+        if cur and tot + nb > max_bases:
+            yield start, cur
+            start, cur, tot = i, [], 0
+        cur.append(s)
+        tot += nb
+    if cur:
+        yield start, cur
+
+
+def find_rotations_stream(finder: RotationFinder, sets: Sequence[Sequence[bytes]], max_bases: int = 1 << 28,
+                          flags: int = 0, with_blocks: bool = False) -> List[SetResult]:
+    """any number of independent sets through one GPU, batch after batch"""
+    out: List[SetResult] = []
+    for _, chunk in batches_by_size(sets, max_bases):
+        out.extend(finder.find_rotations_batch(chunk, flags=flags, with_blocks=with_blocks))
+    return out

@@ -48,3 +48,16 @@ def test_two_gloo_ranks(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(w), ROOT],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, env=env, text=True)
     assert p.returncode == 0 and "SHARD_OK 2" in p.stdout, p.stdout[-2000:]
+
+
+def test_stream_in_batches(emu_finder):
+    import random
+    from common import compare_with_oracle, gen_case, oracle_run
+    from csa_b200.shard import batches_by_size, find_rotations_stream
+    rng = random.Random(9)
+    sets = [gen_case(rng, max_n=450)[1] for _ in range(23)]
+    cuts = list(batches_by_size(sets, 3000))
+    assert len(cuts) > 3 and sum(len(c) for _, c in cuts) == len(sets) and [s for s, _ in cuts] == sorted(s for s, _ in cuts)
+    res = find_rotations_stream(emu_finder, sets, max_bases=3000, with_blocks=True)
+    for i, (r, s) in enumerate(zip(res, sets)):
+        compare_with_oracle(r, oracle_run(s), s, f"stream set {i}")
