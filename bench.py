@@ -45,43 +45,57 @@ def env_int(name, default):
 
 # ---- clocks during the timed region ---------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons while the timed steps run: NVML polled every ~2 ms from a thread
+    (the timed region of a short run is shorter than one `nvidia-smi -lms` period)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, cuda_index):
+        self.samples, self.stop_flag, self.thread, self.h, self.nv = [], False, None, None, None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(cuda_index)
+            try:
+                bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.nv = pynvml
+        except Exception as e:  # no NVML: say so in the line
+            self.err = repr(e)
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(get_reasons(h)),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        rows = [r for r in self.samples if t0 <= r[0] <= t1] or self.samples
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for j, n in enumerate(names) if any(r[5 + j].lower() == "active" for r in rows)]
-        def num(x):
-            try:
-                return float(x)
-            except ValueError:
-                return None
-        sm = [num(r[1]) for r in rows if num(r[1]) is not None]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(rows[0][2]),
-                "power_w_max": max([num(r[3]) or 0 for r in rows]), "samples": len(rows), "reasons": reasons}
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        return {"sm_mhz": statistics.median(r[1] for r in rows),
+                "sm_max_mhz": self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM),
+                "power_w_max": max(r[3] for r in rows), "samples": len(rows),
+                "reasons": [name for bit, name in self.REASONS.items() if bits & bit]}
 
 
 # ---- the reference's CPU implementation ---------------------------------------------------------------

@@ -359,7 +359,7 @@ static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     TRY(dev_zero(ex, c->firstmax.p, sizeof(u32) * nsets));
     { ColorKeyArgs a{v, sa, P<u64>(c->keysA), P<u32>(c->valsA)}; launch_colorkey(ex, N, a); }
     TRY(sort_pairs(c, N, 0, bits_for((u64)c->mmax - 1)));
-    { NextArgs a{v, sa, P<u32>(c->valsA), nxt, P<u32>(c->firstmax)}; launch_next(ex, N, a); }
+    { NextArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA), nxt, P<u32>(c->firstmax)}; launch_next(ex, N, a); }
     { CoverArgs a{v, sa, nxt, P<u32>(c->firstmax), R}; launch_cover(ex, N, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, R, R, N)));
     u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3), *bidx = P<u32>(c->t4);

@@ -58,6 +58,9 @@ HD u32 upper_bound_u64(const u64 *a, u32 n, u64 x) {
     return lo;
 }
 
+// set of SA position i: the suffix array is grouped by set, borders in set_base0 (a small, cached table)
+HD u32 set_of_pos(const BatchView &v, u32 i) { return upper_bound_u32(v.set_base0, (u32)v.nsets + 1, i) - 1; }
+
 // position h letters further round the circle
 HD u32 cyc_add(const BatchView &v, u32 g, u32 h) {
     u32 k = LDG(v.seqof + g);
@@ -257,33 +260,31 @@ MAP_KERNEL(lcp, LcpArgs, 20 * LCP_CHUNK)
 struct ColorKeyArgs { BatchView v; const u32 *sa; u64 *keys; u32 *vals; };
 HD void colorkey_body(long long i, const ColorKeyArgs &a) {
     u32 k = LDG(a.v.seqof + a.sa[i]);
-    a.keys[i] = k - LDG(a.v.set_seq0 + LDG(a.v.seq_set + k));
+    // low bits (the only ones sorted on): sequence-in-set; high word: the sequence, carried along so
+    // that k_next reads its neighbours' sequences from the sorted keys instead of gathering them
+    a.keys[i] = ((u64)k << 32) | (k - LDG(a.v.set_seq0 + LDG(a.v.seq_set + k)));
     a.vals[i] = (u32)i;
 }
 MAP_KERNEL(colorkey, ColorKeyArgs, 20)
 
 // after the sort: vals = SA indices ordered by (colour, index).  cover[i] (read at i+1) = next
 // index of the same sequence; cover[set start] collects the latest first occurrence.
-struct NextArgs { BatchView v; const u32 *sa; const u32 *vals; u32 *nxt; u32 *firstmax; };
+struct NextArgs { BatchView v; const u64 *keys; const u32 *vals; u32 *nxt; u32 *firstmax; };
 HD void next_body(long long j, const NextArgs &a) {
     u32 i = a.vals[j];
-    u32 k = LDG(a.v.seqof + a.sa[i]);
+    u32 k = (u32)(a.keys[j] >> 32);
     u32 s = LDG(a.v.seq_set + k);
-    u32 send = LDG(a.v.set_base0 + s + 1);
-    u32 nx = send;
-    if ((u32)j + 1 < a.v.N) {
-        u32 i2 = a.vals[j + 1];
-        if (LDG(a.v.seqof + a.sa[i2]) == k) nx = i2;
-    }
+    u32 nx = LDG(a.v.set_base0 + s + 1); // "none": the end of the set
+    if ((u32)j + 1 < a.v.N && (u32)(a.keys[j + 1] >> 32) == k) nx = a.vals[j + 1];
     a.nxt[i] = nx;
-    bool first = (j == 0) || LDG(a.v.seqof + a.sa[a.vals[j - 1]]) != k;
+    bool first = (j == 0) || (u32)(a.keys[j - 1] >> 32) != k;
     if (first) ATOMIC_MAX(a.firstmax + s, i);
 }
 MAP_KERNEL(next, NextArgs, 16)
 
 struct CoverArgs { BatchView v; const u32 *sa; const u32 *nxt; const u32 *firstmax; u32 *cover; };
 HD void cover_body(long long i, const CoverArgs &a) {
-    u32 s = LDG(a.v.seq_set + LDG(a.v.seqof + a.sa[i]));
+    u32 s = set_of_pos(a.v, (u32)i);
     u32 s0 = LDG(a.v.set_base0 + s);
     a.cover[i] = ((u32)i == s0) ? a.firstmax[s] : a.nxt[i - 1];
 }
@@ -292,11 +293,17 @@ MAP_KERNEL(cover, CoverArgs, 16)
 // blocks: LCP intervals of exactly m suffixes, one of every sequence, that cannot be extended to
 // the left by one and the same letter (csamsa.c:64,80,283).  One thread per left border.
 struct BlockFindArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *isblock; u32 *depth; };
+HD unsigned letter_before_suffix(const BatchView &v, u32 g) {
+    u32 k = LDG(v.seqof + g);
+    u32 off = LDG(v.seq_off + k), n = LDG(v.seq_off + k + 1) - off;
+    u32 p = g - off;
+    return v.code[off + (p == 0 ? n - 1 : p - 1)];
+}
+#ifdef CSA_EMU
 HD void blockfind_body(long long i, const BlockFindArgs &a) {
     u32 lb = (u32)i;
     a.isblock[lb] = 0;
-    u32 k0 = LDG(a.v.seqof + a.sa[lb]);
-    u32 s = LDG(a.v.seq_set + k0);
+    u32 s = set_of_pos(a.v, lb);
     u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
     u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
     if (lb + m > s1 || m < 2) return;
@@ -327,13 +334,70 @@ HD void blockfind_body(long long i, const BlockFindArgs &a) {
     a.depth[lb] = inner;
 }
 MAP_KERNEL(blockfind, BlockFindArgs, 16)
+#else
+// The same test, warp-cooperative: every lane screens one left border with the cover array; the
+// few candidates a warp finds are then examined by the whole warp, one suffix of the window per
+// lane -- smallest inner lcp by a min-reduction, "all preceded by one letter" by a ballot -- so the
+// m dependent gathers of a candidate run side by side instead of one after the other.
+__global__ void __launch_bounds__(256) k_blockfind(long long n, BlockFindArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    u32 lb = (u32)i, s0 = 0, s1 = 0, m = 0;
+    bool cand = false;
+    if (i < n) {
+        u32 s = set_of_pos(a.v, lb);
+        s0 = LDG(a.v.set_base0 + s); s1 = LDG(a.v.set_base0 + s + 1);
+        m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
+        cand = (lb + m <= s1 && m >= 2 && a.R[lb] == lb + m - 1); // m suffixes, every sequence once
+    }
+    u32 res = 0, resdepth = 0;
+    unsigned todo = __ballot_sync(0xffffffffu, cand);
+    while (todo) {
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1;
+        const u32 clb = __shfl_sync(0xffffffffu, lb, src), cm = __shfl_sync(0xffffffffu, m, src);
+        const u32 cs0 = __shfl_sync(0xffffffffu, s0, src), cs1 = __shfl_sync(0xffffffffu, s1, src);
+        const u32 crb = clb + cm - 1;
+        u32 inner = 0xFFFFFFFFu, c0 = 0xFFu;
+        bool same = true;
+        for (u32 j = clb + lane; j <= crb; j += 32) {
+            if (j > clb) { u32 l = a.lcp[j]; if (l < inner) inner = l; }
+            unsigned c = letter_before_suffix(a.v, a.sa[j]);
+            if (c0 == 0xFFu) c0 = c; else if (c != c0) same = false;
+        }
+        inner = __reduce_min_sync(0xffffffffu, inner);
+        // all letters alike: every lane's own letters alike, and all lanes that saw any agree
+        const unsigned have = __ballot_sync(0xffffffffu, c0 != 0xFFu);
+        const u32 first = __shfl_sync(0xffffffffu, c0, __ffs((int)have) - 1);
+        const bool all_same = __all_sync(0xffffffffu, same && (c0 == 0xFFu || c0 == first));
+        const long long outer_l = (clb == cs0) ? -1 : (long long)a.lcp[clb];
+        const long long outer_r = (crb + 1 == cs1) ? -1 : (long long)a.lcp[crb + 1];
+        const long long outer = outer_l > outer_r ? outer_l : outer_r;
+        // an LCP interval (inner > outer) that no single letter extends to the left (csamsa.c:80;
+        // :85 leaves a list holding only the root alone: depth 0)
+        const bool ok = (long long)inner > outer && !(inner > 0 && all_same);
+        if ((int)lane == src) { res = ok ? 1u : 0u; resdepth = inner; }
+    }
+    if (i < n) {
+        a.isblock[lb] = res;
+        if (res) a.depth[lb] = resdepth;
+    }
+}
+static inline void launch_blockfind(Exec &ex, long long n, BlockFindArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_blockfind", 16.0 * n);
+    k_blockfind<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
 
 // a whole rotation of the shortest sequence occurs in every sequence: the reference walks off its
 // tree (undefined behaviour).  Maximal runs of lcp >= nmin that hold every sequence.
 struct DegenArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *set_flags; };
 HD void degen_body(long long i, const DegenArgs &a) {
     u32 lb = (u32)i;
-    u32 s = LDG(a.v.seq_set + LDG(a.v.seqof + a.sa[lb]));
+    u32 s = set_of_pos(a.v, lb);
     u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
     u32 nmin = LDG(a.v.set_nmin + s);
     if (lb + 1 >= s1 || a.lcp[lb + 1] < nmin) return;
@@ -352,7 +416,7 @@ struct BlockEmitArgs {
 HD void blockemit_body(long long i, const BlockEmitArgs &a) {
     if (!a.isblock[i]) return;
     u32 b = a.bidx[i];
-    u32 s = LDG(a.v.seq_set + LDG(a.v.seqof + a.sa[i]));
+    u32 s = set_of_pos(a.v, (u32)i);
     a.blk_lb[b] = (u32)i;
     a.blk_depth[b] = a.depth[i];
     a.blk_set[b] = s;
@@ -873,7 +937,7 @@ MAP_KERNEL(rot, RotArgs, 8)
 struct WinDepthArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *dv; };
 HD void windepth_body(long long i, const WinDepthArgs &a) {
     u32 l = (u32)i;
-    u32 s = LDG(a.v.seq_set + LDG(a.v.seqof + a.sa[l]));
+    u32 s = set_of_pos(a.v, l);
     u32 s1 = LDG(a.v.set_base0 + s + 1);
     u32 r = a.R[l];
     if (r >= s1) { a.dv[l] = 0; return; } // no window: sorts below every depth
