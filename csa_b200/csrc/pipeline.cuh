@@ -61,9 +61,11 @@ HD u32 upper_bound_u64(const u64 *a, u32 n, u64 x) {
 // set of SA position i: the suffix array is grouped by set, borders in set_base0 (a small, cached table)
 HD u32 set_of_pos(const BatchView &v, u32 i) { return upper_bound_u32(v.set_base0, (u32)v.nsets + 1, i) - 1; }
 
+HD u32 seq_of(const BatchView &v, u32 g) { return LDG(v.seqof + g); }
+
 // position h letters further round the circle
 HD u32 cyc_add(const BatchView &v, u32 g, u32 h) {
-    u32 k = LDG(v.seqof + g);
+    u32 k = seq_of(v, g);
     u32 off = LDG(v.seq_off + k), n = LDG(v.seq_off + k + 1) - off;
     u32 p = g - off;
     if (h >= n) h %= n;
@@ -79,7 +81,8 @@ HD void encode_body(long long i, const EncodeArgs &a) {
     unsigned c = code_of_letter(a.raw[g]);
     a.v.code[g] = (unsigned char)c;
     if (c > 3) *a.any_other = 1u; // same value from every writer
-    a.v.seqof[g] = upper_bound_u32(a.v.seq_off, a.v.M + 1, g) - 1;
+    u32 k = upper_bound_u32(a.v.seq_off, a.v.M + 1, g) - 1;
+    a.v.seqof[g] = k;
 }
 MAP_KERNEL(encode, EncodeArgs, 6)
 
@@ -110,7 +113,7 @@ MAP_KERNEL(pack, PackArgs, 44)
 struct InitKeyArgs { BatchView v; u64 *keys; u32 *vals; int letters; int bits; };
 HD void initkey_body(long long i, const InitKeyArgs &a) {
     u32 g = (u32)i;
-    u32 k = LDG(a.v.seqof + g);
+    u32 k = seq_of(a.v, g);
     u32 off = LDG(a.v.seq_off + k), n = LDG(a.v.seq_off + k + 1) - off;
     u32 p = g - off;
     u64 key = LDG(a.v.seq_set + k);
@@ -216,7 +219,7 @@ HD void lcp_body(long long t, const LcpArgs &a) {
     u64 dk = 0;
     u32 h = 0;
     for (u32 g = g0; g < g1; g++) {
-        u32 kg = LDG(a.v.seqof + g);
+        u32 kg = seq_of(a.v, g);
         if (kg != k) { // a new sequence begins: nothing carries over
             k = kg;
             off = LDG(a.v.seq_off + k);
@@ -228,7 +231,7 @@ HD void lcp_body(long long t, const LcpArgs &a) {
         u32 r = a.isa[g];
         if (r == s0) { a.lcp[r] = 0; h = 0; continue; } // first suffix of its set
         u32 b = a.sa[r - 1];
-        u32 kb = LDG(a.v.seqof + b);
+        u32 kb = seq_of(a.v, b);
         u32 ob = LDG(a.v.seq_off + kb), nb = LDG(a.v.seq_off + kb + 1) - ob;
         u32 cap = n < nb ? n : nb;
         if (h > cap) h = cap;
@@ -259,7 +262,7 @@ MAP_KERNEL(lcp, LcpArgs, 20 * LCP_CHUNK)
 // The colour lists come from one stable radix pass of the SA indices by sequence-in-set.
 struct ColorKeyArgs { BatchView v; const u32 *sa; u64 *keys; u32 *vals; };
 HD void colorkey_body(long long i, const ColorKeyArgs &a) {
-    u32 k = LDG(a.v.seqof + a.sa[i]);
+    u32 k = seq_of(a.v, a.sa[i]);
     // low bits (the only ones sorted on): sequence-in-set; high word: the sequence, carried along so
     // that k_next reads its neighbours' sequences from the sorted keys instead of gathering them
     a.keys[i] = ((u64)k << 32) | (k - LDG(a.v.set_seq0 + LDG(a.v.seq_set + k)));
@@ -294,7 +297,7 @@ MAP_KERNEL(cover, CoverArgs, 16)
 // the left by one and the same letter (csamsa.c:64,80,283).  One thread per left border.
 struct BlockFindArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *isblock; u32 *depth; };
 HD unsigned letter_before_suffix(const BatchView &v, u32 g) {
-    u32 k = LDG(v.seqof + g);
+    u32 k = seq_of(v, g);
     u32 off = LDG(v.seq_off + k), n = LDG(v.seq_off + k + 1) - off;
     u32 p = g - off;
     return v.code[off + (p == 0 ? n - 1 : p - 1)];
@@ -322,7 +325,7 @@ HD void blockfind_body(long long i, const BlockFindArgs &a) {
         unsigned c0 = 0;
         for (u32 j = lb; j <= rb && same; j++) {
             u32 g = a.sa[j];
-            u32 k = LDG(a.v.seqof + g);
+            u32 k = seq_of(a.v, g);
             u32 off = LDG(a.v.seq_off + k), n = LDG(a.v.seq_off + k + 1) - off;
             u32 p = g - off;
             unsigned c = a.v.code[off + (p == 0 ? n - 1 : p - 1)];
@@ -434,7 +437,7 @@ MAP_KERNEL(blockemit, BlockEmitArgs, 8)
 //   before(v) = leaves under the siblings of v whose first occurrence precedes v's.
 struct Seq0FlagArgs { BatchView v; const u32 *sa; u32 *flag; };
 HD void seq0flag_body(long long i, const Seq0FlagArgs &a) {
-    u32 k = LDG(a.v.seqof + a.sa[i]);
+    u32 k = seq_of(a.v, a.sa[i]);
     a.flag[i] = (k == LDG(a.v.set_seq0 + LDG(a.v.seq_set + k))) ? 1u : 0u;
 }
 MAP_KERNEL(seq0flag, Seq0FlagArgs, 12)
@@ -444,7 +447,7 @@ HD void seq0emit_body(long long i, const Seq0EmitArgs &a) {
     if (!a.flag[i]) return;
     u32 t = a.idx0[i];
     u32 g = a.sa[i];
-    u32 k = LDG(a.v.seqof + g);
+    u32 k = seq_of(a.v, g);
     a.sa0[t] = g - LDG(a.v.seq_off + k);
     a.saidx0[t] = (u32)i;
     a.leaf_set[t] = LDG(a.v.seq_set + k);
@@ -684,7 +687,7 @@ HD void blockgather_body(long long b, const BlockGatherArgs &a) {
     u32 lb = a.blk_lb[ob];
     for (u32 j = lb; j < lb + m; j++) {
         u32 g = a.sa[j];
-        u32 k = LDG(a.v.seqof + g);
+        u32 k = seq_of(a.v, g);
         a.o_pos[po + (k - q0)] = (int)(g - LDG(a.v.seq_off + k));
     }
 }
@@ -957,7 +960,7 @@ HD unsigned letter_before(const BatchView &v, u32 g, u32 k) {
 }
 HD void clkey_body(long long i, const ClKeyArgs &a) {
     u32 g = a.sa[i];
-    u32 k = LDG(a.v.seqof + g);
+    u32 k = seq_of(a.v, g);
     u32 color = k - LDG(a.v.set_seq0 + LDG(a.v.seq_set + k));
     a.keys[i] = ((u64)letter_before(a.v, g, k) << a.mbits) | color;
     a.vals[i] = (u32)i;
@@ -970,7 +973,7 @@ HD void prevcl_body(long long j, const PrevClArgs &a) {
     u32 p = 0;
     if (j > 0 && a.keys[j - 1] == a.keys[j]) {
         u32 i0 = a.vals[j - 1];
-        if (LDG(a.v.seqof + a.sa[i0]) == LDG(a.v.seqof + a.sa[i])) p = i0 + 1;
+        if (seq_of(a.v, a.sa[i0]) == seq_of(a.v, a.sa[i])) p = i0 + 1;
     }
     a.prevcl[i] = p;
 }
@@ -984,7 +987,7 @@ HD void plateau_body(long long i, const PlateauArgs &a) {
     u32 l = (u32)i;
     u32 d1 = a.dv[l];
     if (d1 == 0) return;
-    u32 k0 = LDG(a.v.seqof + a.sa[l]);
+    u32 k0 = seq_of(a.v, a.sa[l]);
     u32 s = LDG(a.v.seq_set + k0);
     u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
     if (l != s0) {
@@ -1005,7 +1008,7 @@ HD void plateau_body(long long i, const PlateauArgs &a) {
     for (u32 j = l; j <= rb; j++) {
         if (a.prevcl[j] > l) continue; // an earlier suffix of this sequence in the node has the same letter
         u32 g = a.sa[j];
-        cnt[letter_before(a.v, g, LDG(a.v.seqof + g))]++;
+        cnt[letter_before(a.v, g, seq_of(a.v, g))]++;
     }
     bool sfx = false;
     for (int c = 0; c < 5; c++) if (cnt[c] == m) sfx = true;
@@ -1026,6 +1029,7 @@ MAP_KERNEL(plateau, PlateauArgs, 16)
 #define RF_NOMINAL 1024
 #define RF_CAP 2048
 #define RF_ITEMS (RF_CAP / RF_THREADS)
+#define RF_WARP_GROUP 512u // groups up to this size are ranked by one warp (min-reductions); longer ones by counting
 
 struct TileArgs { const u32 *head; u32 *tb; u32 *oversize; u32 N; u32 ntiles; };
 HD u32 tile_start(const TileArgs &a, u32 t) {
@@ -1088,13 +1092,13 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
     __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled, bit 2 (at a group's
                                                // first place): some member's second rank differs
     __shared__ u32 s_scan[33];
-    __shared__ u32 s_count, s_big;
+    __shared__ u32 s_count, s_big, s_mid;
     u32 *s_okey = (u32 *)s_ck;     // sorted keys; s_ck is dead (and fenced) by then
     const u32 base = a.tb[blockIdx.x];
     const u32 n = a.tb[blockIdx.x + 1] - base;
     if (n == 0 || n > RF_CAP) return;
     const u32 tid = threadIdx.x;
-    if (tid == 0) { s_count = 0; s_big = 0; }
+    if (tid == 0) { s_count = 0; s_big = 0; s_mid = 0; }
     // 1. borders.  A settled suffix is a singleton whose rank is already in BOTH rank buffers.
     //    (every phase that loads from HBM issues all RF_ITEMS loads of a thread before using any:
     //    the gathers below are chains of four dependent L2/HBM accesses and need the overlap)
@@ -1137,7 +1141,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
 #pragma unroll
         for (int x = 0; x < RF_ITEMS; x++) gv[x] = (need >> x & 1u) ? a.sa[base + tid + x * RF_THREADS] : 0u;
 #pragma unroll
-        for (int x = 0; x < RF_ITEMS; x++) kv[x] = (share >> x & 1u) ? LDG(a.v.seqof + gv[x]) : 0u;
+        for (int x = 0; x < RF_ITEMS; x++) kv[x] = (share >> x & 1u) ? seq_of(a.v, gv[x]) : 0u;
 #pragma unroll
         for (int x = 0; x < RF_ITEMS; x++) {
             ov[x] = (share >> x & 1u) ? LDG(a.v.seq_off + kv[x]) : 0u;
@@ -1185,14 +1189,16 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
     }
     u32 total;
     u32 before = block_scan_excl(run, total, ScanMax(), s_scan);
-    bool big = false;
+    bool big = false, mid = false;
 #pragma unroll
     for (int e = 0; e < RF_ITEMS; e++) {
         u32 j = j0 + e;
         seg[e] = seg[e] > before ? seg[e] : before;
-        if (j < n && j - seg[e] >= 32u) big = true;
+        if (j < n && j - seg[e] >= RF_WARP_GROUP) big = true;
+        if (j < n && j - seg[e] >= 32u) mid = true;
     }
     if (big) s_big = 1; // same value from every writer; read after the barriers of the scan below
+    if (mid) s_mid = 1;
     u32 ngroups_listed;
     u32 lbefore = block_scan_excl(nlist, ngroups_listed, ScanSum(), s_scan);
     if (!s_big) {
@@ -1209,29 +1215,70 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
         u32 made = 0;
         for (u32 gi = warp; gi < ngroups_listed; gi += RF_THREADS / 32) {
             const u32 S = s_gstart[gi];
-            const u32 j = S + lane;
-            const u32 w = (j < n) ? s_k2[j] : 0x80000000u;
-            const unsigned nextstart = __ballot_sync(0xffffffffu, lane > 0 && (w >> 31));
-            const u32 size = nextstart ? (u32)(__ffs((int)nextstart) - 1) : 32u;
-            const bool member = lane < size;
-            const u32 k2 = member ? (w & 0x7FFFFFFFu) : 0xFFFFFFFFu;
-            const u32 g = member ? s_sa[j] : 0u;
-            unsigned rem = __ballot_sync(0xffffffffu, member);
-            u32 placed = 0, mynew = 0, myhead = 0;
-            while (rem) {
-                const u32 kk = (rem >> lane & 1u) ? k2 : 0xFFFFFFFFu;
-                const u32 mn = __reduce_min_sync(0xffffffffu, kk);
-                const unsigned eq = __ballot_sync(0xffffffffu, kk == mn) & rem;
-                if (eq >> lane & 1u) { mynew = placed + __popc(eq & ltmask); myhead = placed; }
-                placed += __popc(eq);
-                rem &= ~eq;
-                made++;
+            // the group ends where the next one begins (a border flag; the end of the tile counts as one)
+            u32 size = 0;
+            if (!s_mid) { // no group of the tile is longer than a warp: the next border is within reach
+                const u32 j = S + lane;
+                const u32 w = (j < n) ? s_k2[j] : 0x80000000u;
+                const unsigned nextstart = __ballot_sync(0xffffffffu, lane > 0 && (w >> 31));
+                size = nextstart ? (u32)(__ffs((int)nextstart) - 1) : 32u;
+            } else for (u32 c0 = 0;; c0 += 32) {
+                const u32 j = S + c0 + lane;
+                const u32 w = (j < n) ? s_k2[j] : 0x80000000u;
+                const unsigned nextstart = __ballot_sync(0xffffffffu, (c0 + lane > 0) && (w >> 31));
+                if (nextstart) { size = c0 + (u32)(__ffs((int)nextstart) - 1); break; }
             }
-            if (member) {
-                const u32 p = base + S + mynew, h2 = base + S + myhead;
-                a.sa[p] = g;
-                a.head[p] = h2;
-                a.rank2[g] = h2;
+            if (size <= 32) { // one suffix per lane, everything in registers
+                const u32 j = S + lane;
+                const bool member = lane < size;
+                const u32 k2 = member ? (s_k2[j] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+                const u32 g = member ? s_sa[j] : 0u;
+                unsigned rem = __ballot_sync(0xffffffffu, member);
+                u32 placed = 0, mynew = 0, myhead = 0;
+                while (rem) {
+                    const u32 kk = (rem >> lane & 1u) ? k2 : 0xFFFFFFFFu;
+                    const u32 mn = __reduce_min_sync(0xffffffffu, kk);
+                    const unsigned eq = __ballot_sync(0xffffffffu, kk == mn) & rem;
+                    if (eq >> lane & 1u) { mynew = placed + __popc(eq & ltmask); myhead = placed; }
+                    placed += __popc(eq);
+                    rem &= ~eq;
+                    made++;
+                }
+                if (member) {
+                    const u32 p = base + S + mynew, h2 = base + S + myhead;
+                    a.sa[p] = g;
+                    a.head[p] = h2;
+                    a.rank2[g] = h2;
+                }
+            } else { // several suffixes per lane (striped), second ranks stay in shared memory;
+                     // a placed suffix is marked by an all-ones word (its border bit is never read again)
+                u32 placed = 0;
+                while (placed < size) {
+                    u32 mn = 0xFFFFFFFFu;
+                    for (u32 t = lane; t < size; t += 32) {
+                        u32 w = s_k2[S + t];
+                        if (w != 0xFFFFFFFFu) { w &= 0x7FFFFFFFu; mn = w < mn ? w : mn; }
+                    }
+                    mn = __reduce_min_sync(0xffffffffu, mn);
+                    u32 cnt = 0;
+                    for (u32 t0 = 0; t0 < size; t0 += 32) {
+                        const u32 t = t0 + lane;
+                        u32 w = (t < size) ? s_k2[S + t] : 0xFFFFFFFFu;
+                        const bool eq = w != 0xFFFFFFFFu && (w & 0x7FFFFFFFu) == mn;
+                        const unsigned b = __ballot_sync(0xffffffffu, eq);
+                        if (eq) {
+                            const u32 p = base + S + placed + cnt + __popc(b & ltmask), h2 = base + S + placed;
+                            const u32 g = s_sa[S + t];
+                            a.sa[p] = g;
+                            a.head[p] = h2;
+                            a.rank2[g] = h2;
+                            s_k2[S + t] = 0xFFFFFFFFu;
+                        }
+                        cnt += __popc(b);
+                    }
+                    placed += cnt;
+                    made++;
+                }
             }
         }
         u32 nsingle = 0;
