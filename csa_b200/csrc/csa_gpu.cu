@@ -46,7 +46,7 @@ struct csa_gpu_ctx {
     // ---- device ----
     DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, dbl_off, z0;
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, counter, tiles;
-    int rounds_tiled = 0, rounds_global = 0, force_global_rounds = 0;
+    int rounds_tiled = 0, rounds_global = 0, rounds_quad = 0, force_global_rounds = 0, no_quad_rounds = 0;
     DevMem pyr, sa0, saidx0, leaf_set, lcp0, psv, nsv, pse, parent, nsize, minpos, val, up, val2, up2;
     DevMem set_nblocks, set_blk0, set_pos0, set_flags, set_nchains, set_cyclic, firstmax, set_collected, set_suffixfree;
     bool have_stats = false;
@@ -325,27 +325,40 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
     u64 sorted_len = (u64)letters;
     u32 ngroups = 0;
     TRY(heads_and_ranks(c, head, rank, counter, &ngroups));
-    c->rounds_tiled = c->rounds_global = 0;
+    c->rounds_tiled = c->rounds_global = c->rounds_quad = 0;
+    // counter[0] groups, [1] a tile would overflow, [2] largest group
+    auto largest_group = [&](u32 *out) -> int {
+        TRY(dev_zero(ex, counter + 2, sizeof(u32)));
+        { MaxGroupArgs a{head, counter + 2, N}; launch_maxgroup(ex, N, a); }
+        return read_u32(c, counter + 2, out);
+    };
+    u32 maxg = 0;
+    if (ngroups != N) TRY(largest_group(&maxg));
     // gencycsuffixtrees.c compares rotations letter by letter; two periodic strings that agree on
     // n_a+n_b letters agree for ever, so 2*nmax sorted letters settle every comparison
     while (ngroups != N && sorted_len < 2ull * c->nmax) {
-        TRY(dev_zero(ex, counter, 2 * sizeof(u32)));
+        TRY(dev_zero(ex, counter, 3 * sizeof(u32)));
         { TileArgs a{head, P<u32>(c->tiles), counter + 1, N, ntiles}; launch_tile(ex, ntiles, a); }
         u32 oversize = 0;
-        TRY(read_u32(c, counter + 1, &oversize));
+        if (maxg > RF_NOMINAL) TRY(read_u32(c, counter + 1, &oversize)); // smaller groups always fit a tile
         if (!oversize && !c->force_global_rounds) {
-            RefineArgs a{v, P<u32>(c->valsA), head, rank, rank2, P<u32>(c->tiles), (u32)sorted_len, counter, ntiles};
-            launch_refine(ex, a);
+            RefineArgs a{v, P<u32>(c->valsA), head, rank, rank2, P<u32>(c->tiles), (u32)sorted_len, counter, ntiles, counter + 2};
+            // small groups: four times the letters per round (three rank gathers); else twice
+            const bool quad = maxg <= RF_QUAD_GROUP && !c->no_quad_rounds && 4 * sorted_len < (1ull << 31);
+            if (quad) launch_refine4(ex, a); else launch_refine(ex, a);
             std::swap(rank, rank2);
-            TRY(read_u32(c, counter, &ngroups));
-            c->rounds_tiled++;
+            u32 res[3];
+            TRY(d2h(ex, res, counter, sizeof(res)));
+            ngroups = res[0]; maxg = res[2];
+            if (quad) { c->rounds_quad++; sorted_len *= 4; } else { c->rounds_tiled++; sorted_len *= 2; }
         } else { // a group larger than a tile: device-wide radix sort of (rank, rank h letters on)
             { Key2Args a{v, P<u32>(c->valsA), rank, P<u64>(c->keysA), (u32)sorted_len, nbits}; launch_key2(ex, N, a); }
             TRY(sort_pairs(c, N, 0, 2 * nbits));
             TRY(heads_and_ranks(c, head, rank, counter, &ngroups));
+            if (ngroups != N) TRY(largest_group(&maxg));
             c->rounds_global++;
+            sorted_len *= 2;
         }
-        sorted_len *= 2;
     }
     TRY(d2d(ex, c->sa.p, c->valsA.p, sizeof(u32) * (size_t)N));
     return 0;
@@ -592,8 +605,9 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
 // rounds[0], rounds[1] = rounds of the last run that took the tile path / the device-wide path
 extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds[2]) {
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
-    if (force_global >= 0) c->force_global_rounds = force_global;
-    if (rounds) { rounds[0] = c->rounds_tiled; rounds[1] = c->rounds_global; }
+    // force_global: 0 free choice, 1 device-wide rounds only, 2 tile rounds but no quadrupling
+    if (force_global >= 0) { c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; }
+    if (rounds) { rounds[0] = c->rounds_tiled + c->rounds_quad; rounds[1] = c->rounds_global; }
     return CSA_GPU_OK;
 }
 

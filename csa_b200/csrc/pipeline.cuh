@@ -1029,6 +1029,7 @@ MAP_KERNEL(plateau, PlateauArgs, 16)
 #define RF_NOMINAL 1024
 #define RF_CAP 2048
 #define RF_ITEMS (RF_CAP / RF_THREADS)
+#define RF_QUAD_GROUP 128u // quadrupling rounds (k_refine4) pay off while the groups are this small
 #define RF_WARP_GROUP 512u // groups up to this size are ranked by one warp (min-reductions); longer ones by counting
 
 struct TileArgs { const u32 *head; u32 *tb; u32 *oversize; u32 N; u32 ntiles; };
@@ -1050,13 +1051,47 @@ HD void tile_body(long long t, const TileArgs &a) {
 }
 MAP_KERNEL(tile, TileArgs, 8)
 
+// largest group of equal h-prefixes: the last suffix of a group is as far from its head as the group is long
+struct MaxGroupArgs { const u32 *head; u32 *maxgroup; u32 N; };
+#ifdef CSA_EMU
+HD void maxgroup_body(long long i, const MaxGroupArgs &a) {
+    if ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1) {
+        u32 sz = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
+        if (sz > *a.maxgroup) *a.maxgroup = sz;
+    }
+}
+MAP_KERNEL(maxgroup, MaxGroupArgs, 4)
+#else
+__global__ void __launch_bounds__(256) k_maxgroup(long long n, MaxGroupArgs a) {
+    __shared__ u32 s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 sz = 0;
+    if (i < n && ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1)) sz = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
+    sz = __reduce_max_sync(0xffffffffu, sz);
+    if ((threadIdx.x & 31) == 0 && sz) atomicMax(&s_max, sz);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max) atomicMax(a.maxgroup, s_max);
+}
+static inline void launch_maxgroup(Exec &ex, long long n, MaxGroupArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_maxgroup", 4.0 * n);
+    k_maxgroup<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
+
 struct RefineArgs {
     BatchView v; u32 *sa; u32 *head; const u32 *rank; u32 *rank2; const u32 *tb; u32 h; u32 *ngroups; u32 ntiles;
+    u32 *maxgroup; // largest group after the round (atomic max)
 };
 
 #ifdef CSA_EMU
-static inline void launch_refine(Exec &, const RefineArgs &a) {
-    std::vector<std::pair<u32, u32>> seg; // (key2, suffix)
+static inline void emu_refine(const RefineArgs &a, int nkeys) {
+    struct Item { u32 k[3]; u32 g; };
+    std::vector<Item> seg;
     for (u32 t = 0; t < a.ntiles; t++) {
         u32 base = a.tb[t], end = a.tb[t + 1];
         u32 i = base;
@@ -1064,20 +1099,32 @@ static inline void launch_refine(Exec &, const RefineArgs &a) {
             u32 j = i + 1;
             while (j < end && (a.head[j] & 0x7FFFFFFFu) != j) j++;
             seg.clear();
-            for (u32 x = i; x < j; x++) seg.push_back({a.rank[cyc_add(a.v, a.sa[x], a.h)], a.sa[x]});
-            std::stable_sort(seg.begin(), seg.end(), [](const std::pair<u32, u32> &p, const std::pair<u32, u32> &q) { return p.first < q.first; });
+            for (u32 x = i; x < j; x++) {
+                Item it{{0, 0, 0}, a.sa[x]};
+                u32 g = a.sa[x];
+                for (int q = 0; q < nkeys; q++) { g = cyc_add(a.v, g, a.h); it.k[q] = a.rank[g]; }
+                seg.push_back(it);
+            }
+            auto less = [](const Item &p, const Item &q) {
+                for (int w = 0; w < 3; w++) if (p.k[w] != q.k[w]) return p.k[w] < q.k[w];
+                return false;
+            };
+            std::stable_sort(seg.begin(), seg.end(), less);
             u32 hd = i;
             for (u32 x = i; x < j; x++) {
-                if (x > i && seg[x - i].first != seg[x - i - 1].first) hd = x;
+                if (x > i && less(seg[x - i - 1], seg[x - i])) hd = x;
                 if (hd == x) (*a.ngroups)++;
-                a.sa[x] = seg[x - i].second;
+                if (x - hd + 1 > *a.maxgroup) *a.maxgroup = x - hd + 1;
+                a.sa[x] = seg[x - i].g;
                 a.head[x] = hd;
-                a.rank2[seg[x - i].second] = hd;
+                a.rank2[seg[x - i].g] = hd;
             }
             i = j;
         }
     }
 }
+static inline void launch_refine(Exec &, const RefineArgs &a) { emu_refine(a, 1); }
+static inline void launch_refine4(Exec &, const RefineArgs &a) { emu_refine(a, 3); }
 #else
 #define HEAD_SETTLED 0x80000000u
 __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
@@ -1092,13 +1139,13 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
     __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled, bit 2 (at a group's
                                                // first place): some member's second rank differs
     __shared__ u32 s_scan[33];
-    __shared__ u32 s_count, s_big, s_mid;
+    __shared__ u32 s_count, s_big, s_mid, s_maxg;
     u32 *s_okey = (u32 *)s_ck;     // sorted keys; s_ck is dead (and fenced) by then
     const u32 base = a.tb[blockIdx.x];
     const u32 n = a.tb[blockIdx.x + 1] - base;
     if (n == 0 || n > RF_CAP) return;
     const u32 tid = threadIdx.x;
-    if (tid == 0) { s_count = 0; s_big = 0; s_mid = 0; }
+    if (tid == 0) { s_count = 0; s_big = 0; s_mid = 0; s_maxg = 1; }
     // 1. borders.  A settled suffix is a singleton whose rank is already in BOTH rank buffers.
     //    (every phase that loads from HBM issues all RF_ITEMS loads of a thread before using any:
     //    the gathers below are chains of four dependent L2/HBM accesses and need the overlap)
@@ -1121,7 +1168,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
         }
     }
     if (__syncthreads_and(all_settled)) { // every suffix of the tile has its final place
-        if (tid == 0) atomicAdd(a.ngroups, n);
+        if (tid == 0) { atomicAdd(a.ngroups, n); atomicMax(a.maxgroup, 1u); }
         return;
     }
     // 2. stage the suffixes; only those that still share a group pay for the gathers
@@ -1212,7 +1259,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
             if (listmask >> e & 1u) s_gstart[lbefore++] = j0 + e;
         __syncthreads();
         const unsigned lane = tid & 31u, warp = tid >> 5, ltmask = (1u << lane) - 1u;
-        u32 made = 0;
+        u32 made = 0, widest = 0;
         for (u32 gi = warp; gi < ngroups_listed; gi += RF_THREADS / 32) {
             const u32 S = s_gstart[gi];
             // the group ends where the next one begins (a border flag; the end of the tile counts as one)
@@ -1240,7 +1287,9 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
                     const u32 mn = __reduce_min_sync(0xffffffffu, kk);
                     const unsigned eq = __ballot_sync(0xffffffffu, kk == mn) & rem;
                     if (eq >> lane & 1u) { mynew = placed + __popc(eq & ltmask); myhead = placed; }
-                    placed += __popc(eq);
+                    const u32 c = (u32)__popc(eq);
+                    placed += c;
+                    widest = c > widest ? c : widest;
                     rem &= ~eq;
                     made++;
                 }
@@ -1277,10 +1326,12 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
                         cnt += __popc(b);
                     }
                     placed += cnt;
+                    widest = cnt > widest ? cnt : widest;
                     made++;
                 }
             }
         }
+        if (lane == 0 && widest > 1) atomicMax(&s_maxg, widest);
         u32 nsingle = 0;
         for (u32 j = tid; j < n; j += RF_THREADS) {
             u32 fl = s_fl[j];
@@ -1295,7 +1346,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
         if (lane == 0) nsingle += made;
         if (nsingle) atomicAdd(&s_count, nsingle);
         __syncthreads();
-        if (tid == 0) atomicAdd(a.ngroups, s_count);
+        if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); }
         return;
     }
     // 3c. a group longer than a warp: composite keys and a counting rank over shared memory
@@ -1360,11 +1411,17 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
     u32 total2;
     u32 before2 = block_scan_excl(run2, total2, ScanMax(), s_scan);
     if (nflag) atomicAdd(&s_count, nflag);
+    u32 widest = 1;
 #pragma unroll
     for (int e = 0; e < RF_ITEMS; e++) {
         u32 j = j0 + e;
-        if (j < n) s_k2[j] = base + (hd[e] > before2 ? hd[e] : before2);
+        if (j < n) {
+            u32 hl = hd[e] > before2 ? hd[e] : before2;
+            s_k2[j] = base + hl;
+            widest = (j - hl + 1 > widest) ? j - hl + 1 : widest; // the last suffix of a group tells its size
+        }
     }
+    if (widest > 1) atomicMax(&s_maxg, widest);
     __syncthreads();
     // 7. write back, coalesced.  The new rank goes to the OTHER rank buffer (a round reads only the
     //    ranks of the round before); a suffix that stood alone at the start keeps its place and is
@@ -1384,7 +1441,213 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
             a.rank2[g] = h2;
         }
     }
-    if (tid == 0) atomicAdd(a.ngroups, s_count);
+    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); }
+}
+
+// ---- the same round, four times the letters: groups ordered by the ranks h, 2h and 3h letters on ----------
+// (prefix "quadrupling": half as many rounds, each with three rank gathers instead of one).  One warp
+// per group, lexicographic minimum of the rank triple by three chained min-reductions; any group
+// size works, the host picks this kernel when the groups are small enough to be quick (<= 512).
+__global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
+    __shared__ u32 s_sa[RF_CAP];
+    __shared__ u32 s_ka[RF_CAP]; // rank h on | 1<<31 on the first suffix of a group; all ones once placed
+    __shared__ u32 s_kb[RF_CAP], s_kc[RF_CAP];
+    __shared__ u32 s_gstart[RF_CAP / 2 + 1];
+    __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled
+    __shared__ u32 s_scan[33];
+    __shared__ u32 s_count, s_maxg;
+    const u32 base = a.tb[blockIdx.x];
+    const u32 n = a.tb[blockIdx.x + 1] - base;
+    if (n == 0 || n > RF_CAP) return;
+    const u32 tid = threadIdx.x;
+    if (tid == 0) { s_count = 0; s_maxg = 1; }
+    int all_settled = 1;
+    {
+        u32 hdv[RF_ITEMS];
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            u32 j = tid + x * RF_THREADS;
+            hdv[x] = (j < n) ? a.head[base + j] : 0u;
+        }
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            u32 j = tid + x * RF_THREADS;
+            if (j < n) {
+                u32 fl = ((hdv[x] & ~HEAD_SETTLED) == base + j ? 1u : 0u) | ((hdv[x] >> 31) << 1);
+                s_fl[j] = (unsigned char)fl;
+                all_settled &= (int)(fl >> 1);
+            }
+        }
+    }
+    if (__syncthreads_and(all_settled)) {
+        if (tid == 0) { atomicAdd(a.ngroups, n); atomicMax(a.maxgroup, 1u); }
+        return;
+    }
+    {
+        u32 gv[RF_ITEMS], kv[RF_ITEMS], ov[RF_ITEMS], nv[RF_ITEMS];
+        unsigned need = 0, share = 0;
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            u32 j = tid + x * RF_THREADS;
+            if (j < n) {
+                u32 fl = s_fl[j];
+                bool single = (fl & 1u) && (j + 1 == n || (s_fl[j + 1] & 1u));
+                if (!(single && (fl & 2u))) need |= 1u << x;
+                if (!single) share |= 1u << x;
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) gv[x] = (need >> x & 1u) ? a.sa[base + tid + x * RF_THREADS] : 0u;
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) kv[x] = (share >> x & 1u) ? seq_of(a.v, gv[x]) : 0u;
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            ov[x] = (share >> x & 1u) ? LDG(a.v.seq_off + kv[x]) : 0u;
+            nv[x] = (share >> x & 1u) ? LDG(a.v.seq_off + kv[x] + 1) : 1u;
+        }
+#pragma unroll
+        for (int x = 0; x < RF_ITEMS; x++) {
+            u32 j = tid + x * RF_THREADS;
+            u32 ka = 0, kb = 0, kc = 0;
+            if (share >> x & 1u) {
+                u32 len = nv[x] - ov[x], hh = a.h;
+                if (hh >= len) hh %= len;
+                u32 q1 = gv[x] - ov[x] + hh; if (q1 >= len) q1 -= len;
+                u32 q2 = q1 + hh; if (q2 >= len) q2 -= len;
+                u32 q3 = q2 + hh; if (q3 >= len) q3 -= len;
+                ka = LDG(a.rank + ov[x] + q1);
+                kb = LDG(a.rank + ov[x] + q2);
+                kc = LDG(a.rank + ov[x] + q3);
+            }
+            if (j < n) {
+                if (need >> x & 1u) s_sa[j] = gv[x];
+                s_ka[j] = ka | ((u32)(s_fl[j] & 1u) << 31);
+                s_kb[j] = kb;
+                s_kc[j] = kc;
+            }
+        }
+    }
+    __syncthreads();
+    // the groups that still hold more than one suffix
+    const u32 j0 = tid * RF_ITEMS;
+    u32 nlist = 0, listmask = 0;
+#pragma unroll
+    for (int e = 0; e < RF_ITEMS; e++) {
+        u32 j = j0 + e;
+        if (j < n && (s_ka[j] >> 31) && !(j + 1 == n || (s_ka[j + 1] >> 31))) { nlist++; listmask |= 1u << e; }
+    }
+    u32 ngroups_listed;
+    u32 lbefore = block_scan_excl(nlist, ngroups_listed, ScanSum(), s_scan);
+#pragma unroll
+    for (int e = 0; e < RF_ITEMS; e++)
+        if (listmask >> e & 1u) s_gstart[lbefore++] = j0 + e;
+    __syncthreads();
+    const unsigned lane = tid & 31u, warp = tid >> 5, ltmask = (1u << lane) - 1u;
+    u32 made = 0, widest = 0;
+    for (u32 gi = warp; gi < ngroups_listed; gi += RF_THREADS / 32) {
+        const u32 S = s_gstart[gi];
+        u32 size = 0;
+        for (u32 c0 = 0;; c0 += 32) {
+            const u32 j = S + c0 + lane;
+            const u32 w = (j < n) ? s_ka[j] : 0x80000000u;
+            const unsigned nextstart = __ballot_sync(0xffffffffu, (c0 + lane > 0) && (w >> 31));
+            if (nextstart) { size = c0 + (u32)(__ffs((int)nextstart) - 1); break; }
+        }
+        if (size <= 32) {
+            const u32 j = S + lane;
+            const bool member = lane < size;
+            const u32 ka = member ? (s_ka[j] & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+            const u32 kb = member ? s_kb[j] : 0xFFFFFFFFu, kc = member ? s_kc[j] : 0xFFFFFFFFu;
+            const u32 g = member ? s_sa[j] : 0u;
+            unsigned rem = __ballot_sync(0xffffffffu, member);
+            u32 placed = 0, mynew = 0, myhead = 0;
+            while (rem) {
+                const u32 xa = (rem >> lane & 1u) ? ka : 0xFFFFFFFFu;
+                const u32 ma = __reduce_min_sync(0xffffffffu, xa);
+                const unsigned m1 = __ballot_sync(0xffffffffu, xa == ma) & rem;
+                const u32 xb = (m1 >> lane & 1u) ? kb : 0xFFFFFFFFu;
+                const u32 mb = __reduce_min_sync(0xffffffffu, xb);
+                const unsigned m2 = __ballot_sync(0xffffffffu, xb == mb) & m1;
+                const u32 xc = (m2 >> lane & 1u) ? kc : 0xFFFFFFFFu;
+                const u32 mc = __reduce_min_sync(0xffffffffu, xc);
+                const unsigned eq = __ballot_sync(0xffffffffu, xc == mc) & m2;
+                if (eq >> lane & 1u) { mynew = placed + __popc(eq & ltmask); myhead = placed; }
+                const u32 c = (u32)__popc(eq);
+                placed += c;
+                widest = c > widest ? c : widest;
+                rem &= ~eq;
+                made++;
+            }
+            if (member) {
+                const u32 p = base + S + mynew, h2 = base + S + myhead;
+                a.sa[p] = g;
+                a.head[p] = h2;
+                a.rank2[g] = h2;
+            }
+        } else {
+            u32 placed = 0;
+            while (placed < size) {
+                u32 ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu, mc = 0xFFFFFFFFu;
+                for (u32 t = lane; t < size; t += 32) {
+                    u32 w = s_ka[S + t];
+                    if (w != 0xFFFFFFFFu) { w &= 0x7FFFFFFFu; ma = w < ma ? w : ma; }
+                }
+                ma = __reduce_min_sync(0xffffffffu, ma);
+                for (u32 t = lane; t < size; t += 32) {
+                    u32 w = s_ka[S + t];
+                    if (w != 0xFFFFFFFFu && (w & 0x7FFFFFFFu) == ma) { u32 y = s_kb[S + t]; mb = y < mb ? y : mb; }
+                }
+                mb = __reduce_min_sync(0xffffffffu, mb);
+                for (u32 t = lane; t < size; t += 32) {
+                    u32 w = s_ka[S + t];
+                    if (w != 0xFFFFFFFFu && (w & 0x7FFFFFFFu) == ma && s_kb[S + t] == mb) { u32 y = s_kc[S + t]; mc = y < mc ? y : mc; }
+                }
+                mc = __reduce_min_sync(0xffffffffu, mc);
+                u32 cnt = 0;
+                for (u32 t0 = 0; t0 < size; t0 += 32) {
+                    const u32 t = t0 + lane;
+                    const u32 w = (t < size) ? s_ka[S + t] : 0xFFFFFFFFu;
+                    const bool eq = w != 0xFFFFFFFFu && (w & 0x7FFFFFFFu) == ma && s_kb[S + t] == mb && s_kc[S + t] == mc;
+                    const unsigned b = __ballot_sync(0xffffffffu, eq);
+                    if (eq) {
+                        const u32 p = base + S + placed + cnt + __popc(b & ltmask), h2 = base + S + placed;
+                        const u32 g = s_sa[S + t];
+                        a.sa[p] = g;
+                        a.head[p] = h2;
+                        a.rank2[g] = h2;
+                        s_ka[S + t] = 0xFFFFFFFFu;
+                    }
+                    cnt += __popc(b);
+                }
+                placed += cnt;
+                widest = cnt > widest ? cnt : widest;
+                made++;
+            }
+        }
+    }
+    if (lane == 0 && widest > 1) atomicMax(&s_maxg, widest);
+    u32 nsingle = 0;
+    for (u32 j = tid; j < n; j += RF_THREADS) {
+        u32 fl = s_fl[j];
+        if ((fl & 1u) && (j + 1 == n || (s_fl[j + 1] & 1u))) {
+            nsingle++;
+            if (!(fl & 2u)) {
+                a.rank2[s_sa[j]] = base + j;
+                a.head[base + j] = (base + j) | HEAD_SETTLED;
+            }
+        }
+    }
+    if (lane == 0) nsingle += made;
+    if (nsingle) atomicAdd(&s_count, nsingle);
+    __syncthreads();
+    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); }
+}
+static inline void launch_refine4(Exec &ex, const RefineArgs &a) {
+    if (a.ntiles == 0) return;
+    PROF_BEGIN(ex, "k_refine4", 36.0 * a.v.N);
+    k_refine4<<<a.ntiles, RF_THREADS, 0, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
 }
 static inline void launch_refine(Exec &ex, const RefineArgs &a) {
     if (a.ntiles == 0) return;

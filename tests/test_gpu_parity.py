@@ -118,23 +118,29 @@ def test_gpu_errors(gpu_finder):
 
 
 def test_gpu_tile_rounds_equal_device_wide_rounds(gpu_finder):
-    """the one-pass tile round (k_refine) and the device-wide radix round give the same suffix array"""
-    batch = workload_batch("sets32", 3, seed=3)
+    """the one-pass tile rounds (k_refine4: h -> 4h, k_refine: h -> 2h) and the device-wide radix round
+    give the same suffix array"""
+    out = {}
     try:
-        gpu_finder.debug_rounds(0)
-        res_t = gpu_finder.find_rotations_batch(batch)
-        sa_t, lcp_t = gpu_finder.suffix_array()
-        tiled, _ = gpu_finder.debug_rounds()
-        gpu_finder.debug_rounds(1)
-        res_g = gpu_finder.find_rotations_batch(batch)
-        sa_g, lcp_g = gpu_finder.suffix_array()
-        t2, glob = gpu_finder.debug_rounds()
+        for name, batch in (("sets32", workload_batch("sets32", 3, seed=3)), ("mammals", workload_batch("mammals", 4, seed=4)),
+                            ("variants256", workload_batch("variants256", 1, seed=5))):
+            for mode in (0, 2, 1):  # free choice (quadrupling where groups are small), doubling tiles only, device-wide only
+                gpu_finder.debug_rounds(mode)
+                res = gpu_finder.find_rotations_batch(batch)
+                sa, lcp = gpu_finder.suffix_array()
+                out[(name, mode)] = (res, sa, lcp, gpu_finder.debug_rounds())
     finally:
         gpu_finder.debug_rounds(0)
-    assert tiled > 0 and t2 == 0 and glob > 0
-    assert np.array_equal(sa_t, sa_g) and np.array_equal(lcp_t, lcp_g)
-    for a, b in zip(res_t, res_g):
-        assert np.array_equal(a.rotations, b.rotations) and np.array_equal(a.positions, b.positions)
+    for name in ("sets32", "mammals", "variants256"):
+        r0, sa0, lcp0, rounds0 = out[(name, 0)]
+        assert rounds0[0] > 0
+        assert out[(name, 1)][3][0] == 0 and out[(name, 1)][3][1] > 0
+        assert out[(name, 2)][3][0] >= rounds0[0]  # doubling needs at least as many rounds as quadrupling
+        for mode in (1, 2):
+            r, sa, lcp, _ = out[(name, mode)]
+            assert np.array_equal(sa0, sa) and np.array_equal(lcp0, lcp), (name, mode)
+            for a, b in zip(r0, r):
+                assert np.array_equal(a.rotations, b.rotations) and np.array_equal(a.positions, b.positions)
 
 
 def test_gpu_large_groups_fall_back(gpu_finder):
