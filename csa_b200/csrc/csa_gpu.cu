@@ -46,6 +46,8 @@ struct csa_gpu_ctx {
     // ---- device ----
     DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, dbl_off, z0;
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, counter, tiles;
+    double lcp_mean_sample = 0;
+    int force_kasai = 0;
     int rounds_tiled = 0, rounds_global = 0, rounds_quad = 0, force_global_rounds = 0, no_quad_rounds = 0;
     DevMem pyr, sa0, saidx0, leaf_set, lcp0, psv, nsv, pse, parent, nsize, minpos, val, up, val2, up2;
     DevMem set_nblocks, set_blk0, set_pos0, set_flags, set_nchains, set_cyclic, firstmax, set_collected, set_suffixfree;
@@ -558,8 +560,22 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
     { PackArgs a{v}; launch_pack(ex, (long long)c->TW, a); }
     TRY(stage_suffix_array(c, v));
     mark(c, 1);
-    { IsaArgs a{P<u32>(c->sa), P<u32>(c->t1)}; launch_isa(ex, N, a); }
-    { LcpArgs a{v, P<u32>(c->sa), P<u32>(c->t1), P<u32>(c->t2), any_other}; launch_lcp(ex, ((long long)N + LCP_CHUNK - 1) / LCP_CHUNK, a); }
+    {   // how long are the matches?  a sample of pairs decides between the two LCP kernels
+        const u32 nsample = 4096, stride = N / nsample + 1;
+        unsigned long long *sum = (unsigned long long *)(P<u32>(c->counter) + 10), hsum = 0;
+        TRY(dev_zero(ex, sum, sizeof(*sum)));
+        { LcpDirectArgs a{v, P<u32>(c->sa), nullptr, any_other, stride, sum}; launch_lcpdirect(ex, (N + stride - 1) / stride, a); }
+        TRY(d2h(ex, &hsum, sum, sizeof(hsum)));
+        const double mean = (double)hsum / (double)((N + stride - 1) / stride);
+        c->lcp_mean_sample = mean;
+        if (mean < 96.0 && !c->force_kasai) {
+            LcpDirectArgs a{v, P<u32>(c->sa), P<u32>(c->t2), any_other, 1, nullptr};
+            launch_lcpdirect(ex, N, a);
+        } else {
+            { IsaArgs a{P<u32>(c->sa), P<u32>(c->t1)}; launch_isa(ex, N, a); }
+            { LcpArgs a{v, P<u32>(c->sa), P<u32>(c->t1), P<u32>(c->t2), any_other}; launch_lcp(ex, ((long long)N + LCP_CHUNK - 1) / LCP_CHUNK, a); }
+        }
+    }
     mark(c, 2);
     TRY(dev_zero(ex, c->set_flags.p, sizeof(u32) * nsets));
     TRY(stage_common_blocks(c, v));
@@ -606,7 +622,7 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
 extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds[2]) {
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
     // force_global: 0 free choice, 1 device-wide rounds only, 2 tile rounds but no quadrupling
-    if (force_global >= 0) { c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; }
+    if (force_global >= 0) { c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; c->force_kasai = force_global == 2; }
     if (rounds) { rounds[0] = c->rounds_tiled + c->rounds_quad; rounds[1] = c->rounds_global; }
     return CSA_GPU_OK;
 }

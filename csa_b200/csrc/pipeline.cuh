@@ -254,6 +254,43 @@ HD void lcp_body(long long t, const LcpArgs &a) {
 }
 MAP_KERNEL(lcp, LcpArgs, 20 * LCP_CHUNK)
 
+// SA order: every pair compared from letter 0 -- coalesced reads and writes, no inverse array; the
+// better choice when matches are short (a word compare or two per pair).  The host samples the
+// LCP of a few thousand pairs with this same kernel (stride > 1, sum only) and picks.
+struct LcpDirectArgs { BatchView v; const u32 *sa; u32 *lcp; const u32 *any_other; u32 stride; unsigned long long *sum; };
+HD void lcpdirect_body(long long t, const LcpDirectArgs &a) {
+    const u64 i64 = (u64)t * a.stride;
+    if (i64 >= a.v.N) return;
+    const u32 i = (u32)i64;
+    u32 h = 0;
+    if (i > 0) {
+        u32 ga = a.sa[i - 1], gb = a.sa[i];
+        u32 ka = seq_of(a.v, ga), kb = seq_of(a.v, gb);
+        if (LDG(a.v.seq_set + ka) == LDG(a.v.seq_set + kb)) {
+            const bool masks = *a.any_other != 0;
+            u32 oa = LDG(a.v.seq_off + ka), ob = LDG(a.v.seq_off + kb);
+            u32 na = LDG(a.v.seq_off + ka + 1) - oa, nb = LDG(a.v.seq_off + kb + 1) - ob;
+            u32 cap = na < nb ? na : nb;
+            u64 xa = LDG(a.v.dbl_off + ka) + (ga - oa), xb = LDG(a.v.dbl_off + kb) + (gb - ob);
+            while (h < cap) {
+                u64 d2 = fetch2(a.v.p2, xa + h) ^ fetch2(a.v.p2, xb + h);
+                int f = 32;
+                if (d2) f = ctz64(d2) >> 1;
+                if (masks) {
+                    u32 dm = fetchm(a.v.pm, xa + h) ^ fetchm(a.v.pm, xb + h);
+                    if (dm) { int f2 = ctz32(dm); if (f2 < f) f = f2; }
+                }
+                if (f < 32) { h += (u32)f; break; }
+                h += 32;
+            }
+            if (h > cap) h = cap;
+        }
+    }
+    if (a.sum) { if (h > 4096) h = 4096; ATOMIC_ADD(a.sum, (unsigned long long)h); }
+    else a.lcp[i] = h;
+}
+MAP_KERNEL(lcpdirect, LcpDirectArgs, 12)
+
 // ---- stage 3: common blocks ------------------------------------------------------------------------
 // R[l] = smallest r such that SA[l..r] holds a suffix of every sequence of the set (>= end of the
 // set when there is none).  An LCP interval [lb,rb] "belongs to all the sequences"
