@@ -133,6 +133,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
     for (DevMem *m : all) dev_free(*m);
     for (int i = 0; i < 4; i++) dev_free(c->ps.block_sums[i]);
     dev_free(c->ps.counts);
+    dev_free(c->ps.chain);
 #ifndef CSA_EMU
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->tm.ok) for (int i = 0; i < 8; i++) cudaEventDestroy(c->tm.ev[i]);

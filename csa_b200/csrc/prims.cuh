@@ -14,6 +14,7 @@ struct ScanMax { HDM u32 id() { return 0u; } HDM u32 op(u32 a, u32 b) { return a
 struct PrimScratch {
     DevMem block_sums[4]; // scan recursion levels
     DevMem counts;        // radix digit counters [256][nblocks]
+    DevMem chain;         // single-pass scan: tile counter + one status word per tile
 };
 
 #ifdef CSA_EMU
@@ -117,10 +118,97 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const u32 *in, u32 
     }
 }
 
+// ---- single-pass scan (decoupled look-back) for long arrays: 4 B read + 4 B written per element ----
+// Tiles take their number from an atomic counter, so a tile only ever waits for tiles that have
+// already started.  A tile publishes (status, value) as ONE 64-bit word: status 1 = its own
+// aggregate, 2 = the inclusive prefix up to and including it; warp 0 of a later tile walks back over
+// those words, 32 at a time, until it meets an inclusive prefix.
+#define CS_THREADS 256
+#define CS_ITEMS 16
+#define CS_TILE (CS_THREADS * CS_ITEMS)
+template <class Op, bool INCLUSIVE>
+__global__ void __launch_bounds__(CS_THREADS) k_scan_chain(const u32 *in, u32 *out, long long n, unsigned long long *state) {
+    __shared__ u32 sm[33];
+    __shared__ u32 s_tile, s_prefix;
+    Op o;
+    if (threadIdx.x == 0) s_tile = (u32)atomicAdd(state, 1ull); // state[0]: next tile number; state[1+t]: tile t
+    __syncthreads();
+    const u32 tile = s_tile;
+    volatile unsigned long long *st = state + 1;
+    const long long base = (long long)tile * CS_TILE + (long long)threadIdx.x * CS_ITEMS;
+    u32 v[CS_ITEMS];
+    if (base + CS_ITEMS <= n && ((reinterpret_cast<size_t>(in) & 15) == 0)) {
+        const uint4 *p4 = reinterpret_cast<const uint4 *>(in + base);
+#pragma unroll
+        for (int q = 0; q < CS_ITEMS / 4; q++) { uint4 t = p4[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CS_ITEMS; j++) v[j] = (base + j < n) ? in[base + j] : o.id();
+    }
+    u32 agg = o.id();
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; j++) agg = o.op(agg, v[j]);
+    u32 total;
+    u32 excl = block_scan_excl(agg, total, o, sm);
+    if (threadIdx.x == 0) {
+        st[tile] = ((unsigned long long)(tile == 0 ? 2u : 1u) << 32) | total;
+        if (tile == 0) s_prefix = o.id();
+    }
+    if (tile > 0 && threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        u32 run = o.id();
+        long long look = (long long)tile - 1; // the nearest tile not yet accounted for
+        for (;;) {
+            const long long t = look - lane;
+            unsigned long long w = (t >= 0) ? st[t] : (2ull << 32); // before tile 0: an empty inclusive prefix
+            while (__any_sync(0xffffffffu, (w >> 32) == 0)) w = (t >= 0) ? st[t] : (2ull << 32); // not published yet
+            const unsigned incl = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+            const int stop = incl ? (__ffs((int)incl) - 1) : 32; // nearest inclusive prefix among these 32
+            u32 part = ((int)lane <= stop && lane < 32) ? (u32)w : o.id();
+            if ((int)lane > stop) part = o.id();
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) part = o.op(part, __shfl_xor_sync(0xffffffffu, part, d));
+            run = o.op(part, run);
+            if (incl) break;
+            look -= 32;
+        }
+        if (lane == 0) {
+            s_prefix = run;
+            st[tile] = (2ull << 32) | o.op(run, total);
+        }
+    }
+    __syncthreads();
+    u32 r = o.op(s_prefix, excl);
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; j++) {
+        if (INCLUSIVE) { r = o.op(r, v[j]); v[j] = r; }
+        else { u32 t = v[j]; v[j] = r; r = o.op(r, t); }
+    }
+    if (base + CS_ITEMS <= n && ((reinterpret_cast<size_t>(out) & 15) == 0)) {
+        uint4 *p4 = reinterpret_cast<uint4 *>(out + base);
+#pragma unroll
+        for (int q = 0; q < CS_ITEMS / 4; q++) p4[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < CS_ITEMS; j++) if (base + j < n) out[base + j] = v[j];
+    }
+}
+
 // out may alias in
 template <class Op, bool INCLUSIVE>
 static int scan_u32(Exec &ex, PrimScratch &ps, const u32 *in, u32 *out, long long n, int level = 0) {
     if (n <= 0) return 0;
+    if (n >= (1ll << 20)) { // long arrays: one pass
+        long long nt = (n + CS_TILE - 1) / CS_TILE;
+        int rc = dev_alloc(ps.chain, sizeof(unsigned long long) * (size_t)(nt + 1));
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(ps.chain.p, 0, sizeof(unsigned long long) * (size_t)(nt + 1), ex.stream));
+        PROF_BEGIN(ex, "k_scan_chain", 8.0 * n);
+        k_scan_chain<Op, INCLUSIVE><<<(unsigned)nt, CS_THREADS, 0, ex.stream>>>(in, out, n, (unsigned long long *)ps.chain.p);
+        PROF_END(ex);
+        ex.launches++;
+        return 0;
+    }
     long long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (nb == 1) {
         PROF_BEGIN(ex, "k_scan_apply", 8.0 * n);
