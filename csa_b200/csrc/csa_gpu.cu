@@ -4,6 +4,7 @@
 // the kernel bodies used by the CPU-only tests; it is never part of the product.)
 #include "pipeline.cuh"
 #include "../../include/csa_gpu.h"
+#include <algorithm>
 #include <vector>
 #include <string>
 #include <new>
@@ -45,6 +46,8 @@ struct csa_gpu_ctx {
     long long launches = 0;
     // ---- device ----
     DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, dbl_off, z0;
+    DevMem rs_start, rs_count, rs_cbase, rs_stride;
+    u32 rs_nblocks = 0;
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, counter, tiles;
     double lcp_mean_sample = 0;
     int force_kasai = 0;
@@ -124,7 +127,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
                      &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
-                     &c->t2, &c->t3, &c->t4, &c->counter, &c->tiles, &c->pyr, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
+                     &c->t2, &c->t3, &c->t4, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
                      &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
@@ -236,6 +239,28 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     TRY(h2d(ex, c->set_nmin.p, c->h_set_nmin.data(), sizeof(u32) * nsets));
     TRY(h2d(ex, c->dbl_off.p, c->h_dbl_off.data(), sizeof(u64) * (M + 1)));
     TRY(h2d(ex, c->z0.p, c->h_z0.data(), sizeof(u32) * (nsets + 1)));
+    {   // tile-blocks of the first (segmented) sort: none straddles a set
+        std::vector<u32> bs, bc, bb, bt;
+        u32 cbase = 0;
+        for (int s = 0; s < nsets; s++) {
+            u32 s0 = c->h_set_base0[s], s1 = c->h_set_base0[s + 1];
+            u32 nb = (s1 - s0 + RS_TILE_ELEMS - 1) / RS_TILE_ELEMS;
+            for (u32 j = 0; j < nb; j++) {
+                bs.push_back(s0 + j * RS_TILE_ELEMS);
+                bc.push_back(std::min<u32>(RS_TILE_ELEMS, s1 - (s0 + j * RS_TILE_ELEMS)));
+                bb.push_back(cbase + j);
+                bt.push_back(nb);
+            }
+            cbase += 256 * nb;
+        }
+        c->rs_nblocks = (u32)bs.size();
+        size_t bytes = sizeof(u32) * bs.size();
+        TRY(dev_alloc(c->rs_start, bytes)); TRY(dev_alloc(c->rs_count, bytes));
+        TRY(dev_alloc(c->rs_cbase, bytes)); TRY(dev_alloc(c->rs_stride, bytes));
+        TRY(h2d(ex, c->rs_start.p, bs.data(), bytes)); TRY(h2d(ex, c->rs_count.p, bc.data(), bytes));
+        TRY(h2d(ex, c->rs_cbase.p, bb.data(), bytes)); TRY(h2d(ex, c->rs_stride.p, bt.data(), bytes));
+        TRY(exec_sync(ex));
+    }
     TRY(exec_sync(ex)); // the host vectors and the staging buffer may change after we return
     c->uploaded = true;
     return CSA_GPU_OK;
@@ -297,17 +322,19 @@ static int read_u32(csa_gpu_ctx *c, const void *dev, u32 *out) { return d2h(c->e
 static int sort_pairs(csa_gpu_ctx *c, long long n, int begin_bit, int end_bit) {
     u64 *k = P<u64>(c->keysA), *ka = P<u64>(c->keysB);
     u32 *v = P<u32>(c->valsA), *va = P<u32>(c->valsB);
-    TRY(radix_sort_pairs(c->ex, c->ps, k, v, ka, va, n, begin_bit, end_bit));
+    TRY(radix_sort_pairs<u64>(c->ex, c->ps, k, v, ka, va, n, begin_bit, end_bit));
     if (k != P<u64>(c->keysA)) { std::swap(c->keysA, c->keysB); std::swap(c->valsA, c->valsB); }
     return 0;
 }
 
 // head[]/rank[] from the sorted keys in keysA (device-wide path)
-static int heads_and_ranks(csa_gpu_ctx *c, u32 *head, u32 *rank, u32 *counter, u32 *ngroups) {
+static int heads_and_ranks(csa_gpu_ctx *c, u32 *head, u32 *rank, u32 *counter, u32 *ngroups, bool keys32 = false,
+                           bool fix_set_starts = false) {
     Exec &ex = c->ex;
     u32 N = c->N;
     TRY(dev_zero(ex, counter, sizeof(u32)));
-    { FlagArgs a{P<u64>(c->keysA), head, counter}; launch_flag(ex, N, a); }
+    { FlagArgs a{P<u64>(c->keysA), keys32 ? P<u32>(c->keysA) : nullptr, head, counter}; launch_flag(ex, N, a); }
+    if (fix_set_starts) { SetStartArgs a{view_of(c), head, counter}; launch_setstart(ex, c->nsets, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, head, head, N)));
     { SetRankArgs a{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, a); }
     return read_u32(c, counter, ngroups);
@@ -322,12 +349,25 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
     u32 any_other = 1;
     TRY(read_u32(c, counter + 8, &any_other)); // set by k_encode: a letter outside ACGT somewhere in the batch
     const int letters = any_other ? CSA_K0 : 12, lbits = any_other ? CSA_LETTER_BITS : 2;
-    { InitKeyArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA), letters, lbits}; launch_initkey(ex, N, a); }
-    TRY(sort_pairs(c, N, 0, letters * lbits + bits_for((u64)c->nsets - 1)));
+    RsSeg seg{P<u32>(c->rs_start), P<u32>(c->rs_count), P<u32>(c->rs_cbase), P<u32>(c->rs_stride), c->rs_nblocks,
+              P<u32>(c->set_base0), (u32)c->nsets};
+    { InitKeyArgs a{v, any_other ? P<u64>(c->keysA) : nullptr, any_other ? nullptr : P<u32>(c->keysA), P<u32>(c->valsA)};
+      launch_initkey(ex, N, a); }
+    if (any_other) {
+        u64 *k = P<u64>(c->keysA), *ka = P<u64>(c->keysB);
+        u32 *vv = P<u32>(c->valsA), *va = P<u32>(c->valsB);
+        TRY(radix_sort_pairs<u64>(ex, c->ps, k, vv, ka, va, N, 0, letters * lbits, &seg));
+        if (vv != P<u32>(c->valsA)) { std::swap(c->keysA, c->keysB); std::swap(c->valsA, c->valsB); }
+    } else {
+        u32 *k = P<u32>(c->keysA), *ka = P<u32>(c->keysB);
+        u32 *vv = P<u32>(c->valsA), *va = P<u32>(c->valsB);
+        TRY(radix_sort_pairs<u32>(ex, c->ps, k, vv, ka, va, N, 0, letters * lbits, &seg));
+        if (vv != P<u32>(c->valsA)) { std::swap(c->keysA, c->keysB); std::swap(c->valsA, c->valsB); }
+    }
     int nbits = bits_for((u64)N - 1);
     u64 sorted_len = (u64)letters;
     u32 ngroups = 0;
-    TRY(heads_and_ranks(c, head, rank, counter, &ngroups));
+    TRY(heads_and_ranks(c, head, rank, counter, &ngroups, !any_other, true));
     c->rounds_tiled = c->rounds_global = c->rounds_quad = 0;
     // counter[0] groups, [1] a tile would overflow, [2] largest group
     auto largest_group = [&](u32 *out) -> int {

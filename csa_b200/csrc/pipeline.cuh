@@ -108,29 +108,42 @@ HD void pack_body(long long w, const PackArgs &a) {
 MAP_KERNEL(pack, PackArgs, 44)
 
 // ---- stage 1: suffix array by prefix doubling --------------------------------------------------
-// letters/bits: 13 letters of 3 bits, or -- when the batch holds nothing but A,C,G,T -- 12 letters of
-// 2 bits, which with 8 bits of set number is a 32-bit key: four radix passes instead of six
-struct InitKeyArgs { BatchView v; u64 *keys; u32 *vals; int letters; int bits; };
+// The first sort key: the first letters of the rotation -- 13 letters of 3 bits in a u64, or, when the
+// batch holds nothing but A,C,G,T, 12 letters of 2 bits in a u32 (three radix passes of 8 B per element
+// instead of five of 12 B).  The set number is not in the key: the first sort is segmented by set.
+struct InitKeyArgs { BatchView v; u64 *keys64; u32 *keys32; u32 *vals; };
 HD void initkey_body(long long i, const InitKeyArgs &a) {
     u32 g = (u32)i;
     u32 k = seq_of(a.v, g);
     u32 off = LDG(a.v.seq_off + k), n = LDG(a.v.seq_off + k + 1) - off;
     u32 p = g - off;
-    u64 key = LDG(a.v.seq_set + k);
-    for (int t = 0; t < a.letters; t++) {
-        key = (key << a.bits) | a.v.code[off + p];
-        if (++p == n) p = 0;
+    if (a.keys32) {
+        u32 key = 0;
+        for (int t = 0; t < 12; t++) {
+            key = (key << 2) | a.v.code[off + p];
+            if (++p == n) p = 0;
+        }
+        a.keys32[g] = key;
+    } else {
+        u64 key = 0;
+        for (int t = 0; t < CSA_K0; t++) {
+            key = (key << CSA_LETTER_BITS) | a.v.code[off + p];
+            if (++p == n) p = 0;
+        }
+        a.keys64[g] = key;
     }
-    a.keys[g] = key;
     a.vals[g] = g;
 }
-MAP_KERNEL(initkey, InitKeyArgs, 29)
+MAP_KERNEL(initkey, InitKeyArgs, 21)
 
 // head[i] = i where a new group of equal keys starts, else 0 (max-scanned afterwards)
-struct FlagArgs { const u64 *keys; u32 *head; u32 *ngroups; };
+struct FlagArgs { const u64 *keys; const u32 *keys32; u32 *head; u32 *ngroups; };
+HD bool flag_differs(const FlagArgs &a, long long i) {
+    return a.keys32 ? a.keys32[i] != a.keys32[i - 1] : a.keys[i] != a.keys[i - 1];
+}
 #ifdef CSA_EMU
 HD void flag_body(long long i, const FlagArgs &a) {
-    bool f = (i == 0) || a.keys[i] != a.keys[i - 1];
+    bool f = (i == 0) || flag_differs(a, i);
     a.head[i] = f ? (u32)i : 0u;
     COUNT_IF(a.ngroups, f);
 }
@@ -141,7 +154,7 @@ __global__ void __launch_bounds__(256) k_flag(long long n, FlagArgs a) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool f = false;
     if (i < n) {
-        f = (i == 0) || a.keys[i] != a.keys[i - 1];
+        f = (i == 0) || flag_differs(a, i);
         a.head[i] = f ? (u32)i : 0u;
     }
     int c = __syncthreads_count(f);
@@ -155,6 +168,15 @@ static inline void launch_flag(Exec &ex, long long n, FlagArgs a) {
     ex.launches++;
 }
 #endif
+
+// the first suffix of a set starts a group even when its key equals the last key of the set before
+// (segmented first sort: the set number is not part of the key)
+struct SetStartArgs { BatchView v; u32 *head; u32 *ngroups; };
+HD void setstart_body(long long s, const SetStartArgs &a) {
+    u32 pos = a.v.set_base0[s];
+    if (pos != 0 && a.head[pos] != pos) { a.head[pos] = pos; ATOMIC_ADD(a.ngroups, 1u); }
+}
+MAP_KERNEL(setstart, SetStartArgs, 8)
 
 struct SetRankArgs { const u32 *sa; const u32 *head; u32 *rank; };
 HD void setrank_body(long long i, const SetRankArgs &a) { a.rank[a.sa[i]] = a.head[i]; }

@@ -17,6 +17,20 @@ struct PrimScratch {
     DevMem chain;         // single-pass scan: tile counter + one status word per tile
 };
 
+#define RS_TILE_ELEMS 2048 // keys per tile-block of a radix pass
+// Segmented sort: tile-blocks never straddle a segment (a sequence set) and the digit counters are laid
+// out segment by segment, so one exclusive scan gives offsets that keep every element inside its own
+// segment -- the set number, the most significant part of the order, costs no radix pass.
+struct RsSeg {
+    const u32 *blk_start;  // [nblocks] first element of tile-block b
+    const u32 *blk_count;  // [nblocks] elements in it (<= RS_TILE)
+    const u32 *blk_cbase;  // [nblocks] index of the block's digit-0 counter
+    const u32 *blk_stride; // [nblocks] distance between its counters of consecutive digits (blocks of its segment)
+    u32 nblocks;
+    const u32 *seg_bounds; // [nsegs+1] first element of every segment
+    u32 nsegs;
+};
+
 #ifdef CSA_EMU
 // ------------------------------- CPU emulation (tests only) -------------------------------
 template <class Op, bool INCLUSIVE>
@@ -31,13 +45,20 @@ static int scan_u32(Exec &, PrimScratch &, const u32 *in, u32 *out, long long n,
     return 0;
 }
 
-static int radix_sort_pairs(Exec &, PrimScratch &, u64 *&keys, u32 *&vals, u64 *&keys_alt, u32 *&vals_alt,
-                            long long n, int begin_bit, int end_bit) {
+template <class K>
+static int radix_sort_pairs(Exec &, PrimScratch &, K *&keys, u32 *&vals, K *&keys_alt, u32 *&vals_alt,
+                            long long n, int begin_bit, int end_bit, const RsSeg *seg = nullptr) {
     if (n <= 1 || end_bit <= begin_bit) return 0;
-    u64 mask = (end_bit - begin_bit >= 64) ? ~0ull : (((1ull << (end_bit - begin_bit)) - 1) << begin_bit);
+    const int kb = (int)sizeof(K) * 8;
+    K mask = (end_bit - begin_bit >= kb) ? (K)~(K)0 : (K)((((K)1 << (end_bit - begin_bit)) - 1) << begin_bit);
     std::vector<long long> idx(n);
     for (long long i = 0; i < n; i++) idx[i] = i;
-    std::stable_sort(idx.begin(), idx.end(), [&](long long a, long long b) { return (keys[a] & mask) < (keys[b] & mask); });
+    u32 one[2] = {0, (u32)n};
+    const u32 *bounds = seg ? seg->seg_bounds : one;
+    u32 nsegs = seg ? seg->nsegs : 1;
+    for (u32 g = 0; g < nsegs; g++) // every segment on its own: elements never leave their segment
+        std::stable_sort(idx.begin() + bounds[g], idx.begin() + bounds[g + 1],
+                         [&](long long a, long long b) { return (keys[a] & mask) < (keys[b] & mask); });
     for (long long i = 0; i < n; i++) { keys_alt[i] = keys[idx[i]]; vals_alt[i] = vals[idx[i]]; }
     std::swap(keys, keys_alt);
     std::swap(vals, vals_alt);
@@ -239,56 +260,64 @@ static int scan_u32(Exec &ex, PrimScratch &ps, const u32 *in, u32 *out, long lon
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_ITEMS 8
 #define RS_TILE (RS_THREADS * RS_ITEMS)
+static_assert(RS_TILE == RS_TILE_ELEMS, "tile size");
 #define RS_BITS 8
 #define RS_BINS 256
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const u64 *__restrict__ keys, u32 *__restrict__ counts,
-                                                        long long n, int shift, unsigned nblocks) {
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K *__restrict__ keys, u32 *__restrict__ counts,
+                                                        long long n, int shift, RsSeg seg) {
     __shared__ u32 h[RS_WARPS][RS_BINS];
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    long long base = (long long)blockIdx.x * RS_TILE + (long long)warp * (RS_ITEMS * 32) + lane;
+    const long long start = seg.blk_start ? (long long)seg.blk_start[blockIdx.x] : (long long)blockIdx.x * RS_TILE;
+    const long long end = seg.blk_start ? start + seg.blk_count[blockIdx.x] : (start + RS_TILE < n ? start + RS_TILE : n);
+    long long base = start + (long long)warp * (RS_ITEMS * 32) + lane;
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
         long long i = base + j * 32;
-        if (i < n) {
+        if (i < end) {
             unsigned d = (unsigned)(keys[i] >> shift) & (RS_BINS - 1);
             atomicAdd(&h[warp][d], 1u);
         }
     }
     __syncthreads();
+    const size_t cbase = seg.blk_start ? seg.blk_cbase[blockIdx.x] : blockIdx.x;
+    const size_t stride = seg.blk_start ? seg.blk_stride[blockIdx.x] : seg.nblocks;
     for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
         u32 s = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) s += h[w][d];
-        counts[(size_t)d * nblocks + blockIdx.x] = s;
+        counts[cbase + (size_t)d * stride] = s;
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict__ keys, const u32 *__restrict__ vals,
-                                                           u64 *__restrict__ keys_out, u32 *__restrict__ vals_out,
-                                                           const u32 *__restrict__ offsets, long long n, int shift,
-                                                           unsigned nblocks) {
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *__restrict__ keys, const u32 *__restrict__ vals,
+                                                           K *__restrict__ keys_out, u32 *__restrict__ vals_out,
+                                                           const u32 *__restrict__ offsets, long long n, int shift, RsSeg seg) {
     __shared__ u32 h[RS_WARPS][RS_BINS];
     __shared__ u32 tstart[RS_BINS], gdelta[RS_BINS];
-    __shared__ u64 s_keys[RS_TILE];
+    __shared__ K s_keys[RS_TILE];
     __shared__ u32 s_vals[RS_TILE];
     __shared__ u32 s_scan[33];
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    long long base = (long long)blockIdx.x * RS_TILE + (long long)warp * (RS_ITEMS * 32) + lane;
-    u64 k[RS_ITEMS];
+    const long long start = seg.blk_start ? (long long)seg.blk_start[blockIdx.x] : (long long)blockIdx.x * RS_TILE;
+    const long long end = seg.blk_start ? start + seg.blk_count[blockIdx.x] : (start + RS_TILE < n ? start + RS_TILE : n);
+    long long base = start + (long long)warp * (RS_ITEMS * 32) + lane;
+    K k[RS_ITEMS];
     u32 v[RS_ITEMS];
     u32 rank[RS_ITEMS];
     unsigned dig[RS_ITEMS];
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
         long long i = base + j * 32;
-        bool ok = i < n;
-        k[j] = ok ? keys[i] : 0;
+        bool ok = i < end;
+        k[j] = ok ? keys[i] : (K)0;
         v[j] = ok ? vals[i] : 0;
         dig[j] = ok ? ((unsigned)(k[j] >> shift) & (RS_BINS - 1)) : RS_BINS; // RS_BINS = "no key"
     }
@@ -323,7 +352,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict
     tstart[threadIdx.x] = dstart;
     // the element that ends up at place q of the sorted tile goes to out[gbase[d] + q - tstart[d]]:
     // fold both into one word so the write-out loop needs a single lookup
-    gdelta[threadIdx.x] = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x] - dstart;
+    const size_t cbase = seg.blk_start ? seg.blk_cbase[blockIdx.x] : blockIdx.x;
+    const size_t stride = seg.blk_start ? seg.blk_stride[blockIdx.x] : seg.nblocks;
+    gdelta[threadIdx.x] = offsets[cbase + (size_t)threadIdx.x * stride] - dstart;
     __syncthreads();
     // stage the tile in digit order in shared memory ...
 #pragma unroll
@@ -338,9 +369,9 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict
     __syncthreads();
     // ... and write it out in that order: neighbouring threads write neighbouring addresses inside
     // every digit's run (coalesced), instead of 32 scattered sectors per warp store
-    const u32 cnt = (u32)(((long long)blockIdx.x * RS_TILE + RS_TILE <= n) ? RS_TILE : (n - (long long)blockIdx.x * RS_TILE));
+    const u32 cnt = (u32)(end - start);
     for (u32 q = threadIdx.x; q < cnt; q += RS_THREADS) {
-        u64 kk = s_keys[q];
+        K kk = s_keys[q];
         unsigned d = (unsigned)(kk >> shift) & (RS_BINS - 1);
         u32 pos = gdelta[d] + q;
         keys_out[pos] = kk;
@@ -348,28 +379,33 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const u64 *__restrict
     }
 }
 
-// Stable LSD sort on key bits [begin_bit, end_bit).  keys/vals and the _alt buffers are swapped
-// as passes go; on return keys/vals point at the sorted data.
-static int radix_sort_pairs(Exec &ex, PrimScratch &ps, u64 *&keys, u32 *&vals, u64 *&keys_alt, u32 *&vals_alt,
-                            long long n, int begin_bit, int end_bit) {
+// Stable LSD sort on key bits [begin_bit, end_bit), u32 or u64 keys, optionally segment by segment.
+// keys/vals and the _alt buffers are swapped as passes go; on return keys/vals point at the sorted data.
+template <class K>
+static int radix_sort_pairs(Exec &ex, PrimScratch &ps, K *&keys, u32 *&vals, K *&keys_alt, u32 *&vals_alt,
+                            long long n, int begin_bit, int end_bit, const RsSeg *segp = nullptr) {
     if (n <= 1 || end_bit <= begin_bit) return 0;
     if (n >= (1ll << 32)) CSA_FAIL(-2, "radix sort: more than 2^32 elements");
-    unsigned nb = (unsigned)((n + RS_TILE - 1) / RS_TILE);
+    RsSeg seg;
+    if (segp) seg = *segp;
+    else { seg.blk_start = seg.blk_count = seg.blk_cbase = seg.blk_stride = seg.seg_bounds = nullptr; seg.nsegs = 1; seg.nblocks = (unsigned)((n + RS_TILE - 1) / RS_TILE); }
+    unsigned nb = seg.nblocks;
     int rc = dev_alloc(ps.counts, sizeof(u32) * (size_t)RS_BINS * nb);
     if (rc) return rc;
     u32 *counts = (u32 *)ps.counts.p;
+    const double kbytes = (double)sizeof(K);
     for (int shift = begin_bit; shift < end_bit; shift += RS_BITS) {
-        PROF_BEGIN(ex, "k_rs_hist", 8.0 * n);
-        k_rs_hist<<<nb, RS_THREADS, 0, ex.stream>>>(keys, counts, n, shift, nb);
+        PROF_BEGIN(ex, "k_rs_hist", kbytes * n);
+        k_rs_hist<K><<<nb, RS_THREADS, 0, ex.stream>>>(keys, counts, n, shift, seg);
         PROF_END(ex);
         ex.launches++;
         rc = scan_u32<ScanSum, false>(ex, ps, counts, counts, (long long)RS_BINS * nb);
         if (rc) return rc;
-        PROF_BEGIN(ex, "k_rs_scatter", 24.0 * n);
-        k_rs_scatter<<<nb, RS_THREADS, 0, ex.stream>>>(keys, vals, keys_alt, vals_alt, counts, n, shift, nb);
+        PROF_BEGIN(ex, "k_rs_scatter", 2.0 * (kbytes + 4.0) * n);
+        k_rs_scatter<K><<<nb, RS_THREADS, 0, ex.stream>>>(keys, vals, keys_alt, vals_alt, counts, n, shift, seg);
         PROF_END(ex);
         ex.launches++;
-        u64 *tk = keys; keys = keys_alt; keys_alt = tk;
+        K *tk = keys; keys = keys_alt; keys_alt = tk;
         u32 *tv = vals; vals = vals_alt; vals_alt = tv;
     }
     return 0;
