@@ -281,8 +281,17 @@ def main():
                             "algorithmic_GBps": round(by / ms / 1e6, 1) if ms > 0 else None})
         name, n, ms, by = rows[0]
         ach = by / ms / 1e6
+        # DRAM bytes per launch from the committed ncu capture of this kernel (profiles/traffic.json holds
+        # dram__bytes_read+write per suffix), scaled to this run's launch size
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+            if tr:
+                traffic, traffic_src = tr["dram_bytes_per_item"] * batch.nbases, tr["source"]
+        except (OSError, ValueError, KeyError):
+            pass
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "launches_per_step": n, "avg_launch_ms": ms / n,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": n, "avg_launch_ms": ms / n,
                     "algorithmic_bytes_per_launch": by / n, "share_of_step": ms / tot}
 
     # ---- the reference on this box's host cores (rank 0, N=1 only) ----

@@ -380,19 +380,24 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
     // gencycsuffixtrees.c compares rotations letter by letter; two periodic strings that agree on
     // n_a+n_b letters agree for ever, so 2*nmax sorted letters settle every comparison
     while (ngroups != N && sorted_len < 2ull * c->nmax) {
-        TRY(dev_zero(ex, counter, 3 * sizeof(u32)));
+        TRY(dev_zero(ex, counter, 4 * sizeof(u32)));
         { TileArgs a{head, P<u32>(c->tiles), counter + 1, N, ntiles}; launch_tile(ex, ntiles, a); }
         u32 oversize = 0;
         if (maxg > RF_NOMINAL) TRY(read_u32(c, counter + 1, &oversize)); // smaller groups always fit a tile
         if (!oversize && !c->force_global_rounds) {
-            RefineArgs a{v, P<u32>(c->valsA), head, rank, rank2, P<u32>(c->tiles), (u32)sorted_len, counter, ntiles, counter + 2};
+            RefineArgs a{v, P<u32>(c->valsA), head, rank, rank2, P<u32>(c->tiles), (u32)sorted_len, counter, ntiles, counter + 2, counter + 3};
             // small groups: four times the letters per round (three rank gathers); else twice
             const bool quad = maxg <= RF_QUAD_GROUP && !c->no_quad_rounds && 4 * sorted_len < (1ull << 31);
             if (quad) launch_refine4(ex, a); else launch_refine(ex, a);
             std::swap(rank, rank2);
-            u32 res[3];
+            u32 res[4];
             TRY(d2h(ex, res, counter, sizeof(res)));
             ngroups = res[0]; maxg = res[2];
+#ifndef CSA_EMU
+            // the profile counts what the round really had to move: every suffix's head (4 B), and for
+            // the res[3] suffixes not settled yet the rest (sa in/out, sequence, ranks gathered, head and rank out)
+            if (ex.prof && !ex.prof->recs.empty()) ex.prof->recs.back().bytes = 4.0 * N + (quad ? 32.0 : 24.0) * res[3];
+#endif
             if (quad) { c->rounds_quad++; sorted_len *= 4; } else { c->rounds_tiled++; sorted_len *= 2; }
         } else { // a group larger than a tile: device-wide radix sort of (rank, rank h letters on)
             { Key2Args a{v, P<u32>(c->valsA), rank, P<u64>(c->keysA), (u32)sorted_len, nbits}; launch_key2(ex, N, a); }
@@ -504,16 +509,26 @@ static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
     { TreeArgs a{q, P<u32>(c->psv), P<u32>(c->nsv), P<u32>(c->pse), P<u32>(c->sa0), P<u32>(c->parent), P<u32>(c->nsize), P<u32>(c->minpos)};
       launch_tree(ex, 2ll * N0, a); }
     { MinposArgs a{N0, P<u32>(c->parent), P<u32>(c->minpos)}; launch_minpos(ex, N0, a); }
-    { ChildKeyArgs a{N0, P<u32>(c->parent), P<u32>(c->minpos), P<u64>(c->keysA), P<u32>(c->valsA)}; launch_childkey(ex, 2ll * N0, a); }
-    TRY(sort_pairs(c, 2ll * N0, 0, 32 + bits_for(2ull * N0)));
-    { BeforeArgs a{P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->nsize), P<u32>(c->val), P<u32>(c->up), P<u32>(c->parent)};
+    const int mbits = bits_for(c->n0max);
+    { ChildKeyArgs a{N0, P<u32>(c->parent), P<u32>(c->minpos), P<u64>(c->keysA), P<u32>(c->valsA), mbits}; launch_childkey(ex, 2ll * N0, a); }
+    TRY(sort_pairs(c, 2ll * N0, 0, mbits + bits_for(2ull * N0)));
+    { BeforeArgs a{P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->nsize), P<u32>(c->val), P<u32>(c->up), P<u32>(c->parent), mbits};
       launch_before(ex, 2ll * N0, a); }
+    // pointer jumping: the tree is as deep as log_4 of the set in practice, n0 at worst; stop when
+    // nobody moved (looked at every third round)
     int rounds = bits_for(c->n0max) + 1;
     u32 *val = P<u32>(c->val), *up = P<u32>(c->up), *val2 = P<u32>(c->val2), *up2 = P<u32>(c->up2);
+    u32 *moving = P<u32>(c->counter) + 12;
     for (int r = 0; r < rounds; r++) {
-        JumpArgs a{val, up, val2, up2};
+        if (r % 3 == 0) TRY(dev_zero(ex, moving, sizeof(u32)));
+        JumpArgs a{val, up, val2, up2, moving};
         launch_jump(ex, 2ll * N0, a);
         std::swap(val, val2); std::swap(up, up2);
+        if (r % 3 == 2) {
+            u32 m = 0;
+            TRY(read_u32(c, moving, &m));
+            if (!m) break;
+        }
     }
     // order the blocks: DFS number descending, then stably (set, depth descending)
     BlockKeyArgs k{v, sa, idx0, flag0, val, N0, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set),

@@ -672,34 +672,36 @@ HD void minpos_body(long long t, const MinposArgs &a) {
 MAP_KERNEL(minpos, MinposArgs, 12)
 
 // children grouped by parent and ordered by first occurrence: sort key (parent, minpos)
-struct ChildKeyArgs { u32 N0; const u32 *parent; const u32 *minpos; u64 *keys; u32 *vals; };
+struct ChildKeyArgs { u32 N0; const u32 *parent; const u32 *minpos; u64 *keys; u32 *vals; int mbits; };
 HD void childkey_body(long long x, const ChildKeyArgs &a) {
     u32 p = a.parent[x];
-    // borders that are no node, and roots, sort to the end
+    // borders that are no node, and roots, sort to the end; minpos < 2^mbits (a position in sequence 0)
     bool live = (p != CSA_NONE) && (p != (u32)x);
-    a.keys[x] = live ? (((u64)p << 32) | a.minpos[x]) : ~0ull;
+    a.keys[x] = live ? (((u64)p << a.mbits) | a.minpos[x]) : ~0ull;
     a.vals[x] = (u32)x;
 }
 MAP_KERNEL(childkey, ChildKeyArgs, 20)
 
-struct BeforeArgs { const u64 *keys; const u32 *vals; const u32 *size; u32 *val; u32 *up; const u32 *parent; };
+struct BeforeArgs { const u64 *keys; const u32 *vals; const u32 *size; u32 *val; u32 *up; const u32 *parent; int mbits; };
 HD void before_body(long long j, const BeforeArgs &a) {
     u64 key = a.keys[j];
     u32 x = a.vals[j];
     if (key == ~0ull) { a.val[x] = 0; a.up[x] = (a.parent[x] == CSA_NONE) ? x : a.parent[x]; return; }
-    u32 p = (u32)(key >> 32);
+    u32 p = (u32)(key >> a.mbits);
     u32 sum = 0;
-    for (long long q = j - 1; q >= 0 && (u32)(a.keys[q] >> 32) == p && a.keys[q] != ~0ull; q--) sum += a.size[a.vals[q]];
+    for (long long q = j - 1; q >= 0 && a.keys[q] != ~0ull && (u32)(a.keys[q] >> a.mbits) == p; q--) sum += a.size[a.vals[q]];
     a.val[x] = sum;
     a.up[x] = p;
 }
 MAP_KERNEL(before, BeforeArgs, 24)
 
-struct JumpArgs { const u32 *val; const u32 *up; u32 *val2; u32 *up2; };
+struct JumpArgs { const u32 *val; const u32 *up; u32 *val2; u32 *up2; u32 *moving; };
 HD void jump_body(long long x, const JumpArgs &a) {
     u32 u = a.up[x];
+    u32 uu = a.up[u];
     a.val2[x] = a.val[x] + a.val[u];
-    a.up2[x] = a.up[u];
+    a.up2[x] = uu;
+    if (uu != u) *a.moving = 1u; // somebody has not reached its root yet (same value from every writer)
 }
 MAP_KERNEL(jump, JumpArgs, 16)
 
@@ -1145,6 +1147,7 @@ static inline void launch_maxgroup(Exec &ex, long long n, MaxGroupArgs a) {
 struct RefineArgs {
     BatchView v; u32 *sa; u32 *head; const u32 *rank; u32 *rank2; const u32 *tb; u32 h; u32 *ngroups; u32 ntiles;
     u32 *maxgroup; // largest group after the round (atomic max)
+    u32 *staged;   // suffixes that were not settled yet, i.e. really read, ranked and written (for the profile)
 };
 
 #ifdef CSA_EMU
@@ -1198,13 +1201,13 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
     __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled, bit 2 (at a group's
                                                // first place): some member's second rank differs
     __shared__ u32 s_scan[33];
-    __shared__ u32 s_count, s_big, s_mid, s_maxg;
+    __shared__ u32 s_count, s_big, s_mid, s_maxg, s_staged;
     u32 *s_okey = (u32 *)s_ck;     // sorted keys; s_ck is dead (and fenced) by then
     const u32 base = a.tb[blockIdx.x];
     const u32 n = a.tb[blockIdx.x + 1] - base;
     if (n == 0 || n > RF_CAP) return;
     const u32 tid = threadIdx.x;
-    if (tid == 0) { s_count = 0; s_big = 0; s_mid = 0; s_maxg = 1; }
+    if (tid == 0) { s_count = 0; s_big = 0; s_mid = 0; s_maxg = 1; s_staged = 0; }
     // 1. borders.  A settled suffix is a singleton whose rank is already in BOTH rank buffers.
     //    (every phase that loads from HBM issues all RF_ITEMS loads of a thread before using any:
     //    the gathers below are chains of four dependent L2/HBM accesses and need the overlap)
@@ -1244,6 +1247,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
                 if (!single) share |= 1u << x;
             }
         }
+        if (need) atomicAdd(&s_staged, (u32)__popc(need));
 #pragma unroll
         for (int x = 0; x < RF_ITEMS; x++) gv[x] = (need >> x & 1u) ? a.sa[base + tid + x * RF_THREADS] : 0u;
 #pragma unroll
@@ -1405,7 +1409,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
         if (lane == 0) nsingle += made;
         if (nsingle) atomicAdd(&s_count, nsingle);
         __syncthreads();
-        if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); }
+        if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); atomicAdd(a.staged, s_staged); }
         return;
     }
     // 3c. a group longer than a warp: composite keys and a counting rank over shared memory
@@ -1500,7 +1504,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
             a.rank2[g] = h2;
         }
     }
-    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); }
+    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); atomicAdd(a.staged, s_staged); }
 }
 
 // ---- the same round, four times the letters: groups ordered by the ranks h, 2h and 3h letters on ----------
@@ -1514,12 +1518,12 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
     __shared__ u32 s_gstart[RF_CAP / 2 + 1];
     __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled
     __shared__ u32 s_scan[33];
-    __shared__ u32 s_count, s_maxg;
+    __shared__ u32 s_count, s_maxg, s_staged;
     const u32 base = a.tb[blockIdx.x];
     const u32 n = a.tb[blockIdx.x + 1] - base;
     if (n == 0 || n > RF_CAP) return;
     const u32 tid = threadIdx.x;
-    if (tid == 0) { s_count = 0; s_maxg = 1; }
+    if (tid == 0) { s_count = 0; s_maxg = 1; s_staged = 0; }
     int all_settled = 1;
     {
         u32 hdv[RF_ITEMS];
@@ -1555,6 +1559,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
                 if (!single) share |= 1u << x;
             }
         }
+        if (need) atomicAdd(&s_staged, (u32)__popc(need));
 #pragma unroll
         for (int x = 0; x < RF_ITEMS; x++) gv[x] = (need >> x & 1u) ? a.sa[base + tid + x * RF_THREADS] : 0u;
 #pragma unroll
@@ -1699,7 +1704,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
     if (lane == 0) nsingle += made;
     if (nsingle) atomicAdd(&s_count, nsingle);
     __syncthreads();
-    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); }
+    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); atomicAdd(a.staged, s_staged); }
 }
 static inline void launch_refine4(Exec &ex, const RefineArgs &a) {
     if (a.ntiles == 0) return;
