@@ -1629,12 +1629,18 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
                 const u32 xa = (rem >> lane & 1u) ? ka : 0xFFFFFFFFu;
                 const u32 ma = __reduce_min_sync(0xffffffffu, xa);
                 const unsigned m1 = __ballot_sync(0xffffffffu, xa == ma) & rem;
-                const u32 xb = (m1 >> lane & 1u) ? kb : 0xFFFFFFFFu;
-                const u32 mb = __reduce_min_sync(0xffffffffu, xb);
-                const unsigned m2 = __ballot_sync(0xffffffffu, xb == mb) & m1;
-                const u32 xc = (m2 >> lane & 1u) ? kc : 0xFFFFFFFFu;
-                const u32 mc = __reduce_min_sync(0xffffffffu, xc);
-                const unsigned eq = __ballot_sync(0xffffffffu, xc == mc) & m2;
+                unsigned eq = m1;
+                if (m1 & (m1 - 1)) { // more than one suffix shares the smallest first rank: look further
+                    const u32 xb = (m1 >> lane & 1u) ? kb : 0xFFFFFFFFu;
+                    const u32 mb = __reduce_min_sync(0xffffffffu, xb);
+                    const unsigned m2 = __ballot_sync(0xffffffffu, xb == mb) & m1;
+                    eq = m2;
+                    if (m2 & (m2 - 1)) {
+                        const u32 xc = (m2 >> lane & 1u) ? kc : 0xFFFFFFFFu;
+                        const u32 mc = __reduce_min_sync(0xffffffffu, xc);
+                        eq = __ballot_sync(0xffffffffu, xc == mc) & m2;
+                    }
+                }
                 if (eq >> lane & 1u) { mynew = placed + __popc(eq & ltmask); myhead = placed; }
                 const u32 c = (u32)__popc(eq);
                 placed += c;
