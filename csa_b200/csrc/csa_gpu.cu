@@ -51,6 +51,7 @@ struct csa_gpu_ctx {
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, counter, tiles;
     double lcp_mean_sample = 0;
     int force_kasai = 0;
+    int rounds_list = 0, round_mode = 0;
     int rounds_tiled = 0, rounds_global = 0, rounds_quad = 0, force_global_rounds = 0, no_quad_rounds = 0;
     DevMem pyr, sa0, saidx0, leaf_set, lcp0, psv, nsv, pse, parent, nsize, minpos, val, up, val2, up2;
     DevMem set_nblocks, set_blk0, set_pos0, set_flags, set_nchains, set_cyclic, firstmax, set_collected, set_suffixfree;
@@ -368,7 +369,7 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
     u64 sorted_len = (u64)letters;
     u32 ngroups = 0;
     TRY(heads_and_ranks(c, head, rank, counter, &ngroups, !any_other, true));
-    c->rounds_tiled = c->rounds_global = c->rounds_quad = 0;
+    c->rounds_tiled = c->rounds_global = c->rounds_quad = c->rounds_list = 0;
     // counter[0] groups, [1] a tile would overflow, [2] largest group
     auto largest_group = [&](u32 *out) -> int {
         TRY(dev_zero(ex, counter + 2, sizeof(u32)));
@@ -379,20 +380,70 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
     if (ngroups != N) TRY(largest_group(&maxg));
     // gencycsuffixtrees.c compares rotations letter by letter; two periodic strings that agree on
     // n_a+n_b letters agree for ever, so 2*nmax sorted letters settle every comparison
+    // group lists (see k_refine_g): two lists of (start:size), two of fresh singletons, ping-ponged.
+    // They live in buffers that are idle during this stage; a device-wide round clobbers the scratch.
+    u64 *glist[2] = {P<u64>(c->t4), P<u64>(c->t2)};      // N/2 entries of 8 B each fit 4 B x N
+    bool list_valid = false;
+    u32 nlist = 0, nsingles = 0, active_est = N;
+    int cur = 0;
+    auto singles_buf = [&](int which) { return which == 0 ? P<u32>(c->sa) : P<u32>(c->valsB); };
+    auto flush_singles = [&]() -> int { // ranks of last round's new singletons into the other rank buffer
+        if (nsingles) { CopySinglesArgs a{singles_buf(cur), rank, rank2, head}; launch_copysingles(ex, nsingles, a); }
+        nsingles = 0;
+        return 0;
+    };
     while (ngroups != N && sorted_len < 2ull * c->nmax) {
-        TRY(dev_zero(ex, counter, 4 * sizeof(u32)));
+        // lists pay off once most suffixes stand alone; while nearly all still share a group the tile
+        // rounds stream them at the same cost without the list upkeep
+        // (and while the groups are not tiny: one warp per group wastes its lanes on pairs and triples)
+        const u32 sharing_groups = ngroups > N - active_est ? ngroups - (N - active_est) : 1;
+        const bool want_list = c->round_mode == 0 && maxg <= RF_QUAD_GROUP &&
+                               (list_valid || (active_est < N / 2 && active_est / sharing_groups >= 6));
+        if (want_list) {
+            if (!list_valid) {
+                TRY(dev_zero(ex, counter + 4, sizeof(u32)));
+                { GListBuildArgs a{head, N, glist[cur], counter + 4}; launch_glist_build(ex, a); }
+                TRY(read_u32(c, counter + 4, &nlist));
+                // from here on only listed suffixes are touched: both rank buffers must agree on all others
+                TRY(d2d(ex, rank2, rank, sizeof(u32) * (size_t)N));
+                nsingles = 0;
+                list_valid = true;
+            }
+            TRY(flush_singles());
+            const int nkeys = (4 * sorted_len < (1ull << 31)) ? 3 : 1;
+            TRY(dev_zero(ex, counter + 2, 4 * sizeof(u32))); // [2] largest group [3] staged [4] next list [5] new singletons
+            RefineGArgs a{v, P<u32>(c->valsA), head, rank, rank2, (u32)sorted_len, nkeys, glist[cur], nlist,
+                          glist[cur ^ 1], counter + 4, singles_buf(cur ^ 1), counter + 5, counter + 2, counter + 3,
+                          P<u32>(c->keysA), P<u32>(c->keysA) + N, P<u32>(c->keysB), P<u32>(c->keysB) + N};
+            launch_refine_g(ex, a);
+            std::swap(rank, rank2);
+            cur ^= 1;
+            u32 res[4];
+            TRY(d2h(ex, res, counter + 2, sizeof(res)));
+#ifndef CSA_EMU
+            if (ex.prof && !ex.prof->recs.empty()) ex.prof->recs.back().bytes = (nkeys == 3 ? 36.0 : 28.0) * res[1] + 8.0 * nlist;
+#endif
+            maxg = res[0] > 1 ? res[0] : 1; nlist = res[2]; nsingles = res[3]; active_est = res[1];
+            if (nlist == 0) ngroups = N; // nothing shares a group any more
+            else ngroups = (N - res[1]) + nlist + nsingles; // (rough while lists run; exact again after a tile round)
+            c->rounds_list++;
+            sorted_len *= (nkeys == 3 ? 4 : 2);
+            continue;
+        }
+        if (list_valid) { TRY(flush_singles()); list_valid = false; }
+        TRY(dev_zero(ex, counter, 5 * sizeof(u32)));
         { TileArgs a{head, P<u32>(c->tiles), counter + 1, N, ntiles}; launch_tile(ex, ntiles, a); }
         u32 oversize = 0;
         if (maxg > RF_NOMINAL) TRY(read_u32(c, counter + 1, &oversize)); // smaller groups always fit a tile
         if (!oversize && !c->force_global_rounds) {
-            RefineArgs a{v, P<u32>(c->valsA), head, rank, rank2, P<u32>(c->tiles), (u32)sorted_len, counter, ntiles, counter + 2, counter + 3};
+            RefineArgs a{v, P<u32>(c->valsA), head, rank, rank2, P<u32>(c->tiles), (u32)sorted_len, counter, ntiles, counter + 2, counter + 3, counter + 4};
             // small groups: four times the letters per round (three rank gathers); else twice
             const bool quad = maxg <= RF_QUAD_GROUP && !c->no_quad_rounds && 4 * sorted_len < (1ull << 31);
             if (quad) launch_refine4(ex, a); else launch_refine(ex, a);
             std::swap(rank, rank2);
-            u32 res[4];
+            u32 res[5];
             TRY(d2h(ex, res, counter, sizeof(res)));
-            ngroups = res[0]; maxg = res[2];
+            ngroups = res[0]; maxg = res[2]; active_est = res[4];
 #ifndef CSA_EMU
             // the profile counts what the round really had to move: every suffix's head (4 B), and for
             // the res[3] suffixes not settled yet the rest (sa in/out, sequence, ranks gathered, head and rank out)
@@ -677,9 +728,13 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
 // rounds[0], rounds[1] = rounds of the last run that took the tile path / the device-wide path
 extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds[2]) {
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
-    // force_global: 0 free choice, 1 device-wide rounds only, 2 tile rounds but no quadrupling
-    if (force_global >= 0) { c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; c->force_kasai = force_global == 2; }
-    if (rounds) { rounds[0] = c->rounds_tiled + c->rounds_quad; rounds[1] = c->rounds_global; }
+    // force_global: 0 free choice (group lists while groups are small), 1 device-wide rounds only, 2 tile rounds
+    // with doubling only (and the text-order LCP kernel), 3 tile rounds, quadrupling allowed
+    if (force_global >= 0) {
+        c->round_mode = force_global;
+        c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; c->force_kasai = force_global == 2;
+    }
+    if (rounds) { rounds[0] = c->rounds_tiled + c->rounds_quad + c->rounds_list; rounds[1] = c->rounds_global; }
     return CSA_GPU_OK;
 }
 

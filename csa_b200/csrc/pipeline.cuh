@@ -1148,6 +1148,7 @@ struct RefineArgs {
     BatchView v; u32 *sa; u32 *head; const u32 *rank; u32 *rank2; const u32 *tb; u32 h; u32 *ngroups; u32 ntiles;
     u32 *maxgroup; // largest group after the round (atomic max)
     u32 *staged;   // suffixes that were not settled yet, i.e. really read, ranked and written (for the profile)
+    u32 *active;   // suffixes that still share a group after the round (warp paths only; else = staged)
 };
 
 #ifdef CSA_EMU
@@ -1176,6 +1177,7 @@ static inline void emu_refine(const RefineArgs &a, int nkeys) {
             for (u32 x = i; x < j; x++) {
                 if (x > i && less(seg[x - i - 1], seg[x - i])) hd = x;
                 if (hd == x) (*a.ngroups)++;
+                if (x - hd + 1 == 2) *a.active += 2; else if (x - hd + 1 > 2) *a.active += 1; // suffixes still sharing a group
                 if (x - hd + 1 > *a.maxgroup) *a.maxgroup = x - hd + 1;
                 a.sa[x] = seg[x - i].g;
                 a.head[x] = hd;
@@ -1201,13 +1203,13 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
     __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled, bit 2 (at a group's
                                                // first place): some member's second rank differs
     __shared__ u32 s_scan[33];
-    __shared__ u32 s_count, s_big, s_mid, s_maxg, s_staged;
+    __shared__ u32 s_count, s_big, s_mid, s_maxg, s_staged, s_act;
     u32 *s_okey = (u32 *)s_ck;     // sorted keys; s_ck is dead (and fenced) by then
     const u32 base = a.tb[blockIdx.x];
     const u32 n = a.tb[blockIdx.x + 1] - base;
     if (n == 0 || n > RF_CAP) return;
     const u32 tid = threadIdx.x;
-    if (tid == 0) { s_count = 0; s_big = 0; s_mid = 0; s_maxg = 1; s_staged = 0; }
+    if (tid == 0) { s_count = 0; s_big = 0; s_mid = 0; s_maxg = 1; s_staged = 0; s_act = 0; }
     // 1. borders.  A settled suffix is a singleton whose rank is already in BOTH rank buffers.
     //    (every phase that loads from HBM issues all RF_ITEMS loads of a thread before using any:
     //    the gathers below are chains of four dependent L2/HBM accesses and need the overlap)
@@ -1322,7 +1324,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
             if (listmask >> e & 1u) s_gstart[lbefore++] = j0 + e;
         __syncthreads();
         const unsigned lane = tid & 31u, warp = tid >> 5, ltmask = (1u << lane) - 1u;
-        u32 made = 0, widest = 0;
+        u32 made = 0, widest = 0, sharing = 0;
         for (u32 gi = warp; gi < ngroups_listed; gi += RF_THREADS / 32) {
             const u32 S = s_gstart[gi];
             // the group ends where the next one begins (a border flag; the end of the tile counts as one)
@@ -1353,6 +1355,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
                     const u32 c = (u32)__popc(eq);
                     placed += c;
                     widest = c > widest ? c : widest;
+                    if (c > 1) sharing += c;
                     rem &= ~eq;
                     made++;
                 }
@@ -1390,11 +1393,13 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
                     }
                     placed += cnt;
                     widest = cnt > widest ? cnt : widest;
+                    if (cnt > 1) sharing += cnt;
                     made++;
                 }
             }
         }
         if (lane == 0 && widest > 1) atomicMax(&s_maxg, widest);
+        if (lane == 0 && sharing) atomicAdd(&s_act, sharing);
         u32 nsingle = 0;
         for (u32 j = tid; j < n; j += RF_THREADS) {
             u32 fl = s_fl[j];
@@ -1409,7 +1414,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
         if (lane == 0) nsingle += made;
         if (nsingle) atomicAdd(&s_count, nsingle);
         __syncthreads();
-        if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); atomicAdd(a.staged, s_staged); }
+        if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); atomicAdd(a.staged, s_staged); if (s_act) atomicAdd(a.active, s_act); }
         return;
     }
     // 3c. a group longer than a warp: composite keys and a counting rank over shared memory
@@ -1485,6 +1490,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
         }
     }
     if (widest > 1) atomicMax(&s_maxg, widest);
+    if (tid == 0) s_act = n; // upper bound: this path does not count the suffixes still sharing
     __syncthreads();
     // 7. write back, coalesced.  The new rank goes to the OTHER rank buffer (a round reads only the
     //    ranks of the round before); a suffix that stood alone at the start keeps its place and is
@@ -1504,7 +1510,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine(RefineArgs a) {
             a.rank2[g] = h2;
         }
     }
-    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); atomicAdd(a.staged, s_staged); }
+    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); atomicAdd(a.staged, s_staged); if (s_act) atomicAdd(a.active, s_act); }
 }
 
 // ---- the same round, four times the letters: groups ordered by the ranks h, 2h and 3h letters on ----------
@@ -1518,12 +1524,12 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
     __shared__ u32 s_gstart[RF_CAP / 2 + 1];
     __shared__ unsigned char s_fl[RF_CAP + 4]; // bit 0: first of its group, bit 1: settled
     __shared__ u32 s_scan[33];
-    __shared__ u32 s_count, s_maxg, s_staged;
+    __shared__ u32 s_count, s_maxg, s_staged, s_act;
     const u32 base = a.tb[blockIdx.x];
     const u32 n = a.tb[blockIdx.x + 1] - base;
     if (n == 0 || n > RF_CAP) return;
     const u32 tid = threadIdx.x;
-    if (tid == 0) { s_count = 0; s_maxg = 1; s_staged = 0; }
+    if (tid == 0) { s_count = 0; s_maxg = 1; s_staged = 0; s_act = 0; }
     int all_settled = 1;
     {
         u32 hdv[RF_ITEMS];
@@ -1607,7 +1613,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
         if (listmask >> e & 1u) s_gstart[lbefore++] = j0 + e;
     __syncthreads();
     const unsigned lane = tid & 31u, warp = tid >> 5, ltmask = (1u << lane) - 1u;
-    u32 made = 0, widest = 0;
+    u32 made = 0, widest = 0, sharing = 0;
     for (u32 gi = warp; gi < ngroups_listed; gi += RF_THREADS / 32) {
         const u32 S = s_gstart[gi];
         u32 size = 0;
@@ -1645,6 +1651,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
                 const u32 c = (u32)__popc(eq);
                 placed += c;
                 widest = c > widest ? c : widest;
+                if (c > 1) sharing += c;
                 rem &= ~eq;
                 made++;
             }
@@ -1691,11 +1698,13 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
                 }
                 placed += cnt;
                 widest = cnt > widest ? cnt : widest;
+                if (cnt > 1) sharing += cnt;
                 made++;
             }
         }
     }
     if (lane == 0 && widest > 1) atomicMax(&s_maxg, widest);
+    if (lane == 0 && sharing) atomicAdd(&s_act, sharing);
     u32 nsingle = 0;
     for (u32 j = tid; j < n; j += RF_THREADS) {
         u32 fl = s_fl[j];
@@ -1710,7 +1719,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) k_refine4(RefineArgs a) {
     if (lane == 0) nsingle += made;
     if (nsingle) atomicAdd(&s_count, nsingle);
     __syncthreads();
-    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); atomicAdd(a.staged, s_staged); }
+    if (tid == 0) { atomicAdd(a.ngroups, s_count); atomicMax(a.maxgroup, s_maxg); atomicAdd(a.staged, s_staged); if (s_act) atomicAdd(a.active, s_act); }
 }
 static inline void launch_refine4(Exec &ex, const RefineArgs &a) {
     if (a.ntiles == 0) return;
@@ -1723,6 +1732,280 @@ static inline void launch_refine(Exec &ex, const RefineArgs &a) {
     if (a.ntiles == 0) return;
     PROF_BEGIN(ex, "k_refine", 28.0 * a.v.N);
     k_refine<<<a.ntiles, RF_THREADS, 0, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
+
+// ---- stage 1, group lists: a round touches only the suffixes that still share a group -----------------
+// The tile rounds above read the head of EVERY suffix every round.  Once most suffixes stand alone
+// that is wasted work, so the rounds can also run from a compact list of the groups that still hold
+// two or more suffixes (start : 32 | size : 32).  One warp takes one group: its suffixes sit in
+// consecutive places of the suffix array (one coalesced load), the ranks h (2h, 3h) letters on are
+// gathered, the group is ranked by chained min-reductions as in k_refine4, and sa / head / the other
+// rank buffer are written in place.  New groups of two or more go to the next round's list, new
+// singletons to a list whose ranks are copied into the second rank buffer at the start of the next
+// round (a round may only read ranks of the round before).  Lists are appended through shared
+// memory: one atomic per CTA, not per group.  head[] stays in step, so tile rounds, device-wide
+// rounds and list rounds can follow one another freely.
+struct GListBuildArgs { const u32 *head; u32 N; u64 *list; u32 *count; };
+struct RefineGArgs {
+    BatchView v; u32 *sa; u32 *head; const u32 *rank; u32 *rank2; u32 h; int nkeys;
+    const u64 *list; u32 nlist;
+    u64 *next; u32 *n_next;       // groups of two or more made by this round
+    u32 *singles; u32 *n_singles; // suffixes that came to stand alone in this round
+    u32 *maxgroup; u32 *staged;
+    u32 *ka, *kb, *kc, *gs;       // scratch [N], used by groups longer than a warp
+};
+struct CopySinglesArgs { const u32 *singles; const u32 *rank; u32 *rank2; u32 *head; };
+HD void copysingles_body(long long i, const CopySinglesArgs &a) {
+    u32 g = a.singles[i];
+    u32 r = a.rank[g];
+    a.rank2[g] = r;
+    a.head[r] = r | 0x80000000u; // settled: alone, and its rank is in both buffers
+}
+MAP_KERNEL(copysingles, CopySinglesArgs, 16)
+
+#ifdef CSA_EMU
+static inline void launch_glist_build(Exec &, const GListBuildArgs &a) {
+    for (u32 i = 0; i < a.N; i++)
+        if (i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == i + 1) {
+            u32 st = a.head[i] & 0x7FFFFFFFu;
+            if (i - st + 1 >= 2) a.list[(*a.count)++] = ((u64)st << 32) | (i - st + 1);
+        }
+}
+static inline void launch_refine_g(Exec &, const RefineGArgs &a) {
+    struct Item { u32 k[3]; u32 g; };
+    std::vector<Item> seg;
+    for (u32 gi = 0; gi < a.nlist; gi++) {
+        u32 start = (u32)(a.list[gi] >> 32), size = (u32)a.list[gi];
+        seg.clear();
+        for (u32 x = 0; x < size; x++) {
+            Item it{{0, 0, 0}, a.sa[start + x]};
+            u32 g = it.g;
+            for (int q = 0; q < a.nkeys; q++) { g = cyc_add(a.v, g, a.h); it.k[q] = a.rank[g]; }
+            seg.push_back(it);
+        }
+        auto less = [](const Item &p, const Item &q) {
+            for (int w = 0; w < 3; w++) if (p.k[w] != q.k[w]) return p.k[w] < q.k[w];
+            return false;
+        };
+        std::stable_sort(seg.begin(), seg.end(), less);
+        *a.staged += size;
+        u32 hd = 0;
+        for (u32 x = 0; x <= size; x++) {
+            if (x == size || (x > 0 && less(seg[x - 1], seg[x]))) { // the group [hd, x) is complete
+                u32 c = x - hd;
+                if (c == 1) a.singles[(*a.n_singles)++] = seg[hd].g;
+                else { a.next[(*a.n_next)++] = ((u64)(start + hd) << 32) | c; if (c > *a.maxgroup) *a.maxgroup = c; }
+                hd = x;
+            }
+            if (x < size) { a.sa[start + x] = seg[x].g; a.head[start + x] = start + hd; a.rank2[seg[x].g] = start + hd; }
+        }
+    }
+}
+#else
+__global__ void __launch_bounds__(256) k_glist_build(GListBuildArgs a) {
+    __shared__ u32 sm[33];
+    __shared__ u32 s_base;
+    const u32 i = blockIdx.x * 256u + threadIdx.x;
+    u32 start = 0, size = 0;
+    if (i < a.N && (i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == i + 1)) {
+        start = a.head[i] & 0x7FFFFFFFu;
+        size = i - start + 1;
+    }
+    const u32 f = size >= 2 ? 1u : 0u;
+    u32 total;
+    const u32 off = block_scan_excl(f, total, ScanSum(), sm);
+    if (threadIdx.x == 0 && total) s_base = atomicAdd(a.count, total);
+    __syncthreads();
+    if (f) a.list[s_base + off] = ((u64)start << 32) | size;
+}
+static inline void launch_glist_build(Exec &ex, const GListBuildArgs &a) {
+    if (a.N == 0) return;
+    PROF_BEGIN(ex, "k_glist_build", 4.0 * a.N);
+    k_glist_build<<<(a.N + 255) / 256, 256, 0, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
+}
+
+#define RG_GROUPS 32 // groups per CTA (4 per warp)
+__global__ void __launch_bounds__(256) k_refine_g(RefineGArgs a) {
+    __shared__ u64 s_new[RG_GROUPS * 16];
+    __shared__ u32 s_sing[RG_GROUPS * 32];
+    __shared__ u32 s_nnew, s_nsing, s_maxg, s_staged, s_base_new, s_base_sing;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, ltmask = (1u << lane) - 1u;
+    if (tid == 0) { s_nnew = 0; s_nsing = 0; s_maxg = 1; s_staged = 0; }
+    __syncthreads();
+    const u32 g0 = blockIdx.x * RG_GROUPS;
+    u32 widest = 0, staged = 0;
+    // a warp's RG_GROUPS/8 groups are loaded side by side (every step of the chain list -> suffix ->
+    // sequence -> ranks is a round trip to L2 or HBM), then ranked one after the other
+    constexpr int GW = RG_GROUPS / 8;
+    u32 gstart[GW], gsize[GW], gg[GW], gka[GW], gkb[GW], gkc[GW];
+#pragma unroll
+    for (int q = 0; q < GW; q++) {
+        const u32 gi = g0 + warp + 8u * q;
+        const u64 desc = (gi < a.nlist) ? a.list[gi] : 0ull;
+        gstart[q] = (u32)(desc >> 32);
+        gsize[q] = (u32)desc;
+        staged += gsize[q];
+    }
+#pragma unroll
+    for (int q = 0; q < GW; q++) gg[q] = (gsize[q] <= 32 && lane < gsize[q]) ? a.sa[gstart[q] + lane] : 0u;
+    {
+        u32 kq[GW], oq[GW], lq[GW];
+#pragma unroll
+        for (int q = 0; q < GW; q++) kq[q] = (gsize[q] <= 32 && lane < gsize[q]) ? seq_of(a.v, gg[q]) : 0u;
+#pragma unroll
+        for (int q = 0; q < GW; q++) {
+            const bool m = gsize[q] <= 32 && lane < gsize[q];
+            oq[q] = m ? LDG(a.v.seq_off + kq[q]) : 0u;
+            lq[q] = m ? LDG(a.v.seq_off + kq[q] + 1) : 1u;
+        }
+#pragma unroll
+        for (int q = 0; q < GW; q++) {
+            gka[q] = 0xFFFFFFFFu; gkb[q] = 0; gkc[q] = 0;
+            if (gsize[q] <= 32 && lane < gsize[q]) {
+                const u32 off = oq[q], len = lq[q] - oq[q];
+                u32 hh = a.h;
+                if (hh >= len) hh %= len;
+                u32 q1 = gg[q] - off + hh; if (q1 >= len) q1 -= len;
+                gka[q] = LDG(a.rank + off + q1);
+                if (a.nkeys == 3) {
+                    u32 q2 = q1 + hh; if (q2 >= len) q2 -= len;
+                    u32 q3 = q2 + hh; if (q3 >= len) q3 -= len;
+                    gkb[q] = LDG(a.rank + off + q2);
+                    gkc[q] = LDG(a.rank + off + q3);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < GW; q++) {
+        const u32 start = gstart[q], size = gsize[q];
+        if (size == 0) continue;
+        if (size <= 32) { // one suffix per lane, everything in registers
+            const bool member = lane < size;
+            const u32 g = gg[q], ka = gka[q], kb = gkb[q], kc = gkc[q];
+            unsigned rem = __ballot_sync(0xffffffffu, member);
+            u32 placed = 0, mynew = 0, myhead = 0;
+            bool alone = false;
+            while (rem) {
+                const u32 xa = (rem >> lane & 1u) ? ka : 0xFFFFFFFFu;
+                const u32 ma = __reduce_min_sync(0xffffffffu, xa);
+                const unsigned m1 = __ballot_sync(0xffffffffu, xa == ma) & rem;
+                unsigned eq = m1;
+                if (a.nkeys == 3 && (m1 & (m1 - 1))) { // several share the smallest first rank: look further
+                    const u32 xb = (m1 >> lane & 1u) ? kb : 0xFFFFFFFFu;
+                    const u32 mb = __reduce_min_sync(0xffffffffu, xb);
+                    const unsigned m2 = __ballot_sync(0xffffffffu, xb == mb) & m1;
+                    eq = m2;
+                    if (m2 & (m2 - 1)) {
+                        const u32 xc = (m2 >> lane & 1u) ? kc : 0xFFFFFFFFu;
+                        const u32 mc = __reduce_min_sync(0xffffffffu, xc);
+                        eq = __ballot_sync(0xffffffffu, xc == mc) & m2;
+                    }
+                }
+                const u32 c = (u32)__popc(eq);
+                if (eq >> lane & 1u) { mynew = placed + __popc(eq & ltmask); myhead = placed; alone = (c == 1); }
+                if (c > 1 && (int)lane == __ffs((int)eq) - 1) {
+                    s_new[atomicAdd(&s_nnew, 1u)] = ((u64)(start + placed) << 32) | c;
+                    widest = c > widest ? c : widest;
+                }
+                placed += c;
+                rem &= ~eq;
+            }
+            const unsigned sb = __ballot_sync(0xffffffffu, member && alone);
+            u32 sbase = 0;
+            if (lane == 0 && sb) sbase = atomicAdd(&s_nsing, (u32)__popc(sb));
+            sbase = __shfl_sync(0xffffffffu, sbase, 0);
+            if (member) {
+                const u32 p = start + mynew, h2 = start + myhead;
+                a.sa[p] = g;
+                a.head[p] = h2;
+                a.rank2[g] = h2;
+                if (alone) s_sing[sbase + __popc(sb & ltmask)] = g;
+            }
+        } else { // several suffixes per lane; suffixes and their ranks parked in scratch at the group's places
+            for (u32 t = lane; t < size; t += 32) {
+                const u32 g = a.sa[start + t];
+                const u32 k = seq_of(a.v, g);
+                const u32 off = LDG(a.v.seq_off + k), len = LDG(a.v.seq_off + k + 1) - off;
+                u32 hh = a.h;
+                if (hh >= len) hh %= len;
+                u32 q1 = g - off + hh; if (q1 >= len) q1 -= len;
+                u32 q2 = q1 + hh; if (q2 >= len) q2 -= len;
+                u32 q3 = q2 + hh; if (q3 >= len) q3 -= len;
+                a.gs[start + t] = g;
+                a.ka[start + t] = LDG(a.rank + off + q1);
+                a.kb[start + t] = a.nkeys == 3 ? LDG(a.rank + off + q2) : 0u;
+                a.kc[start + t] = a.nkeys == 3 ? LDG(a.rank + off + q3) : 0u;
+            }
+            __syncwarp();
+            u32 placed = 0;
+            while (placed < size) {
+                u32 ma = 0xFFFFFFFFu, mb = 0xFFFFFFFFu, mc = 0xFFFFFFFFu;
+                for (u32 t = lane; t < size; t += 32) { u32 w = a.ka[start + t]; ma = w < ma ? w : ma; } // placed ones are all ones
+                ma = __reduce_min_sync(0xffffffffu, ma);
+                for (u32 t = lane; t < size; t += 32)
+                    if (a.ka[start + t] == ma) { u32 y = a.kb[start + t]; mb = y < mb ? y : mb; }
+                mb = __reduce_min_sync(0xffffffffu, mb);
+                for (u32 t = lane; t < size; t += 32)
+                    if (a.ka[start + t] == ma && a.kb[start + t] == mb) { u32 y = a.kc[start + t]; mc = y < mc ? y : mc; }
+                mc = __reduce_min_sync(0xffffffffu, mc);
+                u32 cnt = 0;
+                for (u32 t0 = 0; t0 < size; t0 += 32) { // how many share the smallest triple
+                    const u32 t = t0 + lane;
+                    const bool eq = t < size && a.ka[start + t] == ma && a.kb[start + t] == mb && a.kc[start + t] == mc;
+                    cnt += __popc(__ballot_sync(0xffffffffu, eq));
+                }
+                u32 sbase = 0; // this subgroup's singleton (if it is one) or group goes straight to the global lists
+                if (lane == 0) {
+                    if (cnt == 1) sbase = atomicAdd(a.n_singles, 1u);
+                    else { a.next[atomicAdd(a.n_next, 1u)] = ((u64)(start + placed) << 32) | cnt; widest = cnt > widest ? cnt : widest; }
+                }
+                sbase = __shfl_sync(0xffffffffu, sbase, 0);
+                u32 seen = 0;
+                for (u32 t0 = 0; t0 < size; t0 += 32) {
+                    const u32 t = t0 + lane;
+                    const bool eq = t < size && a.ka[start + t] == ma && a.kb[start + t] == mb && a.kc[start + t] == mc;
+                    const unsigned b = __ballot_sync(0xffffffffu, eq);
+                    if (eq) {
+                        const u32 p = start + placed + seen + __popc(b & ltmask), h2 = start + placed;
+                        const u32 g = a.gs[start + t];
+                        a.sa[p] = g;
+                        a.head[p] = h2;
+                        a.rank2[g] = h2;
+                        a.ka[start + t] = 0xFFFFFFFFu;
+                        if (cnt == 1) a.singles[sbase] = g;
+                    }
+                    seen += __popc(b);
+                }
+                placed += cnt;
+            }
+        }
+    }
+    widest = __reduce_max_sync(0xffffffffu, widest);
+    if (lane == 0) {
+        if (widest > 1) atomicMax(&s_maxg, widest);
+        if (staged) atomicAdd(&s_staged, staged);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s_base_new = s_nnew ? atomicAdd(a.n_next, s_nnew) : 0u;
+        s_base_sing = s_nsing ? atomicAdd(a.n_singles, s_nsing) : 0u;
+        atomicMax(a.maxgroup, s_maxg);
+        atomicAdd(a.staged, s_staged);
+    }
+    __syncthreads();
+    for (u32 i = tid; i < s_nnew; i += 256) a.next[s_base_new + i] = s_new[i];
+    for (u32 i = tid; i < s_nsing; i += 256) a.singles[s_base_sing + i] = s_sing[i];
+}
+static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
+    if (a.nlist == 0) return;
+    PROF_BEGIN(ex, "k_refine_g", 0.0);
+    k_refine_g<<<(a.nlist + RG_GROUPS - 1) / RG_GROUPS, 256, 0, ex.stream>>>(a);
     PROF_END(ex);
     ex.launches++;
 }

@@ -60,14 +60,17 @@ def test_emu_both_round_paths(emu_finder):
         emu_finder.debug_rounds(1)
         res_g = emu_finder.find_rotations_batch(sets)
         assert emu_finder.debug_rounds()[0] == 0
+        emu_finder.debug_rounds(3)
+        res_q = emu_finder.find_rotations_batch(sets)
         emu_finder.debug_rounds(2)
         res_d = emu_finder.find_rotations_batch(sets)
         emu_finder.debug_rounds(0)
         res_t = emu_finder.find_rotations_batch(sets)
     finally:
         emu_finder.debug_rounds(0)
-    for i, (a, b, d, s) in enumerate(zip(res_t, res_g, res_d, sets)):
+    for i, (a, b, d, q, s) in enumerate(zip(res_t, res_g, res_d, res_q, sets)):
         o = oracle_run(s)
-        compare_with_oracle(a, o, s, f"tile path (quadrupling) set {i}")
+        compare_with_oracle(a, o, s, f"group-list path set {i}")
+        compare_with_oracle(q, o, s, f"tile path (quadrupling) set {i}")
         compare_with_oracle(d, o, s, f"tile path (doubling) set {i}")
         compare_with_oracle(b, o, s, f"device-wide path set {i}")
