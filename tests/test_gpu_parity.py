@@ -184,3 +184,38 @@ def test_gpu_upload_from_page_locked_buffer(gpu_finder):
         gpu_finder.unpin(h)
     for a, b in zip(r0, r1):
         assert a.status == b.status and np.array_equal(a.rotations, b.rotations) and np.array_equal(a.positions, b.positions)
+
+
+def test_gpu_many_tiny_sets(gpu_finder):
+    """thousands of sets in one batch (per-set tables, segmented first sort, one chain CTA per set)"""
+    rng = random.Random(12)
+    sets = []
+    for _ in range(3000):
+        n = rng.randint(30, 90)
+        base = [rng.choice("ACGT") for _ in range(n)]
+        seqs = []
+        for _ in range(rng.randint(2, 4)):
+            s = [c if rng.random() > 0.03 else rng.choice("ACGT") for c in base]
+            r = rng.randrange(n)
+            seqs.append("".join(s[r:] + s[:r]).encode())
+        from common import drop_rotation_duplicates
+        seqs = drop_rotation_duplicates(seqs)
+        if len(seqs) >= 2:
+            sets.append(seqs)
+    res = gpu_finder.find_rotations_batch(sets)
+    assert len(res) == len(sets)
+    for i in range(0, len(sets), 7):
+        compare_with_oracle(res[i], oracle_run(sets[i]), sets[i], f"tiny set {i}")
+
+
+def test_gpu_large_batch_of_config3_sets(gpu_finder):
+    """BASELINE configs[3] at full set size, 160 sets (85 M bases) in one batch: every set answered, the
+    block properties hold on a sample, three sets checked against the oracle"""
+    batch = workload_batch("sets32", 160, seed=2026)
+    res = gpu_finder.find_rotations_batch(batch)
+    assert len(res) == 160 and all(r.status == 0 for r in res)
+    sets = batch_sets(batch)
+    for i in range(0, 160, 16):
+        check_block_properties(sets[i], res[i])
+    for i in (0, 77, 159):
+        compare_with_oracle(res[i], oracle_run(sets[i]), sets[i], f"set {i}")
