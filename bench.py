@@ -276,6 +276,9 @@ def main():
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
         tot = sum(r[2] for r in rows)
         rows.sort(key=lambda r: -r[2])
+        if os.environ.get("CSA_BENCH_ALL_KERNELS"):
+            for name, n, ms, by in rows:
+                print("  %-18s n=%-4d %8.3f ms %5.1f%% %8.1f GB/s" % (name, n, ms, 100 * ms / tot, by / ms / 1e6 if ms > 0 else 0), file=sys.stderr)
         for name, n, ms, by in rows[:8]:
             kernels.append({"kernel": name, "launches": n, "ms": round(ms, 3), "share": round(ms / tot, 4),
                             "algorithmic_GBps": round(by / ms / 1e6, 1) if ms > 0 else None})

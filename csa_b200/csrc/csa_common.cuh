@@ -112,8 +112,10 @@ struct Exec {
 #define PROF_BEGIN(ex, nm, by) do { (void)(ex); } while (0)
 #define PROF_END(ex) do { (void)(ex); } while (0)
 #else
+static inline bool csa_trace_on() { static int on = -1; if (on < 0) on = getenv("CSA_GPU_TRACE") ? 1 : 0; return on == 1; }
 #define PROF_BEGIN(ex, nm, by)                                                    \
     do {                                                                          \
+        if (csa_trace_on()) { cudaStreamSynchronize((ex).stream); fprintf(stderr, "[csa] %s\n", (nm)); fflush(stderr); } \
         if ((ex).prof) {                                                          \
             ProfRec r__;                                                          \
             r__.name = (nm); r__.bytes = (double)(by);                            \

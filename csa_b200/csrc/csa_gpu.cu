@@ -48,7 +48,10 @@ struct csa_gpu_ctx {
     DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, dbl_off, z0;
     DevMem rs_start, rs_count, rs_cbase, rs_stride;
     u32 rs_nblocks = 0;
-    DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, counter, tiles;
+    DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, t5, counter, tiles;
+    u32 batch_nmin = 0;
+    int lcp_state = 0;          // after the suffix array stage: 0 nothing known, 1 every LCP known, 2 all but the LCP_UNKNOWN places
+    int ws_runs = 0, ws_force = 0; double ws_pairs = 0; u32 ws_depth_cap = WS_DEPTH_CAP; u32 ws_left[6] = {0, 0, 0, 0, 0, 0};
     double lcp_mean_sample = 0;
     int force_kasai = 0;
     int rounds_list = 0, round_mode = 0;
@@ -128,7 +131,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
                      &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
-                     &c->t2, &c->t3, &c->t4, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
+                     &c->t2, &c->t3, &c->t4, &c->t5, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
                      &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
@@ -206,6 +209,7 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     }
     c->h_seq_off[M] = (u32)tot; c->h_dbl_off[M] = dbl;
     c->h_set_seq0[nsets] = (u32)M; c->h_set_base0[nsets] = (u32)tot; c->h_z0[nsets] = z;
+    c->batch_nmin = *std::min_element(c->h_set_nmin.begin(), c->h_set_nmin.end());
     c->N = (u32)tot; c->N0 = z; c->nmax = nmax; c->n0max = n0max; c->mmax = mmax; c->TW = dbl / 32 + 2;
     u32 N = c->N;
     // stage the letters in pinned memory -- unless the caller's buffer is one contiguous, page-locked
@@ -329,15 +333,17 @@ static int sort_pairs(csa_gpu_ctx *c, long long n, int begin_bit, int end_bit) {
 }
 
 // head[]/rank[] from the sorted keys in keysA (device-wide path)
+// (first sort: lcp != nullptr also gives every border its LCP, read off the keys; rank == nullptr: heads only)
 static int heads_and_ranks(csa_gpu_ctx *c, u32 *head, u32 *rank, u32 *counter, u32 *ngroups, bool keys32 = false,
-                           bool fix_set_starts = false) {
+                           bool fix_set_starts = false, u32 *lcp = nullptr, int letters = 0, int lbits = 0) {
     Exec &ex = c->ex;
     u32 N = c->N;
     TRY(dev_zero(ex, counter, sizeof(u32)));
-    { FlagArgs a{P<u64>(c->keysA), keys32 ? P<u32>(c->keysA) : nullptr, head, counter}; launch_flag(ex, N, a); }
-    if (fix_set_starts) { SetStartArgs a{view_of(c), head, counter}; launch_setstart(ex, c->nsets, a); }
+    { FlagArgs a{P<u64>(c->keysA), keys32 ? P<u32>(c->keysA) : nullptr, head, counter, lcp, letters, lbits,
+                 P<u32>(c->valsA), P<u32>(c->seqof), P<u32>(c->seq_off), c->batch_nmin < (u32)letters ? 1 : 0}; launch_flag(ex, N, a); }
+    if (fix_set_starts) { SetStartArgs a{view_of(c), head, counter, lcp}; launch_setstart(ex, c->nsets, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, head, head, N)));
-    { SetRankArgs a{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, a); }
+    if (rank) { SetRankArgs a{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, a); }
     return read_u32(c, counter, ngroups);
 }
 
@@ -368,16 +374,35 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
     int nbits = bits_for((u64)N - 1);
     u64 sorted_len = (u64)letters;
     u32 ngroups = 0;
-    TRY(heads_and_ranks(c, head, rank, counter, &ngroups, !any_other, true));
+    // word sort (k_wsort) first; it leaves what it cannot finish (sets of very short sequences, long repeats)
+    // It compares every pair of suffixes of a group, so it is the choice when groups are small (a handful of
+    // related genomes per set): under WS_PAIRS_PER_SUFFIX pairs per suffix of the batch.  Larger groups (dozens of
+    // near-identical sequences) are cheaper by rank doubling, which never reads a letter twice.
+    bool words = c->round_mode == 0 || c->round_mode == 4;
+    u32 *lcp = P<u32>(c->t5);
+    c->lcp_state = 0;
+    c->ws_runs = 0;
+    if (words) TRY(dev_fill_ff(ex, lcp, sizeof(u32) * (size_t)N));
+    TRY(heads_and_ranks(c, head, nullptr, counter, &ngroups, !any_other, true, words ? lcp : nullptr, letters, lbits));
     c->rounds_tiled = c->rounds_global = c->rounds_quad = c->rounds_list = 0;
+    u32 maxg = 0;
+    if (ngroups != N) {
+        unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs = 0;
+        TRY(dev_zero(ex, counter + 2, sizeof(u32)));
+        TRY(dev_zero(ex, pairs, sizeof(*pairs)));
+        { MaxGroupArgs a{head, counter + 2, N, pairs}; launch_maxgroup(ex, N, a); }
+        TRY(read_u32(c, counter + 2, &maxg));
+        TRY(d2h(ex, &hpairs, pairs, sizeof(hpairs)));
+        c->ws_pairs = (double)hpairs;
+        if (c->round_mode == 0 && !c->ws_force && (double)hpairs > WS_PAIRS_PER_SUFFIX * (double)N) words = false;
+    }
+    if (!words) { SetRankArgs r{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, r); }
     // counter[0] groups, [1] a tile would overflow, [2] largest group
     auto largest_group = [&](u32 *out) -> int {
         TRY(dev_zero(ex, counter + 2, sizeof(u32)));
-        { MaxGroupArgs a{head, counter + 2, N}; launch_maxgroup(ex, N, a); }
+        { MaxGroupArgs a{head, counter + 2, N, nullptr}; launch_maxgroup(ex, N, a); }
         return read_u32(c, counter + 2, out);
     };
-    u32 maxg = 0;
-    if (ngroups != N) TRY(largest_group(&maxg));
     // gencycsuffixtrees.c compares rotations letter by letter; two periodic strings that agree on
     // n_a+n_b letters agree for ever, so 2*nmax sorted letters settle every comparison
     // group lists (see k_refine_g): two lists of (start:size), two of fresh singletons, ping-ponged.
@@ -392,12 +417,46 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
         nsingles = 0;
         return 0;
     };
+    if (words) {
+        c->lcp_state = 1;
+        if (ngroups != N) {
+            u32 *res = counter + 16;
+            const u32 init[6] = {0u, 0u, 0xFFFFFFFFu, 0u, 0u, 0u};
+            TRY(h2d(ex, res, init, sizeof(init)));
+            WSortArgs a{v, P<u32>(c->valsA), head, lcp, N, (u32)letters, c->ws_depth_cap, (int)any_other, glist[0], glist[1], 0u, res};
+            launch_wsort(ex, a);
+            TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
+            const double warp_handled = c->ws_left[4];
+            if (c->ws_left[5]) { // groups that did not fit a warp's window: one CTA each
+                a.nbig = c->ws_left[5];
+                launch_wsort_big(ex, a);
+                TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
+#ifndef CSA_EMU
+                if (ex.prof && !ex.prof->recs.empty()) ex.prof->recs.back().bytes = 8.0 * a.nbig + 16.0 * (c->ws_left[4] - warp_handled);
+#endif
+            }
+#ifndef CSA_EMU
+            // every suffix's head in; per suffix of a group: sa in, sa + head + lcp out
+            if (ex.prof) for (auto &r : ex.prof->recs) if (!strcmp(r.name, "k_wsort")) r.bytes = 4.0 * N + 16.0 * warp_handled;
+#endif
+            c->ws_runs = 1;
+            if (c->ws_left[0] == 0) ngroups = N;
+            else { // some groups run deeper than the walk went (or were too long for a warp): doubling rounds from there
+                { SetRankArgs r{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, r); }
+                TRY(d2d(ex, rank2, rank, sizeof(u32) * (size_t)N));
+                nlist = c->ws_left[0]; active_est = c->ws_left[1]; sorted_len = c->ws_left[2]; maxg = c->ws_left[3];
+                ngroups = N - active_est + nlist;
+                list_valid = true;
+                c->lcp_state = active_est <= N / 8 ? 2 : 0;
+            }
+        }
+    }
     while (ngroups != N && sorted_len < 2ull * c->nmax) {
         // lists pay off once most suffixes stand alone; while nearly all still share a group the tile
         // rounds stream them at the same cost without the list upkeep
         // (and while the groups are not tiny: one warp per group wastes its lanes on pairs and triples)
         const u32 sharing_groups = ngroups > N - active_est ? ngroups - (N - active_est) : 1;
-        const bool want_list = c->round_mode == 0 && maxg <= RF_QUAD_GROUP &&
+        const bool want_list = (c->round_mode == 0 || c->round_mode >= 4) && maxg <= RF_QUAD_GROUP &&
                                (list_valid || (active_est < N / 2 && active_est / sharing_groups >= 6));
         if (want_list) {
             if (!list_valid) {
@@ -467,7 +526,7 @@ static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
     u32 N = c->N;
     int nsets = c->nsets;
-    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t2), *nxt = P<u32>(c->t0), *R = P<u32>(c->t1);
+    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t5), *nxt = P<u32>(c->t0), *R = P<u32>(c->t1);
     TRY(dev_zero(ex, c->firstmax.p, sizeof(u32) * nsets));
     { ColorKeyArgs a{v, sa, P<u64>(c->keysA), P<u32>(c->valsA)}; launch_colorkey(ex, N, a); }
     TRY(sort_pairs(c, N, 0, bits_for((u64)c->mmax - 1)));
@@ -510,7 +569,7 @@ static int stage_stats(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
     u32 N = c->N;
     int nsets = c->nsets;
-    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t2), *R = P<u32>(c->t1), *dv = P<u32>(c->t4), *prevcl = P<u32>(c->t0);
+    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t5), *R = P<u32>(c->t1), *dv = P<u32>(c->t4), *prevcl = P<u32>(c->t0);
     int mbits = bits_for((u64)c->mmax - 1);
     TRY(dev_zero(ex, c->set_collected.p, sizeof(u32) * nsets));
     TRY(dev_zero(ex, c->set_suffixfree.p, sizeof(u32) * nsets));
@@ -529,7 +588,7 @@ static int stage_stats(csa_gpu_ctx *c, const BatchView &v) {
 static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
     u32 N = c->N, N0 = c->N0, B = c->B;
-    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t2), *flag0 = P<u32>(c->t0), *idx0 = P<u32>(c->t3);
+    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t5), *flag0 = P<u32>(c->t0), *idx0 = P<u32>(c->t3);
     size_t n1 = sizeof(u32) * (size_t)N0, n2 = 2 * n1;
     DevMem *one[] = {&c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv, &c->pse};
     for (DevMem *m : one) TRY(dev_alloc(*m, n1));
@@ -652,8 +711,8 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
     size_t n4 = sizeof(u32) * (size_t)N;
     TRY(dev_alloc(c->keysA, 2 * n4)); TRY(dev_alloc(c->keysB, 2 * n4));
     TRY(dev_alloc(c->valsA, n4)); TRY(dev_alloc(c->valsB, n4)); TRY(dev_alloc(c->sa, n4));
-    TRY(dev_alloc(c->t0, n4)); TRY(dev_alloc(c->t1, n4)); TRY(dev_alloc(c->t2, n4)); TRY(dev_alloc(c->t3, n4)); TRY(dev_alloc(c->t4, n4));
-    TRY(dev_alloc(c->counter, 64));
+    TRY(dev_alloc(c->t0, n4)); TRY(dev_alloc(c->t1, n4)); TRY(dev_alloc(c->t2, n4)); TRY(dev_alloc(c->t3, n4)); TRY(dev_alloc(c->t4, n4)); TRY(dev_alloc(c->t5, n4));
+    TRY(dev_alloc(c->counter, 256));
     DevMem *perset[] = {&c->set_nblocks, &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax,
                         &c->set_collected, &c->set_suffixfree};
     for (DevMem *m : perset) TRY(dev_alloc(*m, sizeof(u32) * (nsets + 1)));
@@ -667,7 +726,10 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
     { PackArgs a{v}; launch_pack(ex, (long long)c->TW, a); }
     TRY(stage_suffix_array(c, v));
     mark(c, 1);
-    {   // how long are the matches?  a sample of pairs decides between the two LCP kernels
+    if (c->lcp_state == 2) { // the word sort gave all but the groups the doubling rounds finished
+        LcpFixArgs a{v, P<u32>(c->sa), P<u32>(c->t5), any_other};
+        launch_lcpfix(ex, N, a);
+    } else if (c->lcp_state == 0) {   // how long are the matches?  a sample of pairs decides between the two LCP kernels
         const u32 nsample = 4096, stride = N / nsample + 1;
         unsigned long long *sum = (unsigned long long *)(P<u32>(c->counter) + 10), hsum = 0;
         TRY(dev_zero(ex, sum, sizeof(*sum)));
@@ -676,11 +738,11 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
         const double mean = (double)hsum / (double)((N + stride - 1) / stride);
         c->lcp_mean_sample = mean;
         if (mean < 96.0 && !c->force_kasai) {
-            LcpDirectArgs a{v, P<u32>(c->sa), P<u32>(c->t2), any_other, 1, nullptr};
+            LcpDirectArgs a{v, P<u32>(c->sa), P<u32>(c->t5), any_other, 1, nullptr};
             launch_lcpdirect(ex, N, a);
         } else {
             { IsaArgs a{P<u32>(c->sa), P<u32>(c->t1)}; launch_isa(ex, N, a); }
-            { LcpArgs a{v, P<u32>(c->sa), P<u32>(c->t1), P<u32>(c->t2), any_other}; launch_lcp(ex, ((long long)N + LCP_CHUNK - 1) / LCP_CHUNK, a); }
+            { LcpArgs a{v, P<u32>(c->sa), P<u32>(c->t1), P<u32>(c->t5), any_other}; launch_lcp(ex, ((long long)N + LCP_CHUNK - 1) / LCP_CHUNK, a); }
         }
     }
     mark(c, 2);
@@ -728,13 +790,17 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
 // rounds[0], rounds[1] = rounds of the last run that took the tile path / the device-wide path
 extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds[2]) {
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
-    // force_global: 0 free choice (group lists while groups are small), 1 device-wide rounds only, 2 tile rounds
-    // with doubling only (and the text-order LCP kernel), 3 tile rounds, quadrupling allowed
+    // force_global: 0 free choice (word sort, then group lists while groups are small), 1 device-wide rounds only,
+    // 2 tile rounds with doubling only (and the text-order LCP kernel), 3 tile rounds, quadrupling allowed,
+    // 4 word sort stopped after two words (the rest by doubling rounds), 5 free choice without the word sort
     if (force_global >= 0) {
         c->round_mode = force_global;
+        c->ws_depth_cap = force_global == 4 ? 80u : WS_DEPTH_CAP;
+        c->ws_force = force_global == 6; // 6: word sort whatever the groups look like
+        if (force_global == 6) c->round_mode = 0;
         c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; c->force_kasai = force_global == 2;
     }
-    if (rounds) { rounds[0] = c->rounds_tiled + c->rounds_quad + c->rounds_list; rounds[1] = c->rounds_global; }
+    if (rounds) { rounds[0] = c->rounds_tiled + c->rounds_quad + c->rounds_list + c->ws_runs; rounds[1] = c->rounds_global; }
     return CSA_GPU_OK;
 }
 
@@ -833,7 +899,7 @@ extern "C" int csa_gpu_batch_suffix_array(csa_gpu_ctx *c, unsigned *sa, int *lcp
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
     if (!c->ran) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_suffix_array before csa_gpu_batch_run");
     if (sa) TRY(d2h(c->ex, sa, c->sa.p, sizeof(u32) * (size_t)c->N));
-    if (lcp) TRY(d2h(c->ex, lcp, c->t2.p, sizeof(u32) * (size_t)c->N));
+    if (lcp) TRY(d2h(c->ex, lcp, c->t5.p, sizeof(u32) * (size_t)c->N));
     return CSA_GPU_OK;
 }
 

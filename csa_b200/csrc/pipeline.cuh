@@ -137,14 +137,31 @@ HD void initkey_body(long long i, const InitKeyArgs &a) {
 MAP_KERNEL(initkey, InitKeyArgs, 21)
 
 // head[i] = i where a new group of equal keys starts, else 0 (max-scanned afterwards)
-struct FlagArgs { const u64 *keys; const u32 *keys32; u32 *head; u32 *ngroups; };
+// With lcp != nullptr (first sort only) a border also gets its LCP: the letters the two keys share.
+struct FlagArgs { const u64 *keys; const u32 *keys32; u32 *head; u32 *ngroups; u32 *lcp; int letters; int lbits;
+                  const u32 *sa; const u32 *seqof; const u32 *seq_off; int clamp; };
 HD bool flag_differs(const FlagArgs &a, long long i) {
     return a.keys32 ? a.keys32[i] != a.keys32[i - 1] : a.keys[i] != a.keys[i - 1];
+}
+HD void flag_lcp(const FlagArgs &a, long long i) { // keys differ (or i == 0): first letter sits in the top field
+    u32 c = 0;
+    if (i > 0) {
+        const u64 d = a.keys32 ? (u64)(a.keys32[i] ^ a.keys32[i - 1]) : (a.keys[i] ^ a.keys[i - 1]);
+        c = (u32)(CSA_CLZLL(d) - (64 - a.letters * a.lbits)) / (u32)a.lbits;
+        if (a.clamp) { // a sequence shorter than the key: never more than the shorter rotation (gencycsuffixtrees.c:500)
+            const u32 ka = a.seqof[a.sa[i - 1]], kb = a.seqof[a.sa[i]];
+            const u32 na = a.seq_off[ka + 1] - a.seq_off[ka], nb = a.seq_off[kb + 1] - a.seq_off[kb];
+            const u32 cap = na < nb ? na : nb;
+            if (c > cap) c = cap;
+        }
+    }
+    a.lcp[i] = c;
 }
 #ifdef CSA_EMU
 HD void flag_body(long long i, const FlagArgs &a) {
     bool f = (i == 0) || flag_differs(a, i);
     a.head[i] = f ? (u32)i : 0u;
+    if (f && a.lcp) flag_lcp(a, i);
     COUNT_IF(a.ngroups, f);
 }
 MAP_KERNEL(flag, FlagArgs, 12)
@@ -156,6 +173,7 @@ __global__ void __launch_bounds__(256) k_flag(long long n, FlagArgs a) {
     if (i < n) {
         f = (i == 0) || flag_differs(a, i);
         a.head[i] = f ? (u32)i : 0u;
+        if (f && a.lcp) flag_lcp(a, i);
     }
     int c = __syncthreads_count(f);
     if (threadIdx.x == 0 && c) atomicAdd(a.ngroups, (u32)c);
@@ -171,10 +189,11 @@ static inline void launch_flag(Exec &ex, long long n, FlagArgs a) {
 
 // the first suffix of a set starts a group even when its key equals the last key of the set before
 // (segmented first sort: the set number is not part of the key)
-struct SetStartArgs { BatchView v; u32 *head; u32 *ngroups; };
+struct SetStartArgs { BatchView v; u32 *head; u32 *ngroups; u32 *lcp; };
 HD void setstart_body(long long s, const SetStartArgs &a) {
     u32 pos = a.v.set_base0[s];
     if (pos != 0 && a.head[pos] != pos) { a.head[pos] = pos; ATOMIC_ADD(a.ngroups, 1u); }
+    if (a.lcp) a.lcp[pos] = 0; // nothing in common with another set
 }
 MAP_KERNEL(setstart, SetStartArgs, 8)
 
@@ -1113,27 +1132,37 @@ HD void tile_body(long long t, const TileArgs &a) {
 MAP_KERNEL(tile, TileArgs, 8)
 
 // largest group of equal h-prefixes: the last suffix of a group is as far from its head as the group is long
-struct MaxGroupArgs { const u32 *head; u32 *maxgroup; u32 N; };
+// (pairs != nullptr: also the number of pairs of suffixes that share a group -- what the word sort would compare)
+struct MaxGroupArgs { const u32 *head; u32 *maxgroup; u32 N; unsigned long long *pairs; };
 #ifdef CSA_EMU
 HD void maxgroup_body(long long i, const MaxGroupArgs &a) {
     if ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1) {
         u32 sz = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
         if (sz > *a.maxgroup) *a.maxgroup = sz;
+        if (a.pairs) *a.pairs += (unsigned long long)sz * (sz - 1) / 2;
     }
 }
 MAP_KERNEL(maxgroup, MaxGroupArgs, 4)
 #else
 __global__ void __launch_bounds__(256) k_maxgroup(long long n, MaxGroupArgs a) {
     __shared__ u32 s_max;
-    if (threadIdx.x == 0) s_max = 0;
+    __shared__ unsigned long long s_pairs;
+    if (threadIdx.x == 0) { s_max = 0; s_pairs = 0; }
     __syncthreads();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     u32 sz = 0;
     if (i < n && ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1)) sz = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
+    unsigned long long pr = sz > 1 ? (unsigned long long)sz * (sz - 1) / 2 : 0ull;
+    if (a.pairs) { // one atomic per CTA: same-address atomics serialise in L2
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, d);
+        if ((threadIdx.x & 31) == 0 && pr) atomicAdd(&s_pairs, pr);
+    }
     sz = __reduce_max_sync(0xffffffffu, sz);
     if ((threadIdx.x & 31) == 0 && sz) atomicMax(&s_max, sz);
     __syncthreads();
     if (threadIdx.x == 0 && s_max) atomicMax(a.maxgroup, s_max);
+    if (threadIdx.x == 0 && a.pairs && s_pairs) atomicAdd(a.pairs, s_pairs);
 }
 static inline void launch_maxgroup(Exec &ex, long long n, MaxGroupArgs a) {
     if (n <= 0) return;
@@ -2010,3 +2039,425 @@ static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
     ex.launches++;
 }
 #endif
+
+// ---- stage 1+2 fused, word sort: groups of the first sort ordered straight from the packed text -----
+// After the first sort every group holds the rotations that share their first L0 letters -- in a set of
+// related genomes mostly the m homologous copies of one place.  Prefix doubling would now shuffle RANKS
+// through HBM round after round.  The packed, doubled text of a whole batch, however, is a few tens of MB
+// and lives in the 126 MB L2, so a team of threads can simply read on: it takes a chunk of the suffix
+// array and, 32 letters (one u64 per suffix) at a time, splits every group by the next word until each
+// suffix stands alone or the depth limit is reached.  A split is a three-way partition around the word
+// of the group's first suffix (smaller | equal | larger, stable); the places come from warp ballots and
+// popcounts, not from comparisons between suffixes, and the partition is repeated at the same depth until
+// no group holds two different words.  The place where two neighbours part IS their LCP, so the LCP
+// array falls out of the same pass (gencycsuffixtrees.c:500: never more than the shorter rotation -- the
+// walk stops below the shortest sequence of the set; deeper groups are left to the doubling rounds).
+//   k_wsort     one warp per chunk: the groups that start inside WS_NOM consecutive places (<= 128 suffixes)
+//   k_wsort_big one CTA per group that does not fit a warp's window (<= 1024 suffixes)
+// HBM traffic: head 4 B per suffix in; sa 4 B in, sa + head + lcp 12 B out per suffix of a group.
+#define WS_NOM 32    // SA places whose groups one warp takes
+#define WS_CAP 128   // suffixes a warp can hold
+#define WS_T 4
+#define WS_WARPS 8   // warps (= chunks) per CTA of k_wsort
+#define WS_BIG_WARPS 8
+#define WS_BIG_CAP (32 * WS_BIG_WARPS * WS_T)
+#define WS_DEPTH_CAP 4096u
+#define WS_PAIRS_PER_SUFFIX 3.0 // the word sort is chosen when the groups of the first sort hold fewer pairs than this per suffix
+#define LCP_UNKNOWN 0xFFFFFFFFu
+
+struct WSortArgs {
+    BatchView v; u32 *sa; u32 *head; u32 *lcp; u32 N; u32 L0; u32 depth_cap; int masks;
+    u64 *left; // groups still to be ordered (start : size), for the doubling rounds
+    u64 *big;  // groups too long for a warp's window (start : size), for k_wsort_big
+    u32 nbig;  // (k_wsort_big) entries of big
+    u32 *res;  // [0] groups left, [1] suffixes in them, [2] fewest letters a left group shares, [3] largest left group,
+               // [4] suffixes handled, [5] entries of big
+};
+
+// 32 letters as a number that compares like the letters do: first letter in the top bits
+HD u64 lexkey2(u64 w) {
+#if defined(__CUDA_ARCH__)
+    u64 r = __brevll(w);
+#else
+    u64 r = w;
+    r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+    r = ((r >> 2) & 0x3333333333333333ull) | ((r & 0x3333333333333333ull) << 2);
+    r = ((r >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((r & 0x0F0F0F0F0F0F0F0Full) << 4);
+    r = __builtin_bswap64(r);
+#endif
+    return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1); // bit pairs back in order
+}
+HD u32 lexmask(u32 w) {
+#if defined(__CUDA_ARCH__)
+    return __brev(w);
+#else
+    u32 r = w;
+    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+    r = ((r >> 2) & 0x33333333u) | ((r & 0x33333333u) << 2);
+    r = ((r >> 4) & 0x0F0F0F0Fu) | ((r & 0x0F0F0F0Fu) << 4);
+    return __builtin_bswap32(r);
+#endif
+}
+// (K, M): 2-bit letters and the "not ACGT" bits of one 32-letter word, both first letter on top; the
+// fifth letter (code 4) is the largest and its 2-bit field is 0
+HD bool ws_less(u64 ka, u32 ma, u64 kb, u32 mb) {
+    const u32 dm = ma ^ mb;
+    if (!dm) return ka < kb;
+    const u64 dk = ka ^ kb;
+    const int pm = CSA_CLZ(dm), pk = dk ? (CSA_CLZLL(dk) >> 1) : 32;
+    if (pk < pm) return ka < kb;
+    return (mb >> (31 - pm)) & 1u; // they part at a letter that is "other" in exactly one of them: that one is larger
+}
+HD u32 ws_common(u64 ka, u32 ma, u64 kb, u32 mb) { // letters the two words share (they differ)
+    const u64 dk = ka ^ kb;
+    const u32 dm = ma ^ mb;
+    const u32 pk = dk ? (u32)(CSA_CLZLL(dk) >> 1) : 32u, pm = dm ? (u32)CSA_CLZ(dm) : 32u;
+    return pk < pm ? pk : pm;
+}
+
+#ifdef CSA_EMU
+// one group [p, e) by the letters [L0, Lend): stable; what is still together goes to the list
+static inline void emu_wsort_group(const WSortArgs &a, u32 p, u32 e, u32 Lend) {
+    const BatchView &v = a.v;
+    struct It { u32 g; std::vector<unsigned char> s; };
+    std::vector<It> items;
+    for (u32 x = p; x < e; x++) {
+        It it{a.sa[x], {}};
+        for (u32 h = a.L0; h < Lend; h++) it.s.push_back(v.code[cyc_add(v, it.g, h)]);
+        items.push_back(std::move(it));
+    }
+    a.res[4] += (u32)items.size();
+    std::stable_sort(items.begin(), items.end(), [](const It &x, const It &y) { return x.s < y.s; });
+    u32 hd = p;
+    for (u32 x = p; x <= e; x++) {
+        const bool brk = x == e || (x > p && items[x - p - 1].s != items[x - p].s);
+        if (brk) {
+            if (x - hd >= 2) { // still together after Lend letters
+                a.left[a.res[0]++] = ((u64)hd << 32) | (x - hd);
+                a.res[1] += x - hd;
+                if (Lend < a.res[2]) a.res[2] = Lend;
+                if (x - hd > a.res[3]) a.res[3] = x - hd;
+            }
+            if (x < e) {
+                const auto &s1 = items[x - p - 1].s, &s2 = items[x - p].s;
+                u32 c = 0;
+                while (s1[c] == s2[c]) c++;
+                a.lcp[x] = a.L0 + c;
+            }
+            hd = x;
+        }
+        if (x < e) { a.sa[x] = items[x - p].g; a.head[x] = hd; }
+    }
+}
+static inline void emu_wsort_leave(const WSortArgs &a, u32 p, u32 e) {
+    a.left[a.res[0]++] = ((u64)p << 32) | (e - p);
+    a.res[1] += e - p;
+    if (a.L0 < a.res[2]) a.res[2] = a.L0;
+    if (e - p > a.res[3]) a.res[3] = e - p;
+}
+static inline u32 emu_wsort_lend(const WSortArgs &a, u32 nmin) {
+    const u32 Lmax = nmin < a.depth_cap ? nmin : a.depth_cap;
+    u32 Lend = a.L0;
+    while (Lend + 32 <= Lmax) Lend += 32;
+    return Lend;
+}
+static inline void launch_wsort(Exec &, const WSortArgs &a) {
+    const BatchView &v = a.v;
+    const u32 N = a.N;
+    auto border = [&](u64 p) { return p < N ? (a.head[p] & 0x7FFFFFFFu) == (u32)p : p == N; };
+    for (u64 r0 = 0; r0 < N; r0 += WS_NOM) {
+        // groups that start in [r0, r0+WS_NOM) and end at or before place r0 + WS_CAP - 1
+        std::vector<std::pair<u32, u32>> groups;
+        u32 nmin = 0xFFFFFFFFu;
+        for (u64 p = r0; p < r0 + WS_NOM && p < N; p++) {
+            if (!border(p)) continue;
+            u64 e = p + 1;
+            while (!border(e)) e++;
+            if (e - r0 > WS_CAP - 1) { // runs past the warp's window
+                if (e - p >= 2) a.big[a.res[5]++] = ((u64)p << 32) | (u32)(e - p);
+                break;
+            }
+            if (e - p >= 2) {
+                groups.push_back({(u32)p, (u32)e});
+                for (u64 x = p; x < e; x++) {
+                    u32 nm = v.set_nmin[v.seq_set[v.seqof[a.sa[x]]]];
+                    if (nm < nmin) nmin = nm;
+                }
+            }
+        }
+        for (auto &gr : groups) emu_wsort_group(a, gr.first, gr.second, emu_wsort_lend(a, nmin));
+    }
+}
+static inline void launch_wsort_big(Exec &, const WSortArgs &a) {
+    for (u32 i = 0; i < a.nbig; i++) {
+        const u32 p = (u32)(a.big[i] >> 32), e = p + (u32)a.big[i];
+        if (e - p > WS_BIG_CAP) { emu_wsort_leave(a, p, e); continue; }
+        const u32 nmin = a.v.set_nmin[a.v.seq_set[a.v.seqof[a.sa[p]]]];
+        emu_wsort_group(a, p, e, emu_wsort_lend(a, nmin));
+    }
+}
+#else
+HD u32 ws_next_border(u64 b0, u64 b1, u32 t) { // first border place after t (place WS_CAP always counts as one)
+    if (t < 63) {
+        const u64 m = b0 & (~0ull << (t + 1));
+        if (m) return (u32)(__ffsll((long long)m) - 1);
+        return b1 ? 64u + (u32)(__ffsll((long long)b1) - 1) : (u32)WS_CAP;
+    }
+    if (t == 63) return b1 ? 64u + (u32)(__ffsll((long long)b1) - 1) : (u32)WS_CAP;
+    const u32 tt = t - 64;
+    const u64 m = tt < 63 ? (b1 & (~0ull << (tt + 1))) : 0ull;
+    return m ? 64u + (u32)(__ffsll((long long)m) - 1) : (u32)WS_CAP;
+}
+
+// a team = 1 warp (k_wsort) or the whole CTA (k_wsort_big); place t of its chunk belongs to thread t % threads
+template <int WARPS> struct WsTeam {
+    static __device__ __forceinline__ void sync() { if (WARPS == 1) __syncwarp(); else __syncthreads(); }
+};
+template <int WARPS> struct WsSmem {
+    static constexpr int CAP = 32 * WARPS * WS_T;
+    u64 x[CAP];                 // where the suffix at place t starts in the doubled text
+    u32 g[CAP];                 // the suffix
+    u32 ct[CAP];                // low half: suffixes of its group that are smaller; high half: equal ones that stood before it
+    u32 best[CAP];              // most letters shared with a smaller one = LCP with its predecessor
+    u32 clsz[CAP];              // (by new place) suffixes that are still together there
+    unsigned short seg[CAP];    // first place of its group
+    unsigned short end[CAP];    // place after the last of its group
+};
+
+// Every pair of suffixes of a group is compared once, word by word from letter L0 on, by whichever
+// thread's list it is on (suffix i of a group of g meets i+1 .. i+(g-1)/2 round the group, so every
+// suffix brings the same number of pairs).  A thread walks its list on its own: lanes are in different
+// pairs at different depths and never wait for one another -- no ballot, no barrier until the lists are
+// done.  What a pair tells: the smaller suffix counts towards the larger one's place, and the letters they
+// share bound the larger one's LCP from below (its predecessor is the smaller suffix it shares most
+// with).  Pairs that agree up to the depth limit count as equal (place by old order; the doubling rounds
+// finish them).  On entry: x, g, seg, end set and ct = best = clsz = 0 for every place with act[j].
+template <bool MASKS, int WARPS>
+__device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, const u32 tid, const u32 base,
+                                         const bool (&act)[WS_T], const u32 Lmax) {
+    typedef WsTeam<WARPS> Team;
+    constexpr u32 TT = 32u * WARPS;
+    const u32 L0 = a.L0;
+    const u32 Lend = Lmax >= L0 ? L0 + ((Lmax - L0) & ~31u) : L0; // pairs that agree on [L0, Lend) count as equal
+    unsigned actbits = 0;
+#pragma unroll
+    for (int j = 0; j < WS_T; j++) actbits |= act[j] ? 1u << j : 0u;
+    {
+        int j = -1;
+        u32 t = 0, hs = 0, g = 0, i = 0, d = 0, nd = 0, pb = 0, L = 0;
+        u64 xa = 0, xb = 0;
+        bool busy = false;
+        for (;;) {
+            if (!busy) { // next pair of my list
+                while (d == nd) {
+                    if (++j >= WS_T) break;
+                    if (!(actbits >> j & 1u)) continue;
+                    t = tid + TT * (u32)j;
+                    hs = s.seg[t]; g = (u32)s.end[t] - hs; i = t - hs;
+                    nd = (g - 1u) / 2u + (((g & 1u) == 0u && i < g / 2u) ? 1u : 0u);
+                    d = 0;
+                    xa = s.x[t];
+                }
+                if (j >= WS_T) break;
+                d++;
+                u32 i2 = i + d;
+                if (i2 >= g) i2 -= g;
+                pb = hs + i2;
+                xb = s.x[pb];
+                L = L0;
+                busy = true;
+            }
+            // one word of the pair (t, pb)
+            if (L + 32u > Lmax) { // equal as far as the walk goes: the later one stands behind
+                atomicAdd(&s.ct[t > pb ? t : pb], 0x10000u);
+                busy = false;
+                continue;
+            }
+            const u64 wa = fetch2(a.v.p2, xa + L), wb = fetch2(a.v.p2, xb + L);
+            const u64 d2 = wa ^ wb;
+            u32 ma = 0, mb = 0, dm = 0;
+            if (MASKS) { ma = fetchm(a.v.pm, xa + L); mb = fetchm(a.v.pm, xb + L); dm = ma ^ mb; }
+            if (d2 | dm) {
+                u32 f = d2 ? (u32)ctz64(d2) >> 1 : 32u;
+                if (MASKS && dm) { const u32 fm = (u32)ctz32(dm); f = fm < f ? fm : f; }
+                const u32 ca = (MASKS && (ma >> f & 1u)) ? 4u : (u32)(wa >> (2u * f)) & 3u;
+                const u32 cb = (MASKS && (mb >> f & 1u)) ? 4u : (u32)(wb >> (2u * f)) & 3u;
+                const u32 larger = ca < cb ? pb : t;
+                atomicAdd(&s.ct[larger], 1u);
+                atomicMax(&s.best[larger], L + f);
+                busy = false;
+            } else L += 32u;
+        }
+    }
+    Team::sync();
+    // new places; suffixes that are still together leave their number at the place of their first
+    u32 np[WS_T], nh[WS_T];
+#pragma unroll
+    for (int j = 0; j < WS_T; j++) {
+        if (act[j]) {
+            const u32 t = tid + TT * j, c = s.ct[t] & 0xFFFFu, ti = s.ct[t] >> 16;
+            nh[j] = s.seg[t] + c;
+            np[j] = nh[j] + ti;
+            if (ti) atomicMax(&s.clsz[nh[j]], ti + 1u);
+        }
+    }
+    Team::sync();
+    u32 handled = 0;
+#pragma unroll
+    for (int j = 0; j < WS_T; j++) {
+        if (act[j]) {
+            const u32 t = tid + TT * j;
+            handled++;
+            a.sa[base + np[j]] = s.g[t];
+            a.head[base + np[j]] = base + nh[j];
+            if (np[j] == nh[j]) {
+                if (nh[j] != s.seg[t]) a.lcp[base + np[j]] = s.best[t]; // (the first of the old group keeps its border LCP)
+                const u32 size = s.clsz[nh[j]];
+                if (size) { // still together after Lend letters: the doubling rounds go on from there
+                    a.left[atomicAdd(a.res + 0, 1u)] = ((u64)(base + nh[j]) << 32) | size;
+                    atomicAdd(a.res + 1, size);
+                    atomicMin(a.res + 2, Lend);
+                    atomicMax(a.res + 3, size);
+                }
+            }
+        }
+    }
+    handled = __reduce_add_sync(0xffffffffu, handled);
+    if ((tid & 31u) == 0 && handled) atomicAdd(a.res + 4, handled);
+}
+
+template <bool MASKS>
+__global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
+    static_assert(WS_T == 4 && WS_CAP == 128, "border words are kept as two u64");
+    __shared__ WsSmem<1> s_all[WS_WARPS];
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u64 r0_64 = ((u64)blockIdx.x * WS_WARPS + warp) * WS_NOM;
+    if (r0_64 >= a.N) return;
+    const u32 r0 = (u32)r0_64, N = a.N;
+    WsSmem<1> &s = s_all[warp];
+    // ---- the window: heads of WS_CAP places, borders as a bit set ----
+    u32 hv[WS_T], bw[WS_T];
+#pragma unroll
+    for (int j = 0; j < WS_T; j++) {
+        const u64 p = (u64)r0 + lane + 32u * j;
+        hv[j] = p < N ? (a.head[p] & 0x7FFFFFFFu) : 0u;
+        bw[j] = __ballot_sync(0xffffffffu, p < N ? hv[j] == (u32)p : p == N);
+    }
+    if (bw[0] == 0) return; // no group starts here
+    const u32 tb = (u32)__ffs((int)bw[0]) - 1u;
+    u32 te;
+    if (bw[1]) te = 32u + (u32)__ffs((int)bw[1]) - 1u;
+    else if (bw[2]) te = 64u + (u32)__ffs((int)bw[2]) - 1u;
+    else if (bw[3]) te = 96u + (u32)__ffs((int)bw[3]) - 1u;
+    else if (N - r0 < 32u) te = N - r0; // the array ends inside the first word: that end is the last border seen
+    else { // the last group that starts here runs past the window: k_wsort_big's
+        te = 31u - (u32)__clz((int)bw[0]);
+        // its length: gallop, then bisect (head[p] == its start for every place inside it)
+        const u32 hs = r0 + te;
+        u64 lo = (u64)r0 + WS_CAP - 1, step = WS_CAP; // lo is inside the group
+        while (lo + step < N && (a.head[lo + step] & 0x7FFFFFFFu) == hs) { lo += step; step *= 2; }
+        u64 hi = lo + step < N ? lo + step : N; // first place known to be outside (or N)
+        while (hi - lo > 1) {
+            const u64 mid = (lo + hi) >> 1;
+            if ((a.head[mid] & 0x7FFFFFFFu) == hs) lo = mid; else hi = mid;
+        }
+        if (lane == 0) a.big[atomicAdd(a.res + 5, 1u)] = ((u64)hs << 32) | (u32)(hi - hs);
+    }
+    const u64 b0 = (u64)bw[0] | ((u64)bw[1] << 32), b1 = (u64)bw[2] | ((u64)bw[3] << 32);
+    // ---- the suffixes of every group of two or more ----
+    bool act[WS_T];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < WS_T; j++) {
+        const u32 t = lane + 32u * j;
+        act[j] = false;
+        if (t >= tb && t < te) {
+            const u32 hs = hv[j] - r0, he = ws_next_border(b0, b1, t);
+            act[j] = he - hs >= 2u;
+            s.seg[t] = (unsigned short)hs;
+            s.end[t] = (unsigned short)he;
+        }
+        any |= act[j];
+    }
+    if (!__any_sync(0xffffffffu, any)) return;
+    u32 nmin = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < WS_T; j++) {
+        if (act[j]) {
+            const u32 t = lane + 32u * j;
+            const u32 g = a.sa[r0 + t];
+            const u32 k = seq_of(a.v, g);
+            s.x[t] = LDG(a.v.dbl_off + k) + (g - LDG(a.v.seq_off + k));
+            s.g[t] = g;
+            s.ct[t] = 0; s.best[t] = 0; s.clsz[t] = 0;
+            const u32 nm = LDG(a.v.set_nmin + LDG(a.v.seq_set + k));
+            nmin = nm < nmin ? nm : nmin;
+        }
+    }
+    nmin = __reduce_min_sync(0xffffffffu, nmin);
+    __syncwarp();
+    ws_pairs<MASKS, 1>(a, s, lane, r0, act, nmin < a.depth_cap ? nmin : a.depth_cap);
+}
+
+template <bool MASKS>
+__global__ void __launch_bounds__(WS_BIG_WARPS * 32) k_wsort_big(WSortArgs a) {
+    __shared__ WsSmem<WS_BIG_WARPS> s;
+    const u32 tid = threadIdx.x;
+    const u64 desc = a.big[blockIdx.x];
+    const u32 start = (u32)(desc >> 32), size = (u32)desc;
+    if (size > (u32)WS_BIG_CAP) { // longer than a CTA holds: the doubling rounds order it
+        if (tid == 0) {
+            a.left[atomicAdd(a.res + 0, 1u)] = desc;
+            atomicAdd(a.res + 1, size);
+            atomicMin(a.res + 2, a.L0);
+            atomicMax(a.res + 3, size);
+        }
+        return;
+    }
+    bool act[WS_T];
+#pragma unroll
+    for (int j = 0; j < WS_T; j++) {
+        const u32 t = tid + 32u * WS_BIG_WARPS * j;
+        act[j] = t < size;
+        if (act[j]) {
+            const u32 g = a.sa[start + t];
+            const u32 k = seq_of(a.v, g);
+            s.x[t] = LDG(a.v.dbl_off + k) + (g - LDG(a.v.seq_off + k));
+            s.g[t] = g;
+            s.seg[t] = 0;
+            s.end[t] = (unsigned short)size;
+            s.ct[t] = 0; s.best[t] = 0; s.clsz[t] = 0;
+        }
+    }
+    const u32 nmin = LDG(a.v.set_nmin + LDG(a.v.seq_set + seq_of(a.v, a.sa[start]))); // a group never leaves its set
+    __syncthreads();
+    ws_pairs<MASKS, WS_BIG_WARPS>(a, s, tid, start, act, nmin < a.depth_cap ? nmin : a.depth_cap);
+}
+
+static inline void launch_wsort(Exec &ex, const WSortArgs &a) {
+    if (a.N == 0) return;
+    const u32 nwarps = (a.N + WS_NOM - 1) / WS_NOM;
+    PROF_BEGIN(ex, "k_wsort", 4.0 * a.N);
+    if (a.masks) k_wsort<true><<<(nwarps + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, ex.stream>>>(a);
+    else k_wsort<false><<<(nwarps + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
+}
+static inline void launch_wsort_big(Exec &ex, const WSortArgs &a) {
+    if (a.nbig == 0) return;
+    PROF_BEGIN(ex, "k_wsort_big", 0.0);
+    if (a.masks) k_wsort_big<true><<<a.nbig, WS_BIG_WARPS * 32, 0, ex.stream>>>(a);
+    else k_wsort_big<false><<<a.nbig, WS_BIG_WARPS * 32, 0, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
+
+// LCP of the places the word sort could not give (groups finished by the doubling rounds)
+struct LcpFixArgs { BatchView v; const u32 *sa; u32 *lcp; const u32 *any_other; };
+HD void lcpfix_body(long long i, const LcpFixArgs &a) {
+    if (a.lcp[i] != LCP_UNKNOWN) return;
+    LcpDirectArgs d{a.v, a.sa, a.lcp, a.any_other, 1, nullptr};
+    lcpdirect_body(i, d);
+}
+MAP_KERNEL(lcpfix, LcpFixArgs, 4)

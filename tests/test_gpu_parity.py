@@ -124,9 +124,11 @@ def test_gpu_tile_rounds_equal_device_wide_rounds(gpu_finder):
     try:
         for name, batch in (("sets32", workload_batch("sets32", 3, seed=3)), ("mammals", workload_batch("mammals", 4, seed=4)),
                             ("variants256", workload_batch("variants256", 1, seed=5))):
-            # 0 free choice (group lists while groups are small), 3 tile rounds with quadrupling, 2 tile rounds with
-            # doubling only (+ text-order LCP), 1 device-wide rounds only
-            for mode in (0, 3, 2, 1):
+            # 0 free choice (word sort first), 5 free choice among the doubling rounds (group lists while groups are
+            # small), 4 word sort stopped after two words + doubling, 3 tile rounds with quadrupling, 2 tile rounds
+            # with doubling only (+ text-order LCP), 1 device-wide rounds only
+            # 6 word sort whatever the groups look like (0 picks it only for small groups)
+            for mode in (0, 6, 5, 4, 3, 2, 1):
                 gpu_finder.debug_rounds(mode)
                 res = gpu_finder.find_rotations_batch(batch)
                 sa, lcp = gpu_finder.suffix_array()
@@ -137,8 +139,8 @@ def test_gpu_tile_rounds_equal_device_wide_rounds(gpu_finder):
         r0, sa0, lcp0, rounds0 = out[(name, 0)]
         assert rounds0[0] > 0
         assert out[(name, 1)][3][0] == 0 and out[(name, 1)][3][1] > 0
-        assert out[(name, 2)][3][0] >= rounds0[0]  # doubling needs at least as many rounds as quadrupling
-        for mode in (1, 2, 3):
+        assert out[(name, 2)][3][0] >= out[(name, 3)][3][0]  # doubling needs at least as many rounds as quadrupling
+        for mode in (1, 2, 3, 4, 5, 6):
             r, sa, lcp, _ = out[(name, mode)]
             assert np.array_equal(sa0, sa) and np.array_equal(lcp0, lcp), (name, mode)
             for a, b in zip(r0, r):
