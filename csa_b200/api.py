@@ -78,11 +78,21 @@ def _load(path):
     lib.csa_gpu_batch_suffix_array.argtypes = [vp, C.POINTER(C.c_uint), ip]
     lib.csa_gpu_batch_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
     lib.csa_gpu_debug_rounds.argtypes = [vp, i, ip]
+    lib.csa_gpu_shard_begin.argtypes = [vp, i, i]
+    lib.csa_gpu_shard_view.argtypes = [vp, C.POINTER(ShardInfo)]
+    lib.csa_gpu_shard_finish.argtypes = [vp, i, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
     lib.csa_gpu_profile_enable.argtypes = [vp, i]
     lib.csa_gpu_profile_count.argtypes = [vp]
     lib.csa_gpu_profile_get.argtypes = [vp, i, C.c_char_p, i, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                                         C.POINTER(C.c_double)]
     return lib
+
+
+class ShardInfo(C.Structure):
+    """csa_gpu_shard_info (include/csa_gpu.h)"""
+    _fields_ = [("sa", C.c_void_p), ("head", C.c_void_p), ("lcp", C.c_void_p), ("left", C.c_void_p),
+                ("n", C.c_ulonglong), ("bounds", C.POINTER(C.c_uint)),
+                ("nleft", C.c_uint), ("left_suffixes", C.c_uint), ("min_depth", C.c_uint), ("max_group", C.c_uint)]
 
 
 def _ip(a):
@@ -162,6 +172,18 @@ class RotationFinder:
 
     def run(self, max_interval: int = INT_MAX, flags: int = 0):
         self._check(self.lib.csa_gpu_batch_run(self.ctx, max_interval, flags))
+
+    # ---- one batch, the suffix-array stage sharded over the ranks of a job (csa_b200/shard.py drives it) ----
+    def shard_begin(self, rank: int, nranks: int):
+        self._check(self.lib.csa_gpu_shard_begin(self.ctx, rank, nranks))
+
+    def shard_view(self) -> ShardInfo:
+        v = ShardInfo()
+        self._check(self.lib.csa_gpu_shard_view(self.ctx, C.byref(v)))
+        return v
+
+    def shard_finish(self, max_interval: int, flags: int, nleft: int, left_suffixes: int, min_depth: int, max_group: int):
+        self._check(self.lib.csa_gpu_shard_finish(self.ctx, max_interval, flags, nleft, left_suffixes, min_depth, max_group))
 
     def download(self):
         b = self._batch

@@ -51,7 +51,10 @@ struct csa_gpu_ctx {
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, t5, counter, tiles;
     u32 batch_nmin = 0;
     int lcp_state = 0;          // after the suffix array stage: 0 nothing known, 1 every LCP known, 2 all but the LCP_UNKNOWN places
-    int ws_runs = 0, ws_force = 0; double ws_pairs = 0; u32 ws_depth_cap = WS_DEPTH_CAP; u32 ws_left[6] = {0, 0, 0, 0, 0, 0};
+    int ws_runs = 0, ws_force = 0; double ws_pairs = 0;
+    u32 sa_any_other = 1, sa_ngroups = 0;
+    int shard_rank = 0, shard_nranks = 1, shard_phase = 0;
+    DevMem shard_bounds; std::vector<u32> h_shard_bounds; u32 ws_depth_cap = WS_DEPTH_CAP; u32 ws_left[6] = {0, 0, 0, 0, 0, 0};
     double lcp_mean_sample = 0;
     int force_kasai = 0;
     int rounds_list = 0, round_mode = 0;
@@ -131,7 +134,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
                      &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
-                     &c->t2, &c->t3, &c->t4, &c->t5, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
+                     &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
                      &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
@@ -347,15 +350,24 @@ static int heads_and_ranks(csa_gpu_ctx *c, u32 *head, u32 *rank, u32 *counter, u
     return read_u32(c, counter, ngroups);
 }
 
-static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
+// phase 0: the whole stage.  Sharded over the ranks of a job (csa_gpu_shard_*): phase 1 = first sort (every rank
+// the same), bucket borders, word sort of this rank's bucket; phase 2 = what is left after the buckets were exchanged.
+static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0) {
     Exec &ex = c->ex;
     u32 N = c->N;
     u32 *head = P<u32>(c->t0), *rank = P<u32>(c->t1), *rank2 = P<u32>(c->t3), *counter = P<u32>(c->counter);
     u32 ntiles = (N + RF_NOMINAL - 1) / RF_NOMINAL;
     TRY(dev_alloc(c->tiles, sizeof(u32) * ((size_t)ntiles + 2)));
-    u32 any_other = 1;
-    TRY(read_u32(c, counter + 8, &any_other)); // set by k_encode: a letter outside ACGT somewhere in the batch
+    u32 any_other = c->sa_any_other;
+    if (phase != 2) TRY(read_u32(c, counter + 8, &any_other)); // set by k_encode: a letter outside ACGT somewhere in the batch
+    c->sa_any_other = any_other;
     const int letters = any_other ? CSA_K0 : 12, lbits = any_other ? CSA_LETTER_BITS : 2;
+    int nbits = bits_for((u64)N - 1);
+    u64 sorted_len = (u64)letters;
+    u32 ngroups = c->sa_ngroups, maxg = 0;
+    bool words = true;
+    u32 *lcp = P<u32>(c->t5);
+    if (phase != 2) {
     RsSeg seg{P<u32>(c->rs_start), P<u32>(c->rs_count), P<u32>(c->rs_cbase), P<u32>(c->rs_stride), c->rs_nblocks,
               P<u32>(c->set_base0), (u32)c->nsets};
     { InitKeyArgs a{v, any_other ? P<u64>(c->keysA) : nullptr, any_other ? nullptr : P<u32>(c->keysA), P<u32>(c->valsA)};
@@ -371,21 +383,17 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
         TRY(radix_sort_pairs<u32>(ex, c->ps, k, vv, ka, va, N, 0, letters * lbits, &seg));
         if (vv != P<u32>(c->valsA)) { std::swap(c->keysA, c->keysB); std::swap(c->valsA, c->valsB); }
     }
-    int nbits = bits_for((u64)N - 1);
-    u64 sorted_len = (u64)letters;
-    u32 ngroups = 0;
+    ngroups = 0;
     // word sort (k_wsort) first; it leaves what it cannot finish (sets of very short sequences, long repeats)
     // It compares every pair of suffixes of a group, so it is the choice when groups are small (a handful of
     // related genomes per set): under WS_PAIRS_PER_SUFFIX pairs per suffix of the batch.  Larger groups (dozens of
     // near-identical sequences) are cheaper by rank doubling, which never reads a letter twice.
-    bool words = c->round_mode == 0 || c->round_mode == 4;
-    u32 *lcp = P<u32>(c->t5);
+    words = phase == 1 || c->round_mode == 0 || c->round_mode == 4;
     c->lcp_state = 0;
     c->ws_runs = 0;
     if (words) TRY(dev_fill_ff(ex, lcp, sizeof(u32) * (size_t)N));
     TRY(heads_and_ranks(c, head, nullptr, counter, &ngroups, !any_other, true, words ? lcp : nullptr, letters, lbits));
     c->rounds_tiled = c->rounds_global = c->rounds_quad = c->rounds_list = 0;
-    u32 maxg = 0;
     if (ngroups != N) {
         unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs = 0;
         TRY(dev_zero(ex, counter + 2, sizeof(u32)));
@@ -394,9 +402,11 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
         TRY(read_u32(c, counter + 2, &maxg));
         TRY(d2h(ex, &hpairs, pairs, sizeof(hpairs)));
         c->ws_pairs = (double)hpairs;
-        if (c->round_mode == 0 && !c->ws_force && (double)hpairs > WS_PAIRS_PER_SUFFIX * (double)N) words = false;
+        if (phase == 0 && c->round_mode == 0 && !c->ws_force && (double)hpairs > WS_PAIRS_PER_SUFFIX * (double)N) words = false;
     }
     if (!words) { SetRankArgs r{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, r); }
+    c->sa_ngroups = ngroups;
+    } // phase != 2
     // counter[0] groups, [1] a tile would overflow, [2] largest group
     auto largest_group = [&](u32 *out) -> int {
         TRY(dev_zero(ex, counter + 2, sizeof(u32)));
@@ -419,11 +429,18 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
     };
     if (words) {
         c->lcp_state = 1;
-        if (ngroups != N) {
+        if (phase == 1) { // this rank's bucket: borders at group borders, the same on every rank
+            BoundsArgs b{head, N, (u32)c->shard_nranks, P<u32>(c->shard_bounds)};
+            launch_bounds(ex, b);
+            c->h_shard_bounds.assign(c->shard_nranks + 1, 0);
+            TRY(d2h(ex, c->h_shard_bounds.data(), c->shard_bounds.p, sizeof(u32) * (c->shard_nranks + 1)));
+        }
+        if (ngroups != N && phase != 2) {
             u32 *res = counter + 16;
             const u32 init[6] = {0u, 0u, 0xFFFFFFFFu, 0u, 0u, 0u};
             TRY(h2d(ex, res, init, sizeof(init)));
-            WSortArgs a{v, P<u32>(c->valsA), head, lcp, N, (u32)letters, c->ws_depth_cap, (int)any_other, glist[0], glist[1], 0u, res};
+            const u32 lo = phase == 1 ? c->h_shard_bounds[c->shard_rank] : 0u, hi = phase == 1 ? c->h_shard_bounds[c->shard_rank + 1] : N;
+            WSortArgs a{v, P<u32>(c->valsA), head, lcp, N, lo, hi, (u32)letters, c->ws_depth_cap, (int)any_other, glist[0], glist[1], 0u, res};
             launch_wsort(ex, a);
             TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
             const double warp_handled = c->ws_left[4];
@@ -440,6 +457,9 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v) {
             if (ex.prof) for (auto &r : ex.prof->recs) if (!strcmp(r.name, "k_wsort")) r.bytes = 4.0 * N + 16.0 * warp_handled;
 #endif
             c->ws_runs = 1;
+        }
+        if (phase == 1) return 0; // the caller exchanges the buckets and the lists of what is left, then phase 2
+        if (ngroups != N) {
             if (c->ws_left[0] == 0) ngroups = N;
             else { // some groups run deeper than the walk went (or were too long for a warp): doubling rounds from there
                 { SetRankArgs r{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, r); }
@@ -697,14 +717,15 @@ static int stage_chain(csa_gpu_ctx *c, const BatchView &v, int max_interval) {
     return 0;
 }
 
-extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flags) {
+// phase 0: the whole path; 1: up to this rank's bucket of the suffix array (csa_gpu_shard_begin); 2: the rest
+static int run_phases(csa_gpu_ctx *c, int max_interval, unsigned flags, int phase) {
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
     if (!c->uploaded) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_run before csa_gpu_batch_upload");
 #ifndef CSA_EMU
     CUDA_TRY(cudaSetDevice(c->device));
 #endif
     Exec &ex = c->ex;
-    ex.launches = 0;
+    if (phase != 2) ex.launches = 0;
     c->ran = false;
     u32 N = c->N;
     int nsets = c->nsets;
@@ -717,14 +738,19 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
                         &c->set_collected, &c->set_suffixfree};
     for (DevMem *m : perset) TRY(dev_alloc(*m, sizeof(u32) * (nsets + 1)));
     TRY(dev_alloc(c->rotations, sizeof(int) * (size_t)c->M));
+    TRY(dev_alloc(c->shard_bounds, sizeof(u32) * ((size_t)c->shard_nranks + 2)));
     BatchView v = view_of(c);
 
-    mark(c, 0);
     u32 *any_other = P<u32>(c->counter) + 8;
-    TRY(dev_zero(ex, any_other, sizeof(u32)));
-    { EncodeArgs a{v, P<unsigned char>(c->raw), any_other}; launch_encode(ex, N, a); }
-    { PackArgs a{v}; launch_pack(ex, (long long)c->TW, a); }
-    TRY(stage_suffix_array(c, v));
+    if (phase != 2) {
+        mark(c, 0);
+        TRY(dev_zero(ex, any_other, sizeof(u32)));
+        { EncodeArgs a{v, P<unsigned char>(c->raw), any_other}; launch_encode(ex, N, a); }
+        { PackArgs a{v}; launch_pack(ex, (long long)c->TW, a); }
+    }
+    TRY(stage_suffix_array(c, v, phase));
+    if (phase == 1) { c->shard_phase = 1; return exec_sync(ex); }
+    c->shard_phase = 0;
     mark(c, 1);
     if (c->lcp_state == 2) { // the word sort gave all but the groups the doubling rounds finished
         LcpFixArgs a{v, P<u32>(c->sa), P<u32>(c->t5), any_other};
@@ -784,6 +810,37 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
     }
 #endif
     return CSA_GPU_OK;
+}
+
+extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flags) {
+    if (c) { c->shard_rank = 0; c->shard_nranks = 1; }
+    return run_phases(c, max_interval, flags, 0);
+}
+
+// ---- one batch, the suffix-array stage sharded over the ranks of a job ----------------------------------------
+extern "C" int csa_gpu_shard_begin(csa_gpu_ctx *c, int rank, int nranks) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (nranks < 1 || rank < 0 || rank >= nranks) CSA_FAIL(CSA_GPU_EINVAL, "bad rank %d of %d", rank, nranks);
+    c->shard_rank = rank; c->shard_nranks = nranks;
+    return run_phases(c, 0, 0, 1);
+}
+
+extern "C" int csa_gpu_shard_view(csa_gpu_ctx *c, csa_gpu_shard_info *out) {
+    if (!c || !out) CSA_FAIL(CSA_GPU_EINVAL, "null argument");
+    if (c->shard_phase != 1) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_shard_view before csa_gpu_shard_begin");
+    out->sa = c->valsA.p; out->head = c->t0.p; out->lcp = c->t5.p; out->left = c->t4.p;
+    out->n = c->N;
+    out->bounds = c->h_shard_bounds.data();
+    out->nleft = c->ws_left[0]; out->left_suffixes = c->ws_left[1]; out->min_depth = c->ws_left[2]; out->max_group = c->ws_left[3];
+    return CSA_GPU_OK;
+}
+
+extern "C" int csa_gpu_shard_finish(csa_gpu_ctx *c, int max_interval, unsigned flags, unsigned nleft, unsigned left_suffixes,
+                                    unsigned min_depth, unsigned max_group) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (c->shard_phase != 1) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_shard_finish before csa_gpu_shard_begin");
+    c->ws_left[0] = nleft; c->ws_left[1] = left_suffixes; c->ws_left[2] = min_depth; c->ws_left[3] = max_group;
+    return run_phases(c, max_interval, flags, 2);
 }
 
 // tests: force every doubling round down the device-wide radix path (1) or let the tiles decide (0);

@@ -2066,7 +2066,9 @@ static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
 #define LCP_UNKNOWN 0xFFFFFFFFu
 
 struct WSortArgs {
-    BatchView v; u32 *sa; u32 *head; u32 *lcp; u32 N; u32 L0; u32 depth_cap; int masks;
+    BatchView v; u32 *sa; u32 *head; u32 *lcp; u32 N;
+    u32 lo, hi; // only the groups that start in [lo, hi) (both group borders): one rank's bucket, or 0, N
+    u32 L0; u32 depth_cap; int masks;
     u64 *left; // groups still to be ordered (start : size), for the doubling rounds
     u64 *big;  // groups too long for a warp's window (start : size), for k_wsort_big
     u32 nbig;  // (k_wsort_big) entries of big
@@ -2114,6 +2116,28 @@ HD u32 ws_common(u64 ka, u32 ma, u64 kb, u32 mb) { // letters the two words shar
     const u32 pk = dk ? (u32)(CSA_CLZLL(dk) >> 1) : 32u, pm = dm ? (u32)CSA_CLZ(dm) : 32u;
     return pk < pm ? pk : pm;
 }
+
+// bucket borders for a job of nranks ranks: the first group border at or after r * N / nranks
+struct BoundsArgs { const u32 *head; u32 N; u32 nranks; u32 *bounds; };
+HD void bounds_map_body(long long r, const BoundsArgs &a) {
+    u64 p = (u64)r * a.N / a.nranks;
+    if (r == 0) p = 0;
+    if ((u32)r >= a.nranks) p = a.N;
+    if (p > 0 && p < a.N && (a.head[p] & 0x7FFFFFFFu) != (u32)p) { // inside a group: its end
+        const u32 hs = a.head[p] & 0x7FFFFFFFu;
+        u64 lo = p, step = 1;
+        while (lo + step < a.N && (a.head[lo + step] & 0x7FFFFFFFu) == hs) { lo += step; step *= 2; }
+        u64 hi = lo + step < a.N ? lo + step : a.N;
+        while (hi - lo > 1) {
+            const u64 mid = (lo + hi) >> 1;
+            if ((a.head[mid] & 0x7FFFFFFFu) == hs) lo = mid; else hi = mid;
+        }
+        p = hi;
+    }
+    a.bounds[r] = (u32)p;
+}
+MAP_KERNEL(bounds_map, BoundsArgs, 4)
+static inline void launch_bounds(Exec &ex, const BoundsArgs &a) { launch_bounds_map(ex, (long long)a.nranks + 1, a); }
 
 #ifdef CSA_EMU
 // one group [p, e) by the letters [L0, Lend): stable; what is still together goes to the list
@@ -2165,12 +2189,12 @@ static inline void launch_wsort(Exec &, const WSortArgs &a) {
     const BatchView &v = a.v;
     const u32 N = a.N;
     auto border = [&](u64 p) { return p < N ? (a.head[p] & 0x7FFFFFFFu) == (u32)p : p == N; };
-    for (u64 r0 = 0; r0 < N; r0 += WS_NOM) {
+    for (u64 r0 = a.lo & ~31u; r0 < a.hi; r0 += WS_NOM) {
         // groups that start in [r0, r0+WS_NOM) and end at or before place r0 + WS_CAP - 1
         std::vector<std::pair<u32, u32>> groups;
         u32 nmin = 0xFFFFFFFFu;
-        for (u64 p = r0; p < r0 + WS_NOM && p < N; p++) {
-            if (!border(p)) continue;
+        for (u64 p = r0; p < r0 + WS_NOM && p < a.hi; p++) {
+            if (p < a.lo || !border(p)) continue;
             u64 e = p + 1;
             while (!border(e)) e++;
             if (e - r0 > WS_CAP - 1) { // runs past the warp's window
@@ -2331,8 +2355,8 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
     static_assert(WS_T == 4 && WS_CAP == 128, "border words are kept as two u64");
     __shared__ WsSmem<1> s_all[WS_WARPS];
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const u64 r0_64 = ((u64)blockIdx.x * WS_WARPS + warp) * WS_NOM;
-    if (r0_64 >= a.N) return;
+    const u64 r0_64 = (u64)(a.lo & ~31u) + ((u64)blockIdx.x * WS_WARPS + warp) * WS_NOM;
+    if (r0_64 >= a.hi) return;
     const u32 r0 = (u32)r0_64, N = a.N;
     WsSmem<1> &s = s_all[warp];
     // ---- the window: heads of WS_CAP places, borders as a bit set ----
@@ -2343,10 +2367,15 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
         hv[j] = p < N ? (a.head[p] & 0x7FFFFFFFu) : 0u;
         bw[j] = __ballot_sync(0xffffffffu, p < N ? hv[j] == (u32)p : p == N);
     }
-    if (bw[0] == 0) return; // no group starts here
-    const u32 tb = (u32)__ffs((int)bw[0]) - 1u;
+    // starts that are this launch's: places in [lo, hi)
+    u32 mine = bw[0];
+    if (r0 < a.lo) mine &= ~0u << (a.lo - r0);
+    if (a.hi - r0 < 32u) mine &= (1u << (a.hi - r0)) - 1u;
+    if (mine == 0) return; // no group starts here
+    const u32 tb = (u32)__ffs((int)mine) - 1u;
     u32 te;
-    if (bw[1]) te = 32u + (u32)__ffs((int)bw[1]) - 1u;
+    if (a.hi - r0 < 32u) te = a.hi - r0; // hi is a border (or the end of the array)
+    else if (bw[1]) te = 32u + (u32)__ffs((int)bw[1]) - 1u;
     else if (bw[2]) te = 64u + (u32)__ffs((int)bw[2]) - 1u;
     else if (bw[3]) te = 96u + (u32)__ffs((int)bw[3]) - 1u;
     else if (N - r0 < 32u) te = N - r0; // the array ends inside the first word: that end is the last border seen
@@ -2435,8 +2464,8 @@ __global__ void __launch_bounds__(WS_BIG_WARPS * 32) k_wsort_big(WSortArgs a) {
 }
 
 static inline void launch_wsort(Exec &ex, const WSortArgs &a) {
-    if (a.N == 0) return;
-    const u32 nwarps = (a.N + WS_NOM - 1) / WS_NOM;
+    if (a.hi <= a.lo) return;
+    const u32 nwarps = (a.hi - (a.lo & ~31u) + WS_NOM - 1) / WS_NOM;
     PROF_BEGIN(ex, "k_wsort", 4.0 * a.N);
     if (a.masks) k_wsort<true><<<(nwarps + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, ex.stream>>>(a);
     else k_wsort<false><<<(nwarps + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, ex.stream>>>(a);

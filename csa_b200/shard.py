@@ -58,3 +58,69 @@ def find_rotations_stream(finder: RotationFinder, sets: Sequence[Sequence[bytes]
     for _, chunk in batches_by_size(sets, max_bases):
         out.extend(finder.find_rotations_batch(chunk, flags=flags, with_blocks=with_blocks))
     return out
+
+
+# ---- one set (or batch) too large to be quick on one GPU: the suffix-array stage sharded by buckets ----------
+def _alias(ptr: int, count: int, itemsize: int, cuda: bool):
+    """a torch tensor over `count` items of the library's own buffer at `ptr` (no copy): int32 or int64"""
+    import torch
+    if count == 0:
+        return torch.empty(0, dtype=torch.int32 if itemsize == 4 else torch.int64, device="cuda" if cuda else "cpu")
+    if cuda:
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4" if itemsize == 4 else "<i8",
+                                      "data": (ptr, False), "version": 2}
+        return torch.as_tensor(h, device="cuda")
+    import ctypes as C
+    ctype = C.c_int32 if itemsize == 4 else C.c_int64
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,))
+    return torch.from_numpy(arr)
+
+
+def run_bucket_sharded(finder: RotationFinder, rank: int, world: int, dist=None, max_interval: int = 2**31 - 1,
+                       flags: int = 0, cuda: bool = True):
+    """The batch uploaded to `finder` on EVERY rank (the same batch), its suffix array built bucket by bucket:
+    rank r orders the groups of bucket r (csa_gpu_shard_begin), the buckets -- suffix array, group heads, LCP --
+    are broadcast from their owners over the job's process group (NCCL over NVLink on the GPU box, gloo in the
+    CPU tests), the lists of what the bucket sorts left are concatenated, and every rank runs the rest of the
+    path (csa_gpu_shard_finish).  Afterwards finder.download() / finder.blocks() give the same results on every
+    rank as a single-GPU run.  Returns the bucket borders."""
+    import torch
+    finder.shard_begin(rank, world)
+    v = finder.shard_view()
+    bounds = [int(v.bounds[r]) for r in range(world + 1)]
+    n = int(v.n)
+    mine = [int(v.nleft), int(v.left_suffixes), int(v.min_depth), int(v.max_group)]
+    if world == 1:
+        finder.shard_finish(max_interval, flags, *mine)
+        return bounds
+    dev = "cuda" if cuda else "cpu"
+    for ptr in (v.sa, v.head, v.lcp):
+        t = _alias(ptr, n, 4, cuda)
+        for r in range(world):
+            if bounds[r + 1] > bounds[r]:
+                dist.broadcast(t[bounds[r]:bounds[r + 1]], src=r)
+    cnt = torch.tensor(mine, dtype=torch.int64, device=dev)
+    allc = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(allc, cnt)
+    allc = [c.tolist() for c in allc]
+    nl = [c[0] for c in allc]
+    total = sum(nl)
+    if total:
+        left = _alias(v.left, max(total, nl[rank]), 8, cuda)
+        tmp = torch.empty(total, dtype=torch.int64, device=dev)
+        off = 0
+        for r in range(world):
+            if nl[r]:
+                seg = tmp[off:off + nl[r]]
+                if r == rank:
+                    seg.copy_(left[:nl[r]])
+                dist.broadcast(seg, src=r)
+                off += nl[r]
+        left[:total].copy_(tmp)
+    if cuda:
+        torch.cuda.synchronize()
+    finder.shard_finish(max_interval, flags, total, sum(c[1] for c in allc), min(c[2] for c in allc), max(c[3] for c in allc))
+    return bounds

@@ -123,6 +123,32 @@ int csa_gpu_batch_suffix_array(csa_gpu_ctx *ctx, unsigned *sa, int *lcp);
  * stream): [0] suffix sort, [1] LCP, [2] block discovery, [3] block order, [4] chaining,
  * [5] whole run; launches = kernels launched by the last run. */
 int csa_gpu_batch_timings(csa_gpu_ctx *ctx, float ms[6], long long *launches);
+
+/* ---- one batch, the suffix-array stage sharded over the ranks of a job ----------------------------------
+ * For a single set too large to be quick on one GPU (BASELINE configs[4]: bacterial chromosomes).  The
+ * reference builds ONE generalized tree (gencycsuffixtrees.c:418 buildGeneralizedTree); its counterpart here,
+ * the suffix array, splits by first letters into buckets that are ordered independently of one another:
+ *   every rank:  csa_gpu_batch_upload* of the same batch, then
+ *   csa_gpu_shard_begin(ctx, rank, nranks)   first sort (the same on every rank), bucket borders at group
+ *                                             borders, groups + LCPs of bucket `rank` by the word sort
+ *   csa_gpu_shard_view(ctx, &v)              device pointers and the borders: the caller copies
+ *                                             sa/head/lcp[bounds[r] .. bounds[r+1]) from rank r to all ranks
+ *                                             (NCCL broadcast / all-gather), concatenates the ranks' `left` lists
+ *                                             into `left` and merges nleft (sum), left_suffixes (sum), min_depth
+ *                                             (min), max_group (max)
+ *   csa_gpu_shard_finish(ctx, ...merged...)  the rest of the path on every rank (results as csa_gpu_batch_run)
+ * No collective runs inside the library; csa_b200/shard.py drives the exchange with torch.distributed. */
+typedef struct csa_gpu_shard_info {
+    void *sa, *head, *lcp;        /* device, unsigned[n] */
+    void *left;                   /* device, unsigned long long[]: groups the bucket sort left (start << 32 | size) */
+    unsigned long long n;
+    const unsigned *bounds;       /* host, nranks + 1 entries, valid until the next call on ctx */
+    unsigned nleft, left_suffixes, min_depth, max_group;
+} csa_gpu_shard_info;
+int csa_gpu_shard_begin(csa_gpu_ctx *ctx, int rank, int nranks);
+int csa_gpu_shard_view(csa_gpu_ctx *ctx, csa_gpu_shard_info *out);
+int csa_gpu_shard_finish(csa_gpu_ctx *ctx, int max_interval, unsigned flags, unsigned nleft, unsigned left_suffixes,
+                         unsigned min_depth, unsigned max_group);
 /* tests: force_global = 1 sends every prefix-doubling round down the device-wide radix-sort path,
  * 0 lets the tile path take the rounds whose groups fit a tile, -1 leaves the setting; rounds[0..1]
  * = rounds of the last run on the tile path / on the device-wide path */

@@ -221,3 +221,24 @@ def test_gpu_large_batch_of_config3_sets(gpu_finder):
         check_block_properties(sets[i], res[i])
     for i in (0, 77, 159):
         compare_with_oracle(res[i], oracle_run(sets[i]), sets[i], f"set {i}")
+
+
+def test_gpu_bucket_path_one_rank(gpu_finder):
+    """csa_gpu_shard_begin / _finish with a job of one rank (the whole suffix array is one bucket) give what
+    csa_gpu_batch_run gives; the N > 1 exchange is covered by tests/test_sharding.py on gloo"""
+    from csa_b200.shard import run_bucket_sharded
+    for name, nsets in (("mammals", 3), ("sets32", 2)):
+        batch = workload_batch(name, nsets, seed=11)
+        ref = gpu_finder.find_rotations_batch(batch)
+        sa0, lcp0 = gpu_finder.suffix_array()
+        gpu_finder.upload(batch)
+        bounds = run_bucket_sharded(gpu_finder, 0, 1)
+        assert bounds == [0, batch.nbases]
+        sa, lcp = gpu_finder.suffix_array()
+        assert np.array_equal(sa0, sa) and np.array_equal(lcp0[1:], lcp[1:])
+        rot, info = gpu_finder.download()
+        for k, r in enumerate(ref):
+            q0, q1 = int(batch.set_start[k]), int(batch.set_start[k + 1])
+            assert info[k].status == r.status
+            if r.status == 0:
+                assert np.array_equal(rot[q0:q1], r.rotations)

@@ -32,6 +32,65 @@ dist.destroy_process_group()
 '''
 
 
+BUCKET_WORKER = r'''
+import os, sys, random
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np
+import torch.distributed as dist
+from common import EMU_LIB, build_emu, gen_case, oracle_run, oracle_gsa, compare_with_oracle
+from csa_b200.api import RotationFinder, Batch
+from csa_b200.shard import run_bucket_sharded
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = random.Random(77)
+rf = RotationFinder(lib_path=EMU_LIB)
+for trial in range(6):
+    sets = [gen_case(rng, max_n=1500)[1] for _ in range(rng.randint(1, 4))]
+    rf.debug_rounds(4 if trial % 2 else 0)   # odd trials: the bucket sorts stop early and leave groups to the doubling rounds
+    batch = Batch(sets)
+    rf.upload(batch)
+    bounds = run_bucket_sharded(rf, rank, world, dist, cuda=False)
+    assert bounds[0] == 0 and bounds[-1] == batch.nbases and bounds == sorted(bounds)
+    sa, lcp = rf.suffix_array()
+    off = 0
+    for s in sets:   # every rank holds the whole suffix array afterwards
+        n = sum(len(x) for x in s)
+        osa, olcp = oracle_gsa(s)
+        assert np.array_equal(sa[off:off + n].astype(np.int64) - off, osa.astype(np.int64)), (trial, "suffix array")
+        assert np.array_equal(lcp[off + 1:off + n], olcp[1:]), (trial, "lcp")
+        off += n
+    rf.debug_rounds(0)
+    ref = rf.find_rotations_batch(batch)          # the same batch on one rank alone
+    rf.debug_rounds(4 if trial % 2 else 0)
+    rf.upload(batch)
+    run_bucket_sharded(rf, rank, world, dist, cuda=False)
+    rot, info = rf.download()
+    for k, (s, r) in enumerate(zip(sets, ref)):
+        o = oracle_run(s)
+        assert info[k].status == o["status"] == r.status
+        if o["status"] == 0:
+            q0, q1 = int(batch.set_start[k]), int(batch.set_start[k + 1])
+            assert list(rot[q0:q1]) == list(o["rotations"])
+rf.debug_rounds(0)
+sys.stdout.write("BUCKET_OK_%d_of_%d\n" % (rank, world)); sys.stdout.flush()
+dist.destroy_process_group()
+'''
+
+
+def test_two_gloo_ranks_buckets_of_one_batch(tmp_path):
+    """one batch, its suffix array built bucket by bucket on two ranks (csa_gpu_shard_*), buckets exchanged by
+    gloo broadcasts: suffix array, LCP and rotations equal the oracle's on every rank"""
+    from common import build_emu
+    build_emu()
+    w = tmp_path / "bucket_worker.py"
+    w.write_text(BUCKET_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29537", str(w), ROOT],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900, env=env, text=True)
+    assert p.returncode == 0 and "BUCKET_OK_0_of_2" in p.stdout and "BUCKET_OK_1_of_2" in p.stdout, p.stdout[-3000:]
+
+
 def test_shard_bounds():
     assert shard_bounds(10, 4) == [0, 3, 6, 8, 10]
     assert shard_bounds(3, 8) == [0, 1, 2, 3, 3, 3, 3, 3, 3]
