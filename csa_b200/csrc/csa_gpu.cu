@@ -54,7 +54,9 @@ struct csa_gpu_ctx {
     int ws_runs = 0, ws_force = 0; double ws_pairs = 0;
     u32 sa_any_other = 1, sa_ngroups = 0;
     int shard_rank = 0, shard_nranks = 1, shard_phase = 0;
-    DevMem shard_bounds; std::vector<u32> h_shard_bounds; u32 ws_depth_cap = WS_DEPTH_CAP; u32 ws_left[6] = {0, 0, 0, 0, 0, 0};
+    DevMem shard_bounds; std::vector<u32> h_shard_bounds;
+    DevMem chb_sets, chb_evbase, chb_events, chb_work, chb_redo;
+    int no_chain_big = 0, chain_redone = 0; u32 ws_depth_cap = WS_DEPTH_CAP; u32 ws_left[6] = {0, 0, 0, 0, 0, 0};
     double lcp_mean_sample = 0;
     int force_kasai = 0;
     int rounds_list = 0, round_mode = 0;
@@ -134,7 +136,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
                      &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
-                     &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
+                     &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->chb_sets, &c->chb_evbase, &c->chb_events, &c->chb_work, &c->chb_redo, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
                      &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
@@ -704,9 +706,48 @@ static int stage_chain(csa_gpu_ctx *c, const BatchView &v, int max_interval) {
                 max_interval, P<int>(c->next), P<int>(c->gap)};
       launch_gap(ex, B, a); }
     TRY(dev_zero(ex, c->size.p, nb)); TRY(dev_zero(ex, c->total.p, nb)); TRY(dev_zero(ex, c->interval.p, nb));
-    { ChainArgs a{set_blk0, P<u32>(c->o_depth), P<int>(c->next), P<int>(c->gap), P<int>(c->size), P<int>(c->total), P<int>(c->interval),
-                  P<u32>(c->set_nchains), P<u32>(c->set_flags)};
-      launch_chain(ex, nsets, a); }
+    {
+        ChainArgs a{set_blk0, P<u32>(c->o_depth), P<int>(c->next), P<int>(c->gap), P<int>(c->size), P<int>(c->total), P<int>(c->interval),
+                    P<u32>(c->set_nchains), P<u32>(c->set_flags), 0};
+#ifndef CSA_EMU
+        // sets with more blocks than k_chain holds in shared memory: k_chain_big (walk order in shared memory, sums in parallel)
+        std::vector<u32> big, evb;
+        u64 nev = 0;
+        u32 maxb = 0;
+        for (int s = 0; s < nsets; s++) {
+            const u32 nbk = c->h_set_nblocks[s];
+            if (nbk > CH_CAP && nbk <= CHB_MAX) { big.push_back((u32)s); evb.push_back((u32)nev); nev += 4ull * nbk; maxb = std::max(maxb, nbk); }
+        }
+        if (!big.empty() && nev < (1ull << 32) && !c->no_chain_big) {
+            a.skip_big = 1;
+            TRY(dev_alloc(c->chb_sets, sizeof(u32) * big.size())); TRY(dev_alloc(c->chb_evbase, sizeof(u32) * big.size()));
+            TRY(dev_alloc(c->chb_events, sizeof(u64) * (size_t)nev)); TRY(dev_alloc(c->chb_work, 4 * nb));
+            TRY(dev_alloc(c->chb_redo, sizeof(u32) * (nsets + 1)));
+            TRY(h2d(ex, c->chb_sets.p, big.data(), sizeof(u32) * big.size()));
+            TRY(h2d(ex, c->chb_evbase.p, evb.data(), sizeof(u32) * big.size()));
+            TRY(dev_zero(ex, c->chb_redo.p, sizeof(u32) * (nsets + 1)));
+            ChainBigArgs g{a, P<u32>(c->chb_sets), P<unsigned long long>(c->chb_events), P<u32>(c->chb_evbase),
+                           P<int>(c->chb_work), P<int>(c->chb_work) + B, P<int>(c->chb_work) + 2 * (size_t)B, P<u32>(c->chb_work) + 3 * (size_t)B,
+                           P<u32>(c->chb_redo)};
+            TRY(launch_chain_big(ex, (u32)big.size(), 3 * (size_t)maxb + 16, g));
+        }
+#endif
+        launch_chain(ex, nsets, a);
+#ifndef CSA_EMU
+        if (a.skip_big) { // a set whose sums contradicted the walk order (see k_chain_big): the literal walk redoes it
+            std::vector<u32> redo(nsets);
+            TRY(d2h(ex, redo.data(), c->chb_redo.p, sizeof(u32) * nsets));
+            bool any = false;
+            for (u32 r : redo) any |= r != 0;
+            c->chain_redone = any ? 1 : 0;
+            if (any) {
+                TRY(dev_zero(ex, c->size.p, nb)); TRY(dev_zero(ex, c->total.p, nb)); TRY(dev_zero(ex, c->interval.p, nb));
+                a.skip_big = 0;
+                launch_chain(ex, nsets, a);
+            }
+        }
+#endif
+    }
     { SizeKeyArgs a{P<u32>(c->o_set), P<int>(c->size), P<u64>(c->keysA), P<u32>(c->valsA)}; launch_sizekey(ex, B, a); }
     TRY(sort_pairs(c, B, 0, 32 + bits_for((u64)c->nsets - 1)));
     { InvArgs a{P<u32>(c->valsA), P<u32>(c->inv)}; launch_inv(ex, B, a); }
@@ -854,7 +895,8 @@ extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds
         c->round_mode = force_global;
         c->ws_depth_cap = force_global == 4 ? 80u : WS_DEPTH_CAP;
         c->ws_force = force_global == 6; // 6: word sort whatever the groups look like
-        if (force_global == 6) c->round_mode = 0;
+        c->no_chain_big = force_global == 7; // 7: free choice, but long block lists walked by one thread (k_chain) as short ones are
+        if (force_global == 6 || force_global == 7) c->round_mode = 0;
         c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; c->force_kasai = force_global == 2;
     }
     if (rounds) { rounds[0] = c->rounds_tiled + c->rounds_quad + c->rounds_list + c->ws_runs; rounds[1] = c->rounds_global; }

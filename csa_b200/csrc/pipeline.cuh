@@ -865,6 +865,7 @@ MAP_KERNEL(gap, GapArgs, 16)
 struct ChainArgs {
     const u32 *set_blk0; const u32 *o_depth; const int *next; const int *gap;
     int *size; int *total; int *interval; u32 *set_nchains; u32 *set_flags;
+    int skip_big; // sets of CH_CAP < blocks <= CHB_MAX are k_chain_big's
 };
 // the walk over one set's blocks; arrays are indexed from the set's first block (b0), `next` holds
 // batch-wide block numbers
@@ -923,6 +924,7 @@ MAP_KERNEL(chain, ChainArgs, 16)
 // there; sets with more blocks than fit are walked in global memory
 #define CH_THREADS 128
 #define CH_CAP 1536
+#define CHB_MAX 65534u
 __global__ void __launch_bounds__(CH_THREADS) k_chain(ChainArgs a) {
     __shared__ u32 s_depth[CH_CAP];
     __shared__ int s_next[CH_CAP], s_gap[CH_CAP], s_size[CH_CAP], s_total[CH_CAP], s_interval[CH_CAP];
@@ -941,6 +943,8 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(ChainArgs a) {
         for (u32 i = threadIdx.x; i < B; i += CH_THREADS) {
             a.size[b0 + i] = s_size[i]; a.total[b0 + i] = s_total[i]; a.interval[b0 + i] = s_interval[i];
         }
+    } else if (a.skip_big && B <= CHB_MAX) {
+        return;
     } else if (threadIdx.x == 0) {
         chain_walk(b0, B, a.o_depth + b0, a.next + b0, a.gap + b0, a.size + b0, a.total + b0, a.interval + b0, &mcs, &hang);
     }
@@ -955,6 +959,145 @@ static inline void launch_chain(Exec &ex, long long nsets, ChainArgs a) {
     k_chain<<<(unsigned)nsets, CH_THREADS, 0, ex.stream>>>(a);
     PROF_END(ex);
     ex.launches++;
+}
+#endif
+
+#ifndef CSA_EMU
+// A set with tens of thousands of blocks (bacterial chromosomes): one thread walking them in global memory
+// pays an L2 round trip per block (31 ms for 50 000 blocks).  Only the ORDER of the walk is sequential --
+// which block a walk takes next and whether that block heads a finished chain -- and that needs nothing but
+// `next` and one state byte per block, which fit shared memory (3 B per block).  So:
+//   1. thread 0 replays the control flow of collectNodeChains (csamsa.c:185-233) in shared memory and logs
+//      every step as an event (walk's head, block before, block, kind);
+//   2. all threads add up gaps and depths per walk from the events (the sums of :203-226);
+//   3. sizes/totals of walks that took over a finished chain follow from that chain's (a few parallel rounds);
+//   4. the two places where the control flow looks at a SUM (total[c] > 0 at :201 for a finished head, and for
+//      the walk's own head when a circular chain closes) were taken as true in 1. and are checked now; a set
+//      that fails the check (never seen: every term depth + gap is positive) is redone by the literal walk.
+#define CHB_THREADS 256
+#define CHB_ABS 1u    // total == -1: taken by some walk
+#define CHB_HEAD 2u   // has finished its own walk
+struct ChainBigArgs {
+    ChainArgs c;
+    const u32 *sets; // the sets this launch handles
+    unsigned long long *events; u32 *ev_base; // per set: first event slot; capacity 4 * blocks
+    int *wS, *wT, *wchild; u32 *wdone;        // per block scratch
+    u32 *redo;                                // per set: 1 = the literal walk must redo it
+};
+__global__ void __launch_bounds__(CHB_THREADS) k_chain_big(ChainBigArgs a) {
+    extern __shared__ unsigned char chb_dyn[];
+    __shared__ u32 s_nev, s_mcs, s_fail, s_hang;
+    const u32 s = a.sets[blockIdx.x];
+    const u32 b0 = a.c.set_blk0[s], B = a.c.set_blk0[s + 1] - b0;
+    unsigned short *nx = (unsigned short *)chb_dyn;
+    unsigned char *st = chb_dyn + 2 * (size_t)((B + 1) & ~1u);
+    const u32 *depth = a.c.o_depth + b0;
+    const int *gap = a.c.gap + b0;
+    int *size = a.c.size + b0, *total = a.c.total + b0, *interval = a.c.interval + b0;
+    int *wS = a.wS + b0, *wT = a.wT + b0, *wchild = a.wchild + b0;
+    u32 *wdone = a.wdone + b0;
+    unsigned long long *ev = a.events + a.ev_base[blockIdx.x];
+    const u32 evcap = 4u * B;
+    for (u32 i = threadIdx.x; i < B; i += CHB_THREADS) {
+        const int n = a.c.next[b0 + i];
+        nx[i] = n < 0 ? (unsigned short)0xFFFFu : (unsigned short)((u32)n - b0);
+        st[i] = 0;
+        wS[i] = 0; wT[i] = 0; wchild[i] = -1; wdone[i] = 0; // wS, wT: sums of depths / gaps of the walk that starts at i
+    }
+    if (threadIdx.x == 0) { s_nev = 0; s_mcs = B; s_fail = 0; s_hang = 0; }
+    __syncthreads();
+    // ---- 1. the order of the walks ----
+    if (threadIdx.x == 0) {
+        u32 nev = 0, mcs = B;
+        const long long guard_max = 4ll * B + 16;
+        bool fail = false, hang = false;
+        for (u32 b = 0; b < B && !hang && !fail; b++) {
+            if (st[b] & CHB_ABS) continue;
+            u32 prev = b, cur = nx[b];
+            long long guard = 0;
+            while (cur != 0xFFFFu) {
+                if (++guard > guard_max) { hang = true; break; }
+                if (nev == evcap) { fail = true; break; }
+                const u32 c = cur;
+                const bool finished = (c == b) || ((st[c] & CHB_HEAD) && !(st[c] & CHB_ABS)); // total[c] > 0 (checked in 4.)
+                ev[nev++] = ((unsigned long long)b << 40) | ((unsigned long long)prev << 20) | ((unsigned long long)c << 2) | (finished ? (c == b ? 2ull : 1ull) : 0ull);
+                mcs--;
+                if (finished) {
+                    if (c != b) { st[c] |= CHB_ABS; wchild[b] = (int)c; } else wchild[b] = -2 - (int)prev; // (closed on itself after `prev`)
+                    break;
+                }
+                st[c] |= CHB_ABS;
+                prev = c;
+                cur = nx[c];
+            }
+            st[b] |= CHB_HEAD;
+        }
+        s_nev = nev; s_mcs = mcs; s_fail = fail ? 1u : 0u; s_hang = hang ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_hang || s_fail) {
+        if (threadIdx.x == 0) {
+            if (s_hang) atomicMax(a.c.set_flags + s, 2u); else a.redo[s] = 1;
+            a.c.set_nchains[s] = s_mcs;
+        }
+        return;
+    }
+    // ---- 2. sums per walk ----
+    const u32 nev = s_nev;
+    for (u32 e = threadIdx.x; e < nev; e += CHB_THREADS) {
+        const unsigned long long w = ev[e];
+        const u32 b = (u32)(w >> 40), prev = (u32)(w >> 20) & 0xFFFFFu, c = (u32)(w >> 2) & 0x3FFFFu, kind = (u32)w & 3u;
+        const int iv = gap[prev];
+        interval[prev] = iv;
+        atomicAdd(&wT[b], iv);
+        if (kind == 0) atomicAdd(&wS[b], (int)depth[c]);
+    }
+    __syncthreads();
+    // ---- 3. sizes and totals: S = own depths (+ S of the chain taken over), T = own gaps (+ T of that chain) + S ----
+    // (a round only builds on chains finished in an EARLIER round: wdone 2 = worked out in this round, 1 = before)
+    for (;;) {
+        for (u32 b = threadIdx.x; b < B; b += CHB_THREADS) {
+            if (!(st[b] & CHB_HEAD) || wdone[b]) continue;
+            const int ch = wchild[b];
+            if (ch >= 0 && wdone[ch] != 1u) continue; // the chain it took over is not worked out yet
+            int S = (int)depth[b] + wS[b], T = wT[b];
+            if (ch <= -2) { // circular chain (:201 with cur == b): what the reference leaves
+                const int before = T - gap[-2 - ch]; // total[b] when the walk came back to b
+                if (before <= 0) s_fail = 1;
+                S = (int)depth[b]; T = (int)depth[b] - 1;
+            } else {
+                if (ch >= 0) { if (wT[ch] <= 0) s_fail = 1; S += wS[ch]; T += wT[ch]; }
+                T += S;
+            }
+            wS[b] = S; wT[b] = T;
+            wdone[b] = 2u;
+        }
+        __syncthreads();
+        bool changed = false;
+        for (u32 b = threadIdx.x; b < B; b += CHB_THREADS)
+            if (wdone[b] == 2u) { wdone[b] = 1u; changed = true; }
+        if (!__syncthreads_or(changed)) break;
+    }
+    if (s_fail) { if (threadIdx.x == 0) a.redo[s] = 1; return; }
+    // ---- what the reference leaves in the list ----
+    for (u32 i = threadIdx.x; i < B; i += CHB_THREADS) {
+        if (st[i] & CHB_ABS) { size[i] = (int)depth[i]; total[i] = -1; }
+        else { size[i] = wS[i]; total[i] = wT[i]; }
+    }
+    if (threadIdx.x == 0) a.c.set_nchains[s] = s_mcs;
+}
+static inline int launch_chain_big(Exec &ex, u32 nbig, size_t smem, ChainBigArgs a) {
+    if (nbig == 0) return 0;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(k_chain_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
+    }
+    PROF_BEGIN(ex, "k_chain_big", 0.0);
+    k_chain_big<<<nbig, CHB_THREADS, smem, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
+    return 0;
 }
 #endif
 

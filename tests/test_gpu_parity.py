@@ -242,3 +242,24 @@ def test_gpu_bucket_path_one_rank(gpu_finder):
             assert info[k].status == r.status
             if r.status == 0:
                 assert np.array_equal(rot[q0:q1], r.rotations)
+
+
+def test_gpu_long_block_lists(gpu_finder):
+    """a set with thousands of blocks (bacterial-style: few long genomes) takes k_chain_big -- walk order in shared
+    memory, sums in parallel -- and must leave exactly what the literal one-thread walk (mode 7) and the oracle leave"""
+    from csa_b200.workloads import make_batch, batch_sets
+    batch = make_batch(2, 4, 300_000, 0.01, 0.001, seed=21, population=True)
+    try:
+        gpu_finder.debug_rounds(7)
+        lit = gpu_finder.find_rotations_batch(batch)
+    finally:
+        gpu_finder.debug_rounds(0)
+    res = gpu_finder.find_rotations_batch(batch)
+    for a, b in zip(lit, res):
+        assert len(a.depth) > 1536, "the case must be long enough for k_chain_big"
+        assert a.status == b.status and a.count_chains == b.count_chains
+        for name in ("depth", "size", "totalsize", "interval", "next"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), name
+        assert np.array_equal(a.positions, b.positions) and np.array_equal(a.rotations, b.rotations)
+    s0 = batch_sets(batch, 0, 1)[0]
+    compare_with_oracle(res[0], oracle_run(s0), s0, "long block list")
