@@ -51,7 +51,7 @@ struct csa_gpu_ctx {
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, t5, counter, tiles;
     u32 batch_nmin = 0;
     int lcp_state = 0;          // after the suffix array stage: 0 nothing known, 1 every LCP known, 2 all but the LCP_UNKNOWN places
-    int ws_runs = 0, ws_force = 0; double ws_pairs = 0;
+    int ws_runs = 0, ws_force = 0; double ws_pairs = 0, ws_sharing = 0;
     u32 sa_any_other = 1, sa_ngroups = 0;
     int shard_rank = 0, shard_nranks = 1, shard_phase = 0;
     DevMem shard_bounds; std::vector<u32> h_shard_bounds;
@@ -397,14 +397,15 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     TRY(heads_and_ranks(c, head, nullptr, counter, &ngroups, !any_other, true, words ? lcp : nullptr, letters, lbits));
     c->rounds_tiled = c->rounds_global = c->rounds_quad = c->rounds_list = 0;
     if (ngroups != N) {
-        unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs = 0;
+        unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs[2] = {0, 0};
         TRY(dev_zero(ex, counter + 2, sizeof(u32)));
-        TRY(dev_zero(ex, pairs, sizeof(*pairs)));
+        TRY(dev_zero(ex, pairs, 2 * sizeof(*pairs)));
         { MaxGroupArgs a{head, counter + 2, N, pairs}; launch_maxgroup(ex, N, a); }
         TRY(read_u32(c, counter + 2, &maxg));
-        TRY(d2h(ex, &hpairs, pairs, sizeof(hpairs)));
-        c->ws_pairs = (double)hpairs;
-        if (phase == 0 && c->round_mode == 0 && !c->ws_force && (double)hpairs > WS_PAIRS_PER_SUFFIX * (double)N) words = false;
+        TRY(d2h(ex, hpairs, pairs, sizeof(hpairs)));
+        c->ws_pairs = (double)hpairs[0];
+        c->ws_sharing = (double)hpairs[1];
+        if (phase == 0 && c->round_mode == 0 && !c->ws_force && (double)hpairs[0] > WS_PAIRS_PER_SUFFIX * (double)N) words = false;
     }
     if (!words) { SetRankArgs r{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, r); }
     c->sa_ngroups = ngroups;
@@ -445,18 +446,18 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
             WSortArgs a{v, P<u32>(c->valsA), head, lcp, N, lo, hi, (u32)letters, c->ws_depth_cap, (int)any_other, glist[0], glist[1], 0u, res};
             launch_wsort(ex, a);
             TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
-            const double warp_handled = c->ws_left[4];
             if (c->ws_left[5]) { // groups that did not fit a warp's window: one CTA each
                 a.nbig = c->ws_left[5];
                 launch_wsort_big(ex, a);
                 TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
 #ifndef CSA_EMU
-                if (ex.prof && !ex.prof->recs.empty()) ex.prof->recs.back().bytes = 8.0 * a.nbig + 16.0 * (c->ws_left[4] - warp_handled);
+                if (ex.prof && !ex.prof->recs.empty()) ex.prof->recs.back().bytes = 8.0 * a.nbig;
 #endif
             }
 #ifndef CSA_EMU
             // every suffix's head in; per suffix of a group: sa in, sa + head + lcp out
-            if (ex.prof) for (auto &r : ex.prof->recs) if (!strcmp(r.name, "k_wsort")) r.bytes = 4.0 * N + 16.0 * warp_handled;
+            // (suffixes of a group: counted by k_maxgroup; a bucket's share of them when the stage is sharded)
+            if (ex.prof) for (auto &r : ex.prof->recs) if (!strcmp(r.name, "k_wsort")) r.bytes = (4.0 * N + 16.0 * c->ws_sharing) * ((double)(hi - lo) / N);
 #endif
             c->ws_runs = 1;
         }
@@ -552,6 +553,9 @@ static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     TRY(dev_zero(ex, c->firstmax.p, sizeof(u32) * nsets));
     { ColorKeyArgs a{v, sa, P<u64>(c->keysA), P<u32>(c->valsA)}; launch_colorkey(ex, N, a); }
     TRY(sort_pairs(c, N, 0, bits_for((u64)c->mmax - 1)));
+    // colour 0 first: the SA places of sequence 0 of every set, kept for the block-order stage (k_seq0take)
+    TRY(dev_alloc(c->saidx0, sizeof(u32) * (size_t)c->N0));
+    TRY(d2d(ex, c->saidx0.p, c->valsA.p, sizeof(u32) * (size_t)c->N0));
     { NextArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA), nxt, P<u32>(c->firstmax)}; launch_next(ex, N, a); }
     { CoverArgs a{v, sa, nxt, P<u32>(c->firstmax), R}; launch_cover(ex, N, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, R, R, N)));
@@ -610,15 +614,13 @@ static int stage_stats(csa_gpu_ctx *c, const BatchView &v) {
 static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
     u32 N = c->N, N0 = c->N0, B = c->B;
-    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t5), *flag0 = P<u32>(c->t0), *idx0 = P<u32>(c->t3);
+    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t5);
     size_t n1 = sizeof(u32) * (size_t)N0, n2 = 2 * n1;
     DevMem *one[] = {&c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv, &c->pse};
     for (DevMem *m : one) TRY(dev_alloc(*m, n1));
     DevMem *two[] = {&c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2};
     for (DevMem *m : two) TRY(dev_alloc(*m, n2));
-    { Seq0FlagArgs a{v, sa, flag0}; launch_seq0flag(ex, N, a); }
-    TRY((scan_u32<ScanSum, false>(ex, c->ps, flag0, idx0, N)));
-    { Seq0EmitArgs a{v, sa, flag0, idx0, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0emit(ex, N, a); }
+    { Seq0TakeArgs a{v, sa, P<u32>(c->saidx0), P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0take(ex, N0, a); }
     { Lcp0Args a{lcp, P<u32>(c->saidx0), P<u32>(c->leaf_set), P<u32>(c->z0), P<u32>(c->lcp0)}; launch_lcp0(ex, N0, a); }
     Seq0View q{N0, P<u32>(c->z0), P<u32>(c->leaf_set), P<u32>(c->lcp0)};
     Pyramid py;
@@ -663,7 +665,7 @@ static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
         }
     }
     // order the blocks: DFS number descending, then stably (set, depth descending)
-    BlockKeyArgs k{v, sa, idx0, flag0, val, N0, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set),
+    BlockKeyArgs k{v, sa, P<u32>(c->saidx0), P<u32>(c->z0), val, N0, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set),
                    P<u64>(c->keysA), P<u32>(c->valsA), 0};
     launch_blockkey(ex, B, k);
     TRY(sort_pairs(c, B, 0, 32));

@@ -532,6 +532,19 @@ HD void seq0emit_body(long long i, const Seq0EmitArgs &a) {
 }
 MAP_KERNEL(seq0emit, Seq0EmitArgs, 8)
 
+// The same three arrays without a pass over the whole suffix array: the stable radix pass by colour of stage 3
+// (k_colorkey) leaves the SA places of colour 0 -- sequence 0 of every set -- first, set by set and in SA order.
+struct Seq0TakeArgs { BatchView v; const u32 *sa; const u32 *places; u32 *sa0; u32 *saidx0; u32 *leaf_set; };
+HD void seq0take_body(long long t, const Seq0TakeArgs &a) {
+    u32 i = a.places[t];
+    u32 g = a.sa[i];
+    u32 k = seq_of(a.v, g);
+    a.sa0[t] = g - LDG(a.v.seq_off + k);
+    a.saidx0[t] = i;
+    a.leaf_set[t] = LDG(a.v.seq_set + k);
+}
+MAP_KERNEL(seq0take, Seq0TakeArgs, 24)
+
 struct Seq0View {
     u32 N0;
     const u32 *z0;       // [nsets+1] first leaf of set s
@@ -726,7 +739,7 @@ MAP_KERNEL(jump, JumpArgs, 16)
 
 // per block: its sort keys and its positions (one per sequence of the set)
 struct BlockKeyArgs {
-    BatchView v; const u32 *sa; const u32 *idx0; const u32 *flag0; const u32 *dfs; u32 N0;
+    BatchView v; const u32 *sa; const u32 *saidx0; const u32 *z0; const u32 *dfs; u32 N0;
     const u32 *blk_lb; const u32 *blk_depth; const u32 *blk_set;
     u64 *keys; u32 *vals; int pass; // pass 0: dfs descending; pass 1: (set, depth descending)
 };
@@ -736,8 +749,13 @@ HD void blockkey_body(long long b, const BlockKeyArgs &a) {
         u32 s = a.blk_set[b];
         u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
         u32 d = 0;
+        const u32 k0 = LDG(a.v.set_seq0 + s), z = LDG(a.z0 + s), n0 = LDG(a.z0 + s + 1) - z;
         for (u32 j = lb; j < lb + m; j++)
-            if (a.flag0[j]) d = a.dfs[a.N0 + a.idx0[j]];
+            if (seq_of(a.v, a.sa[j]) == k0) { // the block's place in sequence 0: its leaf = the one with SA place j
+                u32 lo = 0, hi = n0;
+                while (lo < hi) { u32 mid = (lo + hi) >> 1; if (a.saidx0[z + mid] < j) lo = mid + 1; else hi = mid; }
+                d = a.dfs[a.N0 + z + lo];
+            }
         a.keys[b] = 0xFFFFFFFFu - d;
         a.vals[b] = (u32)b;
     } else {
@@ -1275,37 +1293,39 @@ HD void tile_body(long long t, const TileArgs &a) {
 MAP_KERNEL(tile, TileArgs, 8)
 
 // largest group of equal h-prefixes: the last suffix of a group is as far from its head as the group is long
-// (pairs != nullptr: also the number of pairs of suffixes that share a group -- what the word sort would compare)
+// (pairs != nullptr: also pairs[0] = the number of pairs of suffixes that share a group -- what the word sort would
+// compare -- and pairs[1] = the number of suffixes that share a group)
 struct MaxGroupArgs { const u32 *head; u32 *maxgroup; u32 N; unsigned long long *pairs; };
 #ifdef CSA_EMU
 HD void maxgroup_body(long long i, const MaxGroupArgs &a) {
     if ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1) {
         u32 sz = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
         if (sz > *a.maxgroup) *a.maxgroup = sz;
-        if (a.pairs) *a.pairs += (unsigned long long)sz * (sz - 1) / 2;
+        if (a.pairs) { a.pairs[0] += (unsigned long long)sz * (sz - 1) / 2; if (sz > 1) a.pairs[1] += sz; }
     }
 }
 MAP_KERNEL(maxgroup, MaxGroupArgs, 4)
 #else
 __global__ void __launch_bounds__(256) k_maxgroup(long long n, MaxGroupArgs a) {
     __shared__ u32 s_max;
-    __shared__ unsigned long long s_pairs;
-    if (threadIdx.x == 0) { s_max = 0; s_pairs = 0; }
+    __shared__ unsigned long long s_pairs, s_shared;
+    if (threadIdx.x == 0) { s_max = 0; s_pairs = 0; s_shared = 0; }
     __syncthreads();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     u32 sz = 0;
     if (i < n && ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1)) sz = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
     unsigned long long pr = sz > 1 ? (unsigned long long)sz * (sz - 1) / 2 : 0ull;
     if (a.pairs) { // one atomic per CTA: same-address atomics serialise in L2
+        u32 sh = sz > 1 ? sz : 0u;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, d);
-        if ((threadIdx.x & 31) == 0 && pr) atomicAdd(&s_pairs, pr);
+        for (int d = 16; d > 0; d >>= 1) { pr += __shfl_xor_sync(0xffffffffu, pr, d); sh += __shfl_xor_sync(0xffffffffu, sh, d); }
+        if ((threadIdx.x & 31) == 0 && pr) { atomicAdd(&s_pairs, pr); atomicAdd(&s_shared, (unsigned long long)sh); }
     }
     sz = __reduce_max_sync(0xffffffffu, sz);
     if ((threadIdx.x & 31) == 0 && sz) atomicMax(&s_max, sz);
     __syncthreads();
     if (threadIdx.x == 0 && s_max) atomicMax(a.maxgroup, s_max);
-    if (threadIdx.x == 0 && a.pairs && s_pairs) atomicAdd(a.pairs, s_pairs);
+    if (threadIdx.x == 0 && a.pairs && s_pairs) { atomicAdd(a.pairs, s_pairs); atomicAdd(a.pairs + 1, s_shared); }
 }
 static inline void launch_maxgroup(Exec &ex, long long n, MaxGroupArgs a) {
     if (n <= 0) return;
@@ -2216,7 +2236,7 @@ struct WSortArgs {
     u64 *big;  // groups too long for a warp's window (start : size), for k_wsort_big
     u32 nbig;  // (k_wsort_big) entries of big
     u32 *res;  // [0] groups left, [1] suffixes in them, [2] fewest letters a left group shares, [3] largest left group,
-               // [4] suffixes handled, [5] entries of big
+               // [4] unused, [5] entries of big
 };
 
 // 32 letters as a number that compares like the letters do: first letter in the top bits
@@ -2293,7 +2313,6 @@ static inline void emu_wsort_group(const WSortArgs &a, u32 p, u32 e, u32 Lend) {
         for (u32 h = a.L0; h < Lend; h++) it.s.push_back(v.code[cyc_add(v, it.g, h)]);
         items.push_back(std::move(it));
     }
-    a.res[4] += (u32)items.size();
     std::stable_sort(items.begin(), items.end(), [](const It &x, const It &y) { return x.s < y.s; });
     u32 hd = p;
     for (u32 x = p; x <= e; x++) {
@@ -2440,10 +2459,34 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
                 busy = false;
                 continue;
             }
-            const u64 wa = fetch2(a.v.p2, xa + L), wb = fetch2(a.v.p2, xb + L);
-            const u64 d2 = wa ^ wb;
+            u64 wa, wb, d2;
             u32 ma = 0, mb = 0, dm = 0;
-            if (MASKS) { ma = fetchm(a.v.pm, xa + L); mb = fetchm(a.v.pm, xb + L); dm = ma ^ mb; }
+            if (L + 128u <= Lmax) { // four words a side at once: ten independent loads, then up to four compares
+                const u64 ya = xa + L, yb = xb + L;
+                const u64 *pa = a.v.p2 + (ya >> 5), *pb = a.v.p2 + (yb >> 5);
+                const unsigned sha = (unsigned)(ya & 31u) * 2u, shb = (unsigned)(yb & 31u) * 2u;
+                u64 A[5], Bq[5];
+#pragma unroll
+                for (int q = 0; q < 5; q++) { A[q] = LDG(pa + q); Bq[q] = LDG(pb + q); }
+                int hit = -1;
+                wa = wb = d2 = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (hit < 0) {
+                        const u64 ua = sha ? (A[q] >> sha) | (A[q + 1] << (64u - sha)) : A[q];
+                        const u64 ub = shb ? (Bq[q] >> shb) | (Bq[q + 1] << (64u - shb)) : Bq[q];
+                        u32 va = 0, vb = 0;
+                        if (MASKS) { va = fetchm(a.v.pm, ya + 32u * q); vb = fetchm(a.v.pm, yb + 32u * q); }
+                        if ((ua ^ ub) | (u64)(va ^ vb)) { hit = q; wa = ua; wb = ub; d2 = ua ^ ub; ma = va; mb = vb; dm = va ^ vb; }
+                    }
+                }
+                if (hit < 0) { L += 128u; continue; }
+                L += 32u * (u32)hit;
+            } else {
+                wa = fetch2(a.v.p2, xa + L); wb = fetch2(a.v.p2, xb + L);
+                d2 = wa ^ wb;
+                if (MASKS) { ma = fetchm(a.v.pm, xa + L); mb = fetchm(a.v.pm, xb + L); dm = ma ^ mb; }
+            }
             if (d2 | dm) {
                 u32 f = d2 ? (u32)ctz64(d2) >> 1 : 32u;
                 if (MASKS && dm) { const u32 fm = (u32)ctz32(dm); f = fm < f ? fm : f; }
@@ -2469,12 +2512,10 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
         }
     }
     Team::sync();
-    u32 handled = 0;
 #pragma unroll
     for (int j = 0; j < WS_T; j++) {
         if (act[j]) {
             const u32 t = tid + TT * j;
-            handled++;
             a.sa[base + np[j]] = s.g[t];
             a.head[base + np[j]] = base + nh[j];
             if (np[j] == nh[j]) {
@@ -2489,8 +2530,6 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
             }
         }
     }
-    handled = __reduce_add_sync(0xffffffffu, handled);
-    if ((tid & 31u) == 0 && handled) atomicAdd(a.res + 4, handled);
 }
 
 template <bool MASKS>
