@@ -2224,6 +2224,7 @@ static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
 #define WS_WARPS 8   // warps (= chunks) per CTA of k_wsort
 #define WS_BIG_WARPS 8
 #define WS_BIG_CAP (32 * WS_BIG_WARPS * WS_T)
+#define WS_STEP 4    // words (of 32 letters) a pair compares per round trip
 #define WS_DEPTH_CAP 4096u
 #define WS_PAIRS_PER_SUFFIX 3.0 // the word sort is chosen when the groups of the first sort hold fewer pairs than this per suffix
 #define LCP_UNKNOWN 0xFFFFFFFFu
@@ -2406,15 +2407,16 @@ template <int WARPS> struct WsSmem {
     u32 ct[CAP];                // low half: suffixes of its group that are smaller; high half: equal ones that stood before it
     u32 best[CAP];              // most letters shared with a smaller one = LCP with its predecessor
     u32 clsz[CAP];              // (by new place) suffixes that are still together there
+    u32 pre[CAP + 1];           // pairs that the places before t bring (running sum); [CAP] = all pairs of the chunk
     unsigned short seg[CAP];    // first place of its group
     unsigned short end[CAP];    // place after the last of its group
 };
 
-// Every pair of suffixes of a group is compared once, word by word from letter L0 on, by whichever
-// thread's list it is on (suffix i of a group of g meets i+1 .. i+(g-1)/2 round the group, so every
-// suffix brings the same number of pairs).  A thread walks its list on its own: lanes are in different
-// pairs at different depths and never wait for one another -- no ballot, no barrier until the lists are
-// done.  What a pair tells: the smaller suffix counts towards the larger one's place, and the letters they
+// Every pair of suffixes of a group is compared once, word by word from letter L0 on (suffix i of a group
+// of g brings the pairs with i+1 .. i+(g-1)/2 round the group).  The pairs of the whole chunk are numbered
+// through a running sum and dealt out to the threads in turn, so every lane has work whichever places hold
+// the groups; a thread walks its pairs on its own: lanes are in different pairs at different depths and
+// never wait for one another -- no ballot, no barrier until all pairs are done.  What a pair tells: the smaller suffix counts towards the larger one's place, and the letters they
 // share bound the larger one's LCP from below (its predecessor is the smaller suffix it shares most
 // with).  Pairs that agree up to the depth limit count as equal (place by old order; the doubling rounds
 // finish them).  On entry: x, g, seg, end set and ct = best = clsz = 0 for every place with act[j].
@@ -2425,32 +2427,50 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
     constexpr u32 TT = 32u * WARPS;
     const u32 L0 = a.L0;
     const u32 Lend = Lmax >= L0 ? L0 + ((Lmax - L0) & ~31u) : L0; // pairs that agree on [L0, Lend) count as equal
-    unsigned actbits = 0;
+    constexpr u32 CAP = (u32)WsSmem<WARPS>::CAP, PER = CAP / 32u;
 #pragma unroll
-    for (int j = 0; j < WS_T; j++) actbits |= act[j] ? 1u << j : 0u;
+    for (int j = 0; j < WS_T; j++) { // pairs brought by every place
+        const u32 t = tid + TT * j;
+        u32 nd = 0;
+        if (act[j]) {
+            const u32 hs = s.seg[t], g = (u32)s.end[t] - hs, i = t - hs;
+            nd = (g - 1u) / 2u + (((g & 1u) == 0u && i < g / 2u) ? 1u : 0u);
+        }
+        s.pre[t] = nd;
+    }
+    Team::sync();
+    if (tid < 32u) { // running sum over the places (first warp of the team)
+        u32 sum = 0;
+#pragma unroll
+        for (u32 q = 0; q < PER; q++) sum += s.pre[tid * PER + q];
+        u32 incl = sum;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, dd); if (tid >= (u32)dd) incl += o; }
+        u32 run = incl - sum;
+#pragma unroll
+        for (u32 q = 0; q < PER; q++) { const u32 v = s.pre[tid * PER + q]; s.pre[tid * PER + q] = run; run += v; }
+        if (tid == 31u) s.pre[CAP] = incl;
+    }
+    Team::sync();
     {
-        int j = -1;
-        u32 t = 0, hs = 0, g = 0, i = 0, d = 0, nd = 0, pb = 0, L = 0;
+        const u32 P = s.pre[CAP];
+        u32 p = tid, t = 0, pb = 0, L = 0;
         u64 xa = 0, xb = 0;
         bool busy = false;
         for (;;) {
-            if (!busy) { // next pair of my list
-                while (d == nd) {
-                    if (++j >= WS_T) break;
-                    if (!(actbits >> j & 1u)) continue;
-                    t = tid + TT * (u32)j;
-                    hs = s.seg[t]; g = (u32)s.end[t] - hs; i = t - hs;
-                    nd = (g - 1u) / 2u + (((g & 1u) == 0u && i < g / 2u) ? 1u : 0u);
-                    d = 0;
-                    xa = s.x[t];
-                }
-                if (j >= WS_T) break;
-                d++;
-                u32 i2 = i + d;
+            if (!busy) { // my next pair: the place that brings pair p = the last one whose running sum is <= p
+                if (p >= P) break;
+                u32 lo = 0, hi = CAP;
+                while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (s.pre[mid] <= p) lo = mid; else hi = mid; }
+                t = lo;
+                const u32 hs = s.seg[t], g = (u32)s.end[t] - hs;
+                u32 i2 = t - hs + (p - s.pre[t] + 1u);
                 if (i2 >= g) i2 -= g;
                 pb = hs + i2;
+                xa = s.x[t];
                 xb = s.x[pb];
                 L = L0;
+                p += TT;
                 busy = true;
             }
             // one word of the pair (t, pb)
@@ -2461,17 +2481,17 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
             }
             u64 wa, wb, d2;
             u32 ma = 0, mb = 0, dm = 0;
-            if (L + 128u <= Lmax) { // four words a side at once: ten independent loads, then up to four compares
+            if (L + 32u * WS_STEP <= Lmax) { // WS_STEP words a side at once: independent loads, one round trip to L2
                 const u64 ya = xa + L, yb = xb + L;
                 const u64 *pa = a.v.p2 + (ya >> 5), *pb = a.v.p2 + (yb >> 5);
                 const unsigned sha = (unsigned)(ya & 31u) * 2u, shb = (unsigned)(yb & 31u) * 2u;
-                u64 A[5], Bq[5];
+                u64 A[WS_STEP + 1], Bq[WS_STEP + 1];
 #pragma unroll
-                for (int q = 0; q < 5; q++) { A[q] = LDG(pa + q); Bq[q] = LDG(pb + q); }
+                for (int q = 0; q <= WS_STEP; q++) { A[q] = LDG(pa + q); Bq[q] = LDG(pb + q); }
                 int hit = -1;
                 wa = wb = d2 = 0;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int q = 0; q < WS_STEP; q++) {
                     if (hit < 0) {
                         const u64 ua = sha ? (A[q] >> sha) | (A[q + 1] << (64u - sha)) : A[q];
                         const u64 ub = shb ? (Bq[q] >> shb) | (Bq[q + 1] << (64u - shb)) : Bq[q];
@@ -2480,7 +2500,7 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
                         if ((ua ^ ub) | (u64)(va ^ vb)) { hit = q; wa = ua; wb = ub; d2 = ua ^ ub; ma = va; mb = vb; dm = va ^ vb; }
                     }
                 }
-                if (hit < 0) { L += 128u; continue; }
+                if (hit < 0) { L += 32u * WS_STEP; continue; }
                 L += 32u * (u32)hit;
             } else {
                 wa = fetch2(a.v.p2, xa + L); wb = fetch2(a.v.p2, xb + L);

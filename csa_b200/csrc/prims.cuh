@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K *__restrict__ ke
 }
 
 template <class K>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const K *__restrict__ keys, const u32 *__restrict__ vals,
+__global__ void __launch_bounds__(RS_THREADS, 4) k_rs_scatter(const K *__restrict__ keys, const u32 *__restrict__ vals,
                                                            K *__restrict__ keys_out, u32 *__restrict__ vals_out,
                                                            const u32 *__restrict__ offsets, long long n, int shift, RsSeg seg) {
     __shared__ u32 h[RS_WARPS][RS_BINS];
