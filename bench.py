@@ -45,8 +45,9 @@ def env_int(name, default):
 
 # ---- clocks during the timed region ---------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons while the timed steps run: NVML polled every ~2 ms from a thread
-    (the timed region of a short run is shorter than one `nvidia-smi -lms` period)."""
+    """SM clock and throttle reasons while the timed steps run: NVML polled every ~10 ms from a thread
+    (the timed region of a short run is shorter than one `nvidia-smi -lms` period; polling faster than
+    this steals time from the launching thread when eight ranks share the host)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, cuda_index):
@@ -74,7 +75,7 @@ class ClockSampler:
                                      nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.010)
 
     def start(self):
         if self.h is not None:
@@ -141,7 +142,7 @@ def cpu_reference_rate(sets, cores):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="mammals", choices=list(DEFAULT_SETS))
@@ -265,6 +266,10 @@ def main():
     e2e_ms = allmax(e2.elapsed_time(e3))
     rf.unpin(pinned)
     assert np.array_equal(rot, rot2)
+    if buckets:  # the bucket-sharded run against the same set on this GPU alone
+        rf.upload(batch); rf.run()
+        rot3, _ = rf.download()
+        assert np.array_equal(rot, rot3), "bucket-sharded rotations differ from the single-GPU run"
     h2d = batch.nbases + 4 * (2 * batch.nseqs + 4 * batch.nsets + 8) + 8 * (batch.nseqs + 1)
     d2h = 4 * batch.nseqs + 3 * 4 * batch.nsets
     e2e_value = total_bases / (e2e_ms / 1e3)

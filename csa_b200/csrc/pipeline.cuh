@@ -2225,7 +2225,7 @@ static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
 #define WS_BIG_WARPS 8
 #define WS_BIG_CAP (32 * WS_BIG_WARPS * WS_T)
 #define WS_STEP 4    // words (of 32 letters) a pair compares per round trip
-#define WS_DEPTH_CAP 4096u
+#define WS_DEPTH_CAP 32768u // letters a pair is followed; pairs that agree for longer are finished by the doubling rounds
 #define WS_PAIRS_PER_SUFFIX 3.0 // the word sort is chosen when the groups of the first sort hold fewer pairs than this per suffix
 #define LCP_UNKNOWN 0xFFFFFFFFu
 
