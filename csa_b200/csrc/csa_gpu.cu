@@ -53,7 +53,8 @@ struct csa_gpu_ctx {
     int lcp_state = 0;          // after the suffix array stage: 0 nothing known, 1 every LCP known, 2 all but the LCP_UNKNOWN places
     int ws_runs = 0, ws_force = 0; double ws_pairs = 0, ws_sharing = 0;
     u32 sa_any_other = 1, sa_ngroups = 0;
-    int shard_rank = 0, shard_nranks = 1, shard_phase = 0;
+    int shard_rank = 0, shard_nranks = 1, shard_phase = 0, shard_full_sort = 0; bool shard_own_sort = false;
+    DevMem bk_hist;
     DevMem shard_bounds; std::vector<u32> h_shard_bounds;
     DevMem chb_sets, chb_evbase, chb_events, chb_work, chb_redo;
     int no_chain_big = 0, chain_redone = 0; u32 ws_depth_cap = WS_DEPTH_CAP; u32 ws_left[6] = {0, 0, 0, 0, 0, 0};
@@ -136,7 +137,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
                      &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
-                     &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->chb_sets, &c->chb_evbase, &c->chb_events, &c->chb_work, &c->chb_redo, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
+                     &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->bk_hist, &c->chb_sets, &c->chb_evbase, &c->chb_events, &c->chb_work, &c->chb_redo, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
                      &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
@@ -345,7 +346,7 @@ static int heads_and_ranks(csa_gpu_ctx *c, u32 *head, u32 *rank, u32 *counter, u
     u32 N = c->N;
     TRY(dev_zero(ex, counter, sizeof(u32)));
     { FlagArgs a{P<u64>(c->keysA), keys32 ? P<u32>(c->keysA) : nullptr, head, counter, lcp, letters, lbits,
-                 P<u32>(c->valsA), P<u32>(c->seqof), P<u32>(c->seq_off), c->batch_nmin < (u32)letters ? 1 : 0}; launch_flag(ex, N, a); }
+                 P<u32>(c->valsA), P<u32>(c->seqof), P<u32>(c->seq_off), c->batch_nmin < (u32)letters ? 1 : 0, 0u}; launch_flag(ex, N, a); }
     if (fix_set_starts) { SetStartArgs a{view_of(c), head, counter, lcp}; launch_setstart(ex, c->nsets, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, head, head, N)));
     if (rank) { SetRankArgs a{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, a); }
@@ -369,7 +370,58 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     u32 ngroups = c->sa_ngroups, maxg = 0;
     bool words = true;
     u32 *lcp = P<u32>(c->t5);
-    if (phase != 2) {
+    // a job of several ranks on ONE set: every rank sorts only its own bucket (ranges of the key's first 6 letters)
+    const bool own_sort = phase == 1 && c->nsets == 1 && c->shard_nranks > 1 && !c->shard_full_sort;
+    if (phase == 1) c->shard_own_sort = own_sort;
+    if (own_sort) {
+        const int R = c->shard_nranks, kbits = letters * lbits, shift = kbits - BK_BITS;
+        { InitKeyArgs a{v, any_other ? P<u64>(c->keysB) : nullptr, any_other ? nullptr : P<u32>(c->keysB), P<u32>(c->valsB)};
+          launch_initkey(ex, N, a); }
+        TRY(dev_alloc(c->bk_hist, sizeof(u32) * BK_BINS));
+        TRY(dev_zero(ex, c->bk_hist.p, sizeof(u32) * BK_BINS));
+        BucketArgs b{any_other ? P<u64>(c->keysB) : nullptr, any_other ? nullptr : P<u32>(c->keysB), P<u32>(c->valsB), N, shift,
+                     P<u32>(c->bk_hist), 0u, 0u, P<u32>(c->t0), P<u32>(c->t1), nullptr, nullptr, nullptr};
+        launch_bkhist(ex, N, b);
+        std::vector<u32> h(BK_BINS), cut(R + 1, (u32)BK_BINS);
+        TRY(d2h(ex, h.data(), c->bk_hist.p, sizeof(u32) * BK_BINS));
+        c->h_shard_bounds.assign(R + 1, N);
+        cut[0] = 0; c->h_shard_bounds[0] = 0;
+        {   // bucket r starts at the first prefix whose suffixes begin at or after r * N / R
+            u64 cum = 0;
+            int r = 1;
+            for (u32 p = 0; p < (u32)BK_BINS && r < R; p++) {
+                while (r < R && cum >= (u64)r * N / R) { cut[r] = p; c->h_shard_bounds[r] = (u32)cum; r++; }
+                cum += h[p];
+            }
+        }
+        const u32 off = c->h_shard_bounds[c->shard_rank], n_r = c->h_shard_bounds[c->shard_rank + 1] - off;
+        b.plo = cut[c->shard_rank]; b.phi = cut[c->shard_rank + 1];
+        b.out64 = P<u64>(c->keysA) + off; b.out32 = P<u32>(c->keysA) + off; b.outv = P<u32>(c->valsA) + off;
+        launch_bkflag(ex, N, b);
+        TRY((scan_u32<ScanSum, false>(ex, c->ps, P<u32>(c->t0), P<u32>(c->t1), N)));
+        launch_bkscatter(ex, N, b);
+        if (any_other) {
+            u64 *k = P<u64>(c->keysA) + off, *ka = P<u64>(c->keysB) + off;
+            u32 *vv = P<u32>(c->valsA) + off, *va = P<u32>(c->valsB) + off;
+            TRY(radix_sort_pairs<u64>(ex, c->ps, k, vv, ka, va, n_r, 0, kbits));
+            if (vv != P<u32>(c->valsA) + off) { std::swap(c->keysA, c->keysB); std::swap(c->valsA, c->valsB); }
+        } else {
+            u32 *k = P<u32>(c->keysA) + off, *ka = P<u32>(c->keysB) + off;
+            u32 *vv = P<u32>(c->valsA) + off, *va = P<u32>(c->valsB) + off;
+            TRY(radix_sort_pairs<u32>(ex, c->ps, k, vv, ka, va, n_r, 0, kbits));
+            if (vv != P<u32>(c->valsA) + off) { std::swap(c->keysA, c->keysB); std::swap(c->valsA, c->valsB); }
+        }
+        TRY(dev_fill_ff(ex, lcp, sizeof(u32) * (size_t)N));
+        TRY(dev_zero(ex, counter, sizeof(u32)));
+        { FlagArgs a{P<u64>(c->keysA) + off, any_other ? nullptr : P<u32>(c->keysA) + off, head + off, counter, lcp + off, letters, lbits,
+                     P<u32>(c->valsA) + off, P<u32>(c->seqof), P<u32>(c->seq_off), c->batch_nmin < (u32)letters ? 1 : 0, off};
+          launch_flag(ex, n_r, a); }
+        TRY((scan_u32<ScanMax, true>(ex, c->ps, head + off, head + off, n_r)));
+        ngroups = 0; // (not counted: the word sort looks at every group of the bucket anyway)
+        c->sa_ngroups = 0;
+        c->lcp_state = 0; c->ws_runs = 0;
+        c->rounds_tiled = c->rounds_global = c->rounds_quad = c->rounds_list = 0;
+    } else if (phase != 2) {
     RsSeg seg{P<u32>(c->rs_start), P<u32>(c->rs_count), P<u32>(c->rs_cbase), P<u32>(c->rs_stride), c->rs_nblocks,
               P<u32>(c->set_base0), (u32)c->nsets};
     { InitKeyArgs a{v, any_other ? P<u64>(c->keysA) : nullptr, any_other ? nullptr : P<u32>(c->keysA), P<u32>(c->valsA)};
@@ -432,7 +484,7 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     };
     if (words) {
         c->lcp_state = 1;
-        if (phase == 1) { // this rank's bucket: borders at group borders, the same on every rank
+        if (phase == 1 && !own_sort) { // this rank's bucket: borders at group borders, the same on every rank
             BoundsArgs b{head, N, (u32)c->shard_nranks, P<u32>(c->shard_bounds)};
             launch_bounds(ex, b);
             c->h_shard_bounds.assign(c->shard_nranks + 1, 0);
@@ -472,6 +524,11 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
                 list_valid = true;
                 c->lcp_state = active_est <= N / 8 ? 2 : 0;
             }
+        }
+        if (phase == 2 && c->shard_own_sort) { // what two neighbouring buckets share at their border: no rank has seen both keys
+            for (int r = 1; r < c->shard_nranks; r++)
+                if (c->h_shard_bounds[r] > 0 && c->h_shard_bounds[r] < N) TRY(dev_fill_ff(ex, lcp + c->h_shard_bounds[r], sizeof(u32)));
+            if (c->lcp_state == 1) c->lcp_state = 2;
         }
     }
     while (ngroups != N && sorted_len < 2ull * c->nmax) {
@@ -898,7 +955,8 @@ extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds
         c->ws_depth_cap = force_global == 4 ? 80u : WS_DEPTH_CAP;
         c->ws_force = force_global == 6; // 6: word sort whatever the groups look like
         c->no_chain_big = force_global == 7; // 7: free choice, but long block lists walked by one thread (k_chain) as short ones are
-        if (force_global == 6 || force_global == 7) c->round_mode = 0;
+        c->shard_full_sort = force_global == 8; // 8: sharded runs of one set sort the whole set on every rank (as batches of sets do)
+        if (force_global >= 6) c->round_mode = 0;
         c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; c->force_kasai = force_global == 2;
     }
     if (rounds) { rounds[0] = c->rounds_tiled + c->rounds_quad + c->rounds_list + c->ws_runs; rounds[1] = c->rounds_global; }

@@ -139,7 +139,8 @@ MAP_KERNEL(initkey, InitKeyArgs, 21)
 // head[i] = i where a new group of equal keys starts, else 0 (max-scanned afterwards)
 // With lcp != nullptr (first sort only) a border also gets its LCP: the letters the two keys share.
 struct FlagArgs { const u64 *keys; const u32 *keys32; u32 *head; u32 *ngroups; u32 *lcp; int letters; int lbits;
-                  const u32 *sa; const u32 *seqof; const u32 *seq_off; int clamp; };
+                  const u32 *sa; const u32 *seqof; const u32 *seq_off; int clamp;
+                  u32 base; }; // the arrays start at SA place `base` (a bucket of a sharded run), heads are SA places
 HD bool flag_differs(const FlagArgs &a, long long i) {
     return a.keys32 ? a.keys32[i] != a.keys32[i - 1] : a.keys[i] != a.keys[i - 1];
 }
@@ -160,7 +161,7 @@ HD void flag_lcp(const FlagArgs &a, long long i) { // keys differ (or i == 0): f
 #ifdef CSA_EMU
 HD void flag_body(long long i, const FlagArgs &a) {
     bool f = (i == 0) || flag_differs(a, i);
-    a.head[i] = f ? (u32)i : 0u;
+    a.head[i] = f ? a.base + (u32)i : 0u;
     if (f && a.lcp) flag_lcp(a, i);
     COUNT_IF(a.ngroups, f);
 }
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(256) k_flag(long long n, FlagArgs a) {
     bool f = false;
     if (i < n) {
         f = (i == 0) || flag_differs(a, i);
-        a.head[i] = f ? (u32)i : 0u;
+        a.head[i] = f ? a.base + (u32)i : 0u;
         if (f && a.lcp) flag_lcp(a, i);
     }
     int c = __syncthreads_count(f);
@@ -2281,6 +2282,50 @@ HD u32 ws_common(u64 ka, u32 ma, u64 kb, u32 mb) { // letters the two words shar
     return pk < pm ? pk : pm;
 }
 
+// ---- sharded run of ONE set: every rank sorts only the suffixes of its bucket ----------------------------------
+// Buckets are ranges of the first 6 letters of the sort key (4096 prefixes): a histogram of the prefixes, the same
+// on every rank, fixes the cut points and with them every bucket's place in the suffix array; a rank then keeps
+// the (key, suffix) pairs of its prefixes -- in text order, the sort must stay stable -- and sorts those alone.
+#define BK_BITS 12
+#define BK_BINS (1 << BK_BITS)
+struct BucketArgs {
+    const u64 *keys64; const u32 *keys32; const u32 *vals; u32 N; int shift; // prefix = key >> shift
+    u32 *hist;                       // k_bkhist: [BK_BINS]
+    u32 plo, phi;                    // k_bkflag / k_bkscatter: this rank's prefixes [plo, phi)
+    u32 *flag; const u32 *idx; u64 *out64; u32 *out32; u32 *outv;
+};
+HD u32 bk_prefix(const BucketArgs &a, long long i) { return a.keys32 ? (a.keys32[i] >> a.shift) : (u32)(a.keys64[i] >> a.shift); }
+HD void bkflag_body(long long i, const BucketArgs &a) { const u32 p = bk_prefix(a, i); a.flag[i] = (p >= a.plo && p < a.phi) ? 1u : 0u; }
+MAP_KERNEL(bkflag, BucketArgs, 8)
+HD void bkscatter_body(long long i, const BucketArgs &a) {
+    const u32 p = bk_prefix(a, i);
+    if (p < a.plo || p >= a.phi) return;
+    const u32 q = a.idx[i];
+    if (a.keys32) a.out32[q] = a.keys32[i]; else a.out64[q] = a.keys64[i];
+    a.outv[q] = a.vals[i];
+}
+MAP_KERNEL(bkscatter, BucketArgs, 12)
+#ifdef CSA_EMU
+HD void bkhist_body(long long i, const BucketArgs &a) { a.hist[bk_prefix(a, i)]++; }
+MAP_KERNEL(bkhist, BucketArgs, 4)
+#else
+__global__ void __launch_bounds__(256) k_bkhist(BucketArgs a) { // counts in shared memory, one flush per CTA
+    __shared__ u32 h[BK_BINS];
+    for (u32 i = threadIdx.x; i < BK_BINS; i += 256) h[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.N; i += (long long)gridDim.x * 256) atomicAdd(&h[bk_prefix(a, i)], 1u);
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < BK_BINS; i += 256) if (h[i]) atomicAdd(a.hist + i, h[i]);
+}
+static inline void launch_bkhist(Exec &ex, long long n, BucketArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_bkhist", (a.keys32 ? 4.0 : 8.0) * n);
+    k_bkhist<<<148 * 4, 256, 0, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
+
 // bucket borders for a job of nranks ranks: the first group border at or after r * N / nranks
 struct BoundsArgs { const u32 *head; u32 N; u32 nranks; u32 *bounds; };
 HD void bounds_map_body(long long r, const BoundsArgs &a) {
@@ -2351,7 +2396,8 @@ static inline u32 emu_wsort_lend(const WSortArgs &a, u32 nmin) {
 static inline void launch_wsort(Exec &, const WSortArgs &a) {
     const BatchView &v = a.v;
     const u32 N = a.N;
-    auto border = [&](u64 p) { return p < N ? (a.head[p] & 0x7FFFFFFFu) == (u32)p : p == N; };
+    (void)N; // (heads beyond hi may belong to another rank's bucket and not be there yet: hi itself is a border)
+    auto border = [&](u64 p) { return p < a.hi ? (a.head[p] & 0x7FFFFFFFu) == (u32)p : p == a.hi; };
     for (u64 r0 = a.lo & ~31u; r0 < a.hi; r0 += WS_NOM) {
         // groups that start in [r0, r0+WS_NOM) and end at or before place r0 + WS_CAP - 1
         std::vector<std::pair<u32, u32>> groups;
@@ -2559,7 +2605,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const u64 r0_64 = (u64)(a.lo & ~31u) + ((u64)blockIdx.x * WS_WARPS + warp) * WS_NOM;
     if (r0_64 >= a.hi) return;
-    const u32 r0 = (u32)r0_64, N = a.N;
+    const u32 r0 = (u32)r0_64, N = a.hi; // (heads beyond hi may be another rank's and not there yet: hi itself is a border)
     WsSmem<1> &s = s_all[warp];
     // ---- the window: heads of WS_CAP places, borders as a bit set ----
     u32 hv[WS_T], bw[WS_T];

@@ -44,9 +44,12 @@ dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 rng = random.Random(77)
 rf = RotationFinder(lib_path=EMU_LIB)
-for trial in range(6):
-    sets = [gen_case(rng, max_n=1500)[1] for _ in range(rng.randint(1, 4))]
-    rf.debug_rounds(4 if trial % 2 else 0)   # odd trials: the bucket sorts stop early and leave groups to the doubling rounds
+for trial in range(8):
+    # trials 0-3: ONE set (every rank sorts only its own bucket of key prefixes; trial 3: the whole set on every rank);
+    # later trials: batches of sets (first sort on every rank, buckets cut at group borders)
+    sets = [gen_case(rng, max_n=1500)[1] for _ in range(1 if trial < 4 else rng.randint(2, 4))]
+    mode = 8 if trial == 3 else (4 if trial % 2 else 0)   # 4: the bucket sorts stop early and leave groups to the doubling rounds
+    rf.debug_rounds(mode)
     batch = Batch(sets)
     rf.upload(batch)
     bounds = run_bucket_sharded(rf, rank, world, dist, cuda=False)
@@ -61,7 +64,7 @@ for trial in range(6):
         off += n
     rf.debug_rounds(0)
     ref = rf.find_rotations_batch(batch)          # the same batch on one rank alone
-    rf.debug_rounds(4 if trial % 2 else 0)
+    rf.debug_rounds(mode)
     rf.upload(batch)
     run_bucket_sharded(rf, rank, world, dist, cuda=False)
     rot, info = rf.download()
