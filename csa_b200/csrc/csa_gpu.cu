@@ -780,13 +780,15 @@ static int stage_chain(csa_gpu_ctx *c, const BatchView &v, int max_interval) {
         if (!big.empty() && nev < (1ull << 32) && !c->no_chain_big) {
             a.skip_big = 1;
             TRY(dev_alloc(c->chb_sets, sizeof(u32) * big.size())); TRY(dev_alloc(c->chb_evbase, sizeof(u32) * big.size()));
-            TRY(dev_alloc(c->chb_events, sizeof(u64) * (size_t)nev)); TRY(dev_alloc(c->chb_work, 4 * nb));
+            TRY(dev_alloc(c->chb_events, sizeof(u64) * (size_t)nev)); TRY(dev_alloc(c->chb_work, 9 * nb));
             TRY(dev_alloc(c->chb_redo, sizeof(u32) * (nsets + 1)));
             TRY(h2d(ex, c->chb_sets.p, big.data(), sizeof(u32) * big.size()));
             TRY(h2d(ex, c->chb_evbase.p, evb.data(), sizeof(u32) * big.size()));
             TRY(dev_zero(ex, c->chb_redo.p, sizeof(u32) * (nsets + 1)));
             ChainBigArgs g{a, P<u32>(c->chb_sets), P<unsigned long long>(c->chb_events), P<u32>(c->chb_evbase),
                            P<int>(c->chb_work), P<int>(c->chb_work) + B, P<int>(c->chb_work) + 2 * (size_t)B, P<u32>(c->chb_work) + 3 * (size_t)B,
+                           P<u32>(c->chb_work) + 4 * (size_t)B, P<u32>(c->chb_work) + 5 * (size_t)B, P<u32>(c->chb_work) + 6 * (size_t)B,
+                           P<u32>(c->chb_work) + 7 * (size_t)B, P<u32>(c->chb_work) + 8 * (size_t)B,
                            P<u32>(c->chb_redo)};
             TRY(launch_chain_big(ex, (u32)big.size(), 3 * (size_t)maxb + 16, g));
         }

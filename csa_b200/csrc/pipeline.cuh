@@ -993,7 +993,7 @@ static inline void launch_chain(Exec &ex, long long nsets, ChainArgs a) {
 //   4. the two places where the control flow looks at a SUM (total[c] > 0 at :201 for a finished head, and for
 //      the walk's own head when a circular chain closes) were taken as true in 1. and are checked now; a set
 //      that fails the check (never seen: every term depth + gap is positive) is redone by the literal walk.
-#define CHB_THREADS 256
+#define CHB_THREADS 1024
 #define CHB_ABS 1u    // total == -1: taken by some walk
 #define CHB_HEAD 2u   // has finished its own walk
 struct ChainBigArgs {
@@ -1001,11 +1001,12 @@ struct ChainBigArgs {
     const u32 *sets; // the sets this launch handles
     unsigned long long *events; u32 *ev_base; // per set: first event slot; capacity 4 * blocks
     int *wS, *wT, *wchild; u32 *wdone;        // per block scratch
+    u32 *wpred, *wjump, *wmin, *wjump2, *wmin2; // per block scratch of the parallel walk order (jump/min double buffered)
     u32 *redo;                                // per set: 1 = the literal walk must redo it
 };
 __global__ void __launch_bounds__(CHB_THREADS) k_chain_big(ChainBigArgs a) {
     extern __shared__ unsigned char chb_dyn[];
-    __shared__ u32 s_nev, s_mcs, s_fail, s_hang;
+    __shared__ u32 s_nev, s_mcs, s_fail, s_hang, s_multi;
     const u32 s = a.sets[blockIdx.x];
     const u32 b0 = a.c.set_blk0[s], B = a.c.set_blk0[s + 1] - b0;
     unsigned short *nx = (unsigned short *)chb_dyn;
@@ -1014,7 +1015,7 @@ __global__ void __launch_bounds__(CHB_THREADS) k_chain_big(ChainBigArgs a) {
     const int *gap = a.c.gap + b0;
     int *size = a.c.size + b0, *total = a.c.total + b0, *interval = a.c.interval + b0;
     int *wS = a.wS + b0, *wT = a.wT + b0, *wchild = a.wchild + b0;
-    u32 *wdone = a.wdone + b0;
+    u32 *wdone = a.wdone + b0, *wpred = a.wpred + b0, *wjump = a.wjump + b0, *wmin = a.wmin + b0, *wjump2 = a.wjump2 + b0, *wmin2 = a.wmin2 + b0;
     unsigned long long *ev = a.events + a.ev_base[blockIdx.x];
     const u32 evcap = 4u * B;
     for (u32 i = threadIdx.x; i < B; i += CHB_THREADS) {
@@ -1022,11 +1023,61 @@ __global__ void __launch_bounds__(CHB_THREADS) k_chain_big(ChainBigArgs a) {
         nx[i] = n < 0 ? (unsigned short)0xFFFFu : (unsigned short)((u32)n - b0);
         st[i] = 0;
         wS[i] = 0; wT[i] = 0; wchild[i] = -1; wdone[i] = 0; // wS, wT: sums of depths / gaps of the walk that starts at i
+        wpred[i] = CSA_NONE;
     }
-    if (threadIdx.x == 0) { s_nev = 0; s_mcs = B; s_fail = 0; s_hang = 0; }
+    if (threadIdx.x == 0) { s_nev = 0; s_mcs = B; s_fail = 0; s_hang = 0; s_multi = 0; }
     __syncthreads();
-    // ---- 1. the order of the walks ----
-    if (threadIdx.x == 0) {
+    // ---- 1a. the usual shape: no block is the `next` of two others, the blocks form paths and rings ----
+    // Then the walk order needs no walking.  On a path, a block starts a walk iff its number is smaller than
+    // every number upstream of it (the outer loop of :185 reaches it before anything that could take it);
+    // every other block, and every such head but the first, is taken by the walk of the smallest number
+    // upstream.  On a ring the smallest number walks all the way round and closes on itself.  "Smallest
+    // number upstream" is a prefix minimum along the paths: pointer jumping, log2(blocks) rounds, all threads.
+    for (u32 i = threadIdx.x; i < B; i += CHB_THREADS)
+        if (nx[i] != 0xFFFFu && atomicCAS(&wpred[nx[i]], CSA_NONE, i) != CSA_NONE) s_multi = 1;
+    __syncthreads();
+    if (!s_multi) {
+        for (u32 i = threadIdx.x; i < B; i += CHB_THREADS) { wjump[i] = wpred[i]; wmin[i] = wpred[i]; }
+        __syncthreads();
+        u32 rounds = 1;
+        while ((1u << rounds) < B) rounds++;
+        for (u32 r = 0; r <= rounds; r++) { // a round reads the pointers of the round before only
+            bool moved = false;
+            for (u32 i = threadIdx.x; i < B; i += CHB_THREADS) {
+                const u32 j = wjump[i];
+                u32 mi = wmin[i], ji = CSA_NONE;
+                if (j != CSA_NONE) {
+                    const u32 mj = wmin[j];
+                    mi = mj < mi ? mj : mi;
+                    ji = wjump[j];
+                    moved = true;
+                }
+                wmin2[i] = mi; wjump2[i] = ji;
+            }
+            u32 *t1 = wjump; wjump = wjump2; wjump2 = t1;
+            u32 *t2 = wmin; wmin = wmin2; wmin2 = t2;
+            if (!__syncthreads_or(moved)) break;
+        }
+        u32 nev = 0;
+        for (u32 c = threadIdx.x; c < B; c += CHB_THREADS) {
+            const u32 pr = wpred[c];
+            if (pr == CSA_NONE) { st[c] = CHB_HEAD; continue; } // first block of a path
+            const int iv = gap[pr];
+            interval[pr] = iv;
+            nev++;
+            const bool ring = wjump[c] != CSA_NONE;
+            const u32 m = wmin[c]; // smallest number upstream (on a ring: of the whole ring, c included)
+            if (ring && m == c) { atomicAdd(&wT[c], iv); wchild[c] = -2 - (int)pr; st[c] = CHB_HEAD; }
+            else if (!ring && c < m) { atomicAdd(&wT[m], iv); wchild[m] = (int)c; st[c] = CHB_HEAD | CHB_ABS; }
+            else { atomicAdd(&wT[m], iv); atomicAdd(&wS[m], (int)depth[c]); st[c] = CHB_ABS; }
+        }
+        if (nev) atomicAdd(&s_nev, nev);
+        __syncthreads();
+        if (threadIdx.x == 0) s_mcs = B - s_nev;
+        __syncthreads();
+    }
+    // ---- 1b. any other shape: thread 0 replays the order of the walks, then 2. adds up ----
+    if (s_multi && threadIdx.x == 0) {
         u32 nev = 0, mcs = B;
         const long long guard_max = 4ll * B + 16;
         bool fail = false, hang = false;
@@ -1054,7 +1105,7 @@ __global__ void __launch_bounds__(CHB_THREADS) k_chain_big(ChainBigArgs a) {
         s_nev = nev; s_mcs = mcs; s_fail = fail ? 1u : 0u; s_hang = hang ? 1u : 0u;
     }
     __syncthreads();
-    if (s_hang || s_fail) {
+    if (s_multi && (s_hang || s_fail)) {
         if (threadIdx.x == 0) {
             if (s_hang) atomicMax(a.c.set_flags + s, 2u); else a.redo[s] = 1;
             a.c.set_nchains[s] = s_mcs;
@@ -1062,7 +1113,7 @@ __global__ void __launch_bounds__(CHB_THREADS) k_chain_big(ChainBigArgs a) {
         return;
     }
     // ---- 2. sums per walk ----
-    const u32 nev = s_nev;
+    const u32 nev = s_multi ? s_nev : 0u;
     for (u32 e = threadIdx.x; e < nev; e += CHB_THREADS) {
         const unsigned long long w = ev[e];
         const u32 b = (u32)(w >> 40), prev = (u32)(w >> 20) & 0xFFFFFu, c = (u32)(w >> 2) & 0x3FFFFu, kind = (u32)w & 3u;
