@@ -49,7 +49,7 @@ struct csa_gpu_ctx {
     DevMem rs_start, rs_count, rs_cbase, rs_stride;
     u32 rs_nblocks = 0;
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, t5, counter, tiles;
-    u32 batch_nmin = 0;
+    u32 batch_nmin = 0, max_set_bases = 0;
     int lcp_state = 0;          // after the suffix array stage: 0 nothing known, 1 every LCP known, 2 all but the LCP_UNKNOWN places
     int ws_runs = 0, ws_force = 0; double ws_pairs = 0, ws_sharing = 0;
     u32 sa_any_other = 1, sa_ngroups = 0;
@@ -216,6 +216,8 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     c->h_seq_off[M] = (u32)tot; c->h_dbl_off[M] = dbl;
     c->h_set_seq0[nsets] = (u32)M; c->h_set_base0[nsets] = (u32)tot; c->h_z0[nsets] = z;
     c->batch_nmin = *std::min_element(c->h_set_nmin.begin(), c->h_set_nmin.end());
+    c->max_set_bases = 0;
+    for (int s = 0; s < nsets; s++) c->max_set_bases = std::max(c->max_set_bases, c->h_set_base0[s + 1] - c->h_set_base0[s]);
     c->N = (u32)tot; c->N0 = z; c->nmax = nmax; c->n0max = n0max; c->mmax = mmax; c->TW = dbl / 32 + 2;
     u32 N = c->N;
     // stage the letters in pinned memory -- unless the caller's buffer is one contiguous, page-locked
@@ -457,7 +459,11 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
         TRY(d2h(ex, hpairs, pairs, sizeof(hpairs)));
         c->ws_pairs = (double)hpairs[0];
         c->ws_sharing = (double)hpairs[1];
-        if (phase == 0 && c->round_mode == 0 && !c->ws_force && (double)hpairs[0] > WS_PAIRS_PER_SUFFIX * (double)N) words = false;
+        if (getenv("CSA_GPU_TRACE")) fprintf(stderr, "[csa] groups %u of %u suffixes, largest %u, pairs %.0f (%.2f per suffix), sharing %.0f\n", ngroups, N, maxg, c->ws_pairs, c->ws_pairs / N, c->ws_sharing);
+        // measured: ~0.05 ns per pair; rank doubling + LCP ~0.2 ns per suffix while a set's ranks live in L2, ~0.55 ns when
+        // they do not (one set of tens of millions of suffixes: every gather a trip to HBM)
+        const double per_suffix = c->max_set_bases > WS_LARGE_SET ? WS_PAIRS_PER_SUFFIX_LARGE : WS_PAIRS_PER_SUFFIX;
+        if (phase == 0 && c->round_mode == 0 && !c->ws_force && (double)hpairs[0] > per_suffix * (double)N) words = false;
     }
     if (!words) { SetRankArgs r{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, r); }
     c->sa_ngroups = ngroups;

@@ -2279,6 +2279,8 @@ static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
 #define WS_STEP 4    // words (of 32 letters) a pair compares per round trip
 #define WS_DEPTH_CAP 32768u // letters a pair is followed; pairs that agree for longer are finished by the doubling rounds
 #define WS_PAIRS_PER_SUFFIX 3.0 // the word sort is chosen when the groups of the first sort hold fewer pairs than this per suffix
+#define WS_PAIRS_PER_SUFFIX_LARGE 10.0 // ... when the largest set of the batch has more than WS_LARGE_SET suffixes
+#define WS_LARGE_SET (8u << 20)
 #define LCP_UNKNOWN 0xFFFFFFFFu
 
 struct WSortArgs {
