@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "circular bases/sec"
 UNIT = "bases/s"
-DEFAULT_SETS = {"mammals": 160, "sets32": 64, "variants256": 8, "bacterial": 1}
+DEFAULT_SETS = {"mammals": 480, "sets32": 192, "variants256": 24, "bacterial": 1}
 
 
 def env_int(name, default):

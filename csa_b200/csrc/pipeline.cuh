@@ -2552,24 +2552,33 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
     }
     Team::sync();
     {
+        // thread i takes the pairs [P*i/threads, P*(i+1)/threads): one search for the place of its first pair, then on
+        // from place to place (neighbouring pairs mostly share their first suffix)
         const u32 P = s.pre[CAP];
-        u32 p = tid, t = 0, pb = 0, L = 0;
+        u32 p = (u32)((u64)P * tid / TT);
+        const u32 pend = (u32)((u64)P * (tid + 1u) / TT);
+        u32 t = 0, tnext = 0, hs = 0, g = 0, pb = 0, L = 0;
         u64 xa = 0, xb = 0;
         bool busy = false;
+        if (p < pend) { // the place that brings pair p = the last one whose running sum is <= p
+            u32 lo = 0, hi = CAP;
+            while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (s.pre[mid] <= p) lo = mid; else hi = mid; }
+            t = lo; tnext = s.pre[t + 1];
+            hs = s.seg[t]; g = (u32)s.end[t] - hs; xa = s.x[t];
+        }
         for (;;) {
-            if (!busy) { // my next pair: the place that brings pair p = the last one whose running sum is <= p
-                if (p >= P) break;
-                u32 lo = 0, hi = CAP;
-                while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (s.pre[mid] <= p) lo = mid; else hi = mid; }
-                t = lo;
-                const u32 hs = s.seg[t], g = (u32)s.end[t] - hs;
+            if (!busy) { // my next pair
+                if (p >= pend) break;
+                if (p >= tnext) {
+                    do { t++; tnext = s.pre[t + 1]; } while (p >= tnext);
+                    hs = s.seg[t]; g = (u32)s.end[t] - hs; xa = s.x[t];
+                }
                 u32 i2 = t - hs + (p - s.pre[t] + 1u);
                 if (i2 >= g) i2 -= g;
                 pb = hs + i2;
-                xa = s.x[t];
                 xb = s.x[pb];
                 L = L0;
-                p += TT;
+                p++;
                 busy = true;
             }
             // one word of the pair (t, pb)
