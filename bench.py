@@ -292,9 +292,10 @@ def main():
         if os.environ.get("CSA_BENCH_ALL_KERNELS"):
             for name, n, ms, by in rows:
                 print("  %-18s n=%-4d %8.3f ms %5.1f%% %8.1f GB/s" % (name, n, ms, 100 * ms / tot, by / ms / 1e6 if ms > 0 else 0), file=sys.stderr)
-        for name, n, ms, by in rows[:8]:
+        for name, n, ms, by in rows[:12]:
             kernels.append({"kernel": name, "launches": n, "ms": round(ms, 3), "share": round(ms / tot, 4),
-                            "algorithmic_GBps": round(by / ms / 1e6, 1) if ms > 0 else None})
+                            "algorithmic_GBps": round(by / ms / 1e6, 1) if ms > 0 else None,
+                            "frac": round(by / ms / 1e6 / peak, 3) if ms > 0 else None})
         name, n, ms, by = rows[0]
         ach = by / ms / 1e6
         # DRAM bytes per launch from the committed ncu capture of this kernel (profiles/traffic.json holds

@@ -84,7 +84,51 @@ HD void encode_body(long long i, const EncodeArgs &a) {
     u32 k = upper_bound_u32(a.v.seq_off, a.v.M + 1, g) - 1;
     a.v.seqof[g] = k;
 }
+#ifdef CSA_EMU
 MAP_KERNEL(encode, EncodeArgs, 6)
+#else
+// 16 bases per thread: one 16-byte load, one search for the sequence of the first base (the others follow
+// by comparing with the next border), 16 + 64 bytes stored as five 16-byte words
+__global__ void __launch_bounds__(256) k_encode(long long n, EncodeArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long g0 = t * 16;
+    if (g0 >= n) return;
+    if (g0 + 16 > n) { for (long long g = g0; g < n; g++) encode_body(g, a); return; }
+    const uint4 w = *reinterpret_cast<const uint4 *>(a.raw + g0);
+    const u32 in[4] = {w.x, w.y, w.z, w.w};
+    u32 k = upper_bound_u32(a.v.seq_off, a.v.M + 1, (u32)g0) - 1;
+    u32 nextb = LDG(a.v.seq_off + k + 1);
+    u32 outc[4], outk[16];
+    bool other = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        u32 oc = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const u32 g = (u32)g0 + 4 * q + b;
+            while (g >= nextb) { k++; nextb = LDG(a.v.seq_off + k + 1); }
+            const unsigned c = code_of_letter((unsigned char)(in[q] >> (8 * b)));
+            other |= c > 3;
+            oc |= c << (8 * b);
+            outk[4 * q + b] = k;
+        }
+        outc[q] = oc;
+    }
+    *reinterpret_cast<uint4 *>(a.v.code + g0) = make_uint4(outc[0], outc[1], outc[2], outc[3]);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        *reinterpret_cast<uint4 *>(a.v.seqof + g0 + 4 * q) = make_uint4(outk[4 * q], outk[4 * q + 1], outk[4 * q + 2], outk[4 * q + 3]);
+    if (other) *a.any_other = 1u;
+}
+static inline void launch_encode(Exec &ex, long long n, EncodeArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_encode", 6.0 * n);
+    const long long threads = (n + 15) / 16;
+    k_encode<<<(unsigned)((threads + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
 
 // one thread per 32-base word of the doubled text: sequence k occupies bases
 // [dbl_off[k], dbl_off[k+1]) = s_k s_k s_k... so that any window p..p+n+63 reads without wrap
@@ -1363,12 +1407,17 @@ __global__ void __launch_bounds__(256) k_maxgroup(long long n, MaxGroupArgs a) {
     __shared__ unsigned long long s_pairs, s_shared;
     if (threadIdx.x == 0) { s_max = 0; s_pairs = 0; s_shared = 0; }
     __syncthreads();
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 sz = 0;
-    if (i < n && ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1)) sz = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
-    unsigned long long pr = sz > 1 ? (unsigned long long)sz * (sz - 1) / 2 : 0ull;
+    // a persistent grid: every thread folds many places (neighbouring lanes read neighbouring words)
+    u32 sz = 0, sh = 0;
+    unsigned long long pr = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1) {
+            const u32 z = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
+            sz = z > sz ? z : sz;
+            if (z > 1) { pr += (unsigned long long)z * (z - 1) / 2; sh += z; }
+        }
+    }
     if (a.pairs) { // one atomic per CTA: same-address atomics serialise in L2
-        u32 sh = sz > 1 ? sz : 0u;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { pr += __shfl_xor_sync(0xffffffffu, pr, d); sh += __shfl_xor_sync(0xffffffffu, sh, d); }
         if ((threadIdx.x & 31) == 0 && pr) { atomicAdd(&s_pairs, pr); atomicAdd(&s_shared, (unsigned long long)sh); }
@@ -1382,7 +1431,8 @@ __global__ void __launch_bounds__(256) k_maxgroup(long long n, MaxGroupArgs a) {
 static inline void launch_maxgroup(Exec &ex, long long n, MaxGroupArgs a) {
     if (n <= 0) return;
     PROF_BEGIN(ex, "k_maxgroup", 4.0 * n);
-    k_maxgroup<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    const long long want = (n + 255) / 256, cap = 148 * 16;
+    k_maxgroup<<<(unsigned)(want < cap ? want : cap), 256, 0, ex.stream>>>(n, a);
     PROF_END(ex);
     ex.launches++;
 }

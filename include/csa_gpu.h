@@ -149,10 +149,14 @@ int csa_gpu_shard_begin(csa_gpu_ctx *ctx, int rank, int nranks);
 int csa_gpu_shard_view(csa_gpu_ctx *ctx, csa_gpu_shard_info *out);
 int csa_gpu_shard_finish(csa_gpu_ctx *ctx, int max_interval, unsigned flags, unsigned nleft, unsigned left_suffixes,
                          unsigned min_depth, unsigned max_group);
-/* tests: force_global = 1 sends every prefix-doubling round down the device-wide radix-sort path,
- * 0 lets the tile path take the rounds whose groups fit a tile, -1 leaves the setting; rounds[0..1]
- * = rounds of the last run on the tile path / on the device-wide path */
-int csa_gpu_debug_rounds(csa_gpu_ctx *ctx, int force_global, int rounds[2]);
+/* tests: which of the equivalent ways the suffix-array stage takes (they must all give the same suffix array and
+ * LCP array).  mode: -1 leaves the setting; 0 free choice (word sort when the groups of the first sort are small,
+ * rank doubling otherwise); 1 device-wide radix rounds only; 2 tile rounds with doubling only (+ text-order LCP);
+ * 3 tile rounds, quadrupling allowed; 4 word sort stopped after two words, the rest by doubling rounds; 5 free choice
+ * among the doubling rounds (no word sort); 6 word sort whatever the groups look like; 7 free choice, long block
+ * lists chained by the literal one-thread walk; 8 free choice, sharded runs of one set sort the whole set on every
+ * rank.  rounds[0..1] = rounds of the last run on the tile/list/word-sort paths and on the device-wide path */
+int csa_gpu_debug_rounds(csa_gpu_ctx *ctx, int mode, int rounds[2]);
 /* per-kernel profile: with it enabled every launch of the next runs is bracketed by CUDA events on
  * the run's stream; after a run row i gives the kernel's name, its launches, their summed device
  * time (ms) and the ALGORITHMIC bytes they moved (DESIGN.md lists the per-item figures).  Off by
