@@ -30,6 +30,7 @@ template <class T> static inline T emu_atomic_max(T *p, T v) { T o = *p; if (v >
 #define COUNT_IF(p, flag) do { if (flag) (*(p))++; } while (0)
 #define ATOMIC_MIN(p, v) emu_atomic_min(p, v)
 #define ATOMIC_MAX(p, v) emu_atomic_max(p, v)
+#define ATOMIC_OR(p, v) (*(p) |= (v))
 #define LDG(p) (*(p))
 typedef int csaStream_t;
 #else
@@ -55,6 +56,7 @@ typedef int csaStream_t;
     } while (0)
 #define ATOMIC_MIN(p, v) atomicMin(p, v)
 #define ATOMIC_MAX(p, v) atomicMax(p, v)
+#define ATOMIC_OR(p, v) atomicOr(p, v)
 typedef cudaStream_t csaStream_t;
 #endif
 

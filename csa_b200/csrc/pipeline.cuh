@@ -530,7 +530,7 @@ HD void degen_body(long long i, const DegenArgs &a) {
     if (lb != s0 && a.lcp[lb] >= nmin) return; // not the head of the run
     u32 rb = lb + 1;
     while (rb + 1 < s1 && a.lcp[rb + 1] >= nmin) rb++;
-    if (rb >= a.R[lb]) ATOMIC_MAX(a.set_flags + s, 1u);
+    if (rb >= a.R[lb]) ATOMIC_OR(a.set_flags + s, 1u);
 }
 MAP_KERNEL(degen, DegenArgs, 12)
 
@@ -978,7 +978,7 @@ HD void chain_body(long long s, const ChainArgs &a) {
     bool hang;
     chain_walk(b0, B, a.o_depth + b0, a.next + b0, a.gap + b0, a.size + b0, a.total + b0, a.interval + b0, &mcs, &hang);
     a.set_nchains[s] = mcs;
-    if (hang) ATOMIC_MAX(a.set_flags + s, 2u);
+    if (hang) ATOMIC_OR(a.set_flags + s, 2u);
 }
 MAP_KERNEL(chain, ChainArgs, 16)
 #else
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(ChainArgs a) {
     }
     if (threadIdx.x == 0) {
         a.set_nchains[s] = mcs;
-        if (hang) atomicMax(a.set_flags + s, 2u);
+        if (hang) atomicOr(a.set_flags + s, 2u);
     }
 }
 static inline void launch_chain(Exec &ex, long long nsets, ChainArgs a) {
@@ -1151,7 +1151,7 @@ __global__ void __launch_bounds__(CHB_THREADS) k_chain_big(ChainBigArgs a) {
     __syncthreads();
     if (s_multi && (s_hang || s_fail)) {
         if (threadIdx.x == 0) {
-            if (s_hang) atomicMax(a.c.set_flags + s, 2u); else a.redo[s] = 1;
+            if (s_hang) atomicOr(a.c.set_flags + s, 2u); else a.redo[s] = 1;
             a.c.set_nchains[s] = s_mcs;
         }
         return;

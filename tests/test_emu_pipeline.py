@@ -84,3 +84,15 @@ def test_emu_both_round_paths(emu_finder):
         compare_with_oracle(q, o, s, f"tile path (quadrupling) set {i}")
         compare_with_oracle(d, o, s, f"tile path (doubling) set {i}")
         compare_with_oracle(b, o, s, f"device-wide path set {i}")
+
+
+def test_emu_degenerate_and_nonterminating_together(emu_finder):
+    """a set that is degenerate (a whole rotation inside all others) AND whose block chain does not terminate keeps
+    the classification the tree walk reaches first (csamsa.c:64 runs before collectNodeChains): DEGENERATE.
+    Found by the randomized GPU sweep (the two flags used to be combined with max instead of or)."""
+    rng = random.Random(1000 + 9)
+    cases = [gen_case(rng, max_n=rng.choice([500, 1500, 6000]))[1] for _ in range(150)]
+    s = cases[94]
+    o = oracle_run(s)
+    assert o["status"] == 3
+    compare_with_oracle(emu_finder.find_rotations(s), o, s, "degenerate + nonterminating")
