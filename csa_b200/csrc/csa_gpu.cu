@@ -716,12 +716,12 @@ static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
     int rounds = bits_for(c->n0max) + 1;
     u32 *val = P<u32>(c->val), *up = P<u32>(c->up), *val2 = P<u32>(c->val2), *up2 = P<u32>(c->up2);
     u32 *moving = P<u32>(c->counter) + 12;
-    for (int r = 0; r < rounds; r++) {
-        if (r % 3 == 0) TRY(dev_zero(ex, moving, sizeof(u32)));
+    for (int r = 0; r < rounds; r++) { // (a round over 2 N0 nodes costs ten times a look at the flag: look after every round but the first three)
+        TRY(dev_zero(ex, moving, sizeof(u32)));
         JumpArgs a{val, up, val2, up2, moving};
         launch_jump(ex, 2ll * N0, a);
         std::swap(val, val2); std::swap(up, up2);
-        if (r % 3 == 2) {
+        if (r >= 3) {
             u32 m = 0;
             TRY(read_u32(c, moving, &m));
             if (!m) break;
