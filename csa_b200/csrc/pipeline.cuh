@@ -62,6 +62,14 @@ HD u32 upper_bound_u64(const u64 *a, u32 n, u64 x) {
 HD u32 set_of_pos(const BatchView &v, u32 i) { return upper_bound_u32(v.set_base0, (u32)v.nsets + 1, i) - 1; }
 
 HD u32 seq_of(const BatchView &v, u32 g) { return LDG(v.seqof + g); }
+// The same by a search in the table of sequence starts: for a batch of a few long sequences (bacterial
+// chromosomes) the table sits in L1 and the search beats a 4-byte gather from an N-sized array in HBM in the
+// kernels that do little else (measured on 16 x 5 Mb: k_blockfind 2.65 -> 1.41 ms, k_colorkey 1.45 -> 0.45 ms);
+// for thousands of short sequences the gather wins.
+HD u32 seq_of_few(const BatchView &v, u32 g) {
+    if (v.M <= 64u) return upper_bound_u32(v.seq_off, v.M + 1, g) - 1;
+    return LDG(v.seqof + g);
+}
 
 // position h letters further round the circle
 HD u32 cyc_add(const BatchView &v, u32 g, u32 h) {
@@ -385,7 +393,7 @@ MAP_KERNEL(lcpdirect, LcpDirectArgs, 12)
 // The colour lists come from one stable radix pass of the SA indices by sequence-in-set.
 struct ColorKeyArgs { BatchView v; const u32 *sa; u64 *keys; u32 *vals; };
 HD void colorkey_body(long long i, const ColorKeyArgs &a) {
-    u32 k = seq_of(a.v, a.sa[i]);
+    u32 k = seq_of_few(a.v, a.sa[i]);
     // low bits (the only ones sorted on): sequence-in-set; high word: the sequence, carried along so
     // that k_next reads its neighbours' sequences from the sorted keys instead of gathering them
     a.keys[i] = ((u64)k << 32) | (k - LDG(a.v.set_seq0 + LDG(a.v.seq_set + k)));
@@ -420,7 +428,7 @@ MAP_KERNEL(cover, CoverArgs, 16)
 // the left by one and the same letter (csamsa.c:64,80,283).  One thread per left border.
 struct BlockFindArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *isblock; u32 *depth; };
 HD unsigned letter_before_suffix(const BatchView &v, u32 g) {
-    u32 k = seq_of(v, g);
+    u32 k = seq_of_few(v, g);
     u32 off = LDG(v.seq_off + k), n = LDG(v.seq_off + k + 1) - off;
     u32 p = g - off;
     return v.code[off + (p == 0 ? n - 1 : p - 1)];
@@ -2602,11 +2610,15 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
     }
     Team::sync();
     {
-        // thread i takes the pairs [P*i/threads, P*(i+1)/threads): one search for the place of its first pair, then on
-        // from place to place (neighbouring pairs mostly share their first suffix)
+        // Many pairs (long groups): thread i takes the pairs i, i + threads, ... -- neighbouring pairs are alike in
+        // length, dealt out in turn they even out over the lanes.  Few pairs: thread i takes the run
+        // [P*i/threads, P*(i+1)/threads), whose pairs mostly share their first suffix.  Either way one search for
+        // the place of the first pair, then on from place to place.
         const u32 P = s.pre[CAP];
-        u32 p = (u32)((u64)P * tid / TT);
-        const u32 pend = (u32)((u64)P * (tid + 1u) / TT);
+        const bool in_turn = P > 5u * TT;
+        const u32 pstep = in_turn ? TT : 1u;
+        u32 p = in_turn ? tid : (u32)((u64)P * tid / TT);
+        const u32 pend = in_turn ? P : (u32)((u64)P * (tid + 1u) / TT);
         u32 t = 0, tnext = 0, hs = 0, g = 0, pb = 0, L = 0;
         u64 xa = 0, xb = 0;
         bool busy = false;
@@ -2628,7 +2640,7 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
                 pb = hs + i2;
                 xb = s.x[pb];
                 L = L0;
-                p++;
+                p += pstep;
                 busy = true;
             }
             // one word of the pair (t, pb)

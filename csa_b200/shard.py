@@ -97,17 +97,19 @@ def run_bucket_sharded(finder: RotationFinder, rank: int, world: int, dist=None,
         finder.shard_finish(max_interval, flags, *mine)
         return bounds
     dev = "cuda" if cuda else "cpu"
-    for ptr in (v.sa, v.head, v.lcp):
-        t = _alias(ptr, n, 4, cuda)
-        for r in range(world):
-            if bounds[r + 1] > bounds[r]:
-                dist.broadcast(t[bounds[r]:bounds[r + 1]], src=r)
     cnt = torch.tensor(mine, dtype=torch.int64, device=dev)
     allc = [torch.zeros_like(cnt) for _ in range(world)]
     dist.all_gather(allc, cnt)
     allc = [c.tolist() for c in allc]
     nl = [c[0] for c in allc]
     total = sum(nl)
+    # suffix array and LCP of every bucket to every rank; the group heads only when some bucket sort left groups
+    # for the doubling rounds (which work on the heads)
+    for ptr in (v.sa, v.lcp) + ((v.head,) if total else ()):
+        t = _alias(ptr, n, 4, cuda)
+        for r in range(world):
+            if bounds[r + 1] > bounds[r]:
+                dist.broadcast(t[bounds[r]:bounds[r + 1]], src=r)
     if total:
         left = _alias(v.left, max(total, nl[rank]), 8, cuda)
         tmp = torch.empty(total, dtype=torch.int64, device=dev)
