@@ -3,6 +3,7 @@
 The path has no exchange step between sets, so there is no data-path collective: rank r takes a
 contiguous slice of the sets, runs it on its own GPU, and the rotations are gathered once at the end
 (torch.distributed, NCCL on the GPU box, gloo in the CPU tests)."""
+import os
 from typing import List, Sequence
 
 import numpy as np
@@ -105,11 +106,25 @@ def run_bucket_sharded(finder: RotationFinder, rank: int, world: int, dist=None,
     total = sum(nl)
     # suffix array and LCP of every bucket to every rank; the group heads only when some bucket sort left groups
     # for the doubling rounds (which work on the heads)
-    for ptr in (v.sa, v.lcp) + ((v.head,) if total else ()):
-        t = _alias(ptr, n, 4, cuda)
-        for r in range(world):
-            if bounds[r + 1] > bounds[r]:
-                dist.broadcast(t[bounds[r]:bounds[r + 1]], src=r)
+    arrays = [_alias(ptr, n, 4, cuda) for ptr in (v.sa, v.lcp) + ((v.head,) if total else ())]
+    width = max(bounds[r + 1] - bounds[r] for r in range(world))
+    if cuda and os.environ.get("CSA_SHARD_EXCHANGE", "allgather") == "allgather" and width * world <= 2 * n + 1024:
+        # one all-gather per array (buckets are even to within n/4096: padded to the widest), then every bucket
+        # copied to its place -- one collective instead of `world` broadcasts one after the other
+        mine_t = torch.empty(width, dtype=torch.int32, device=dev)
+        allb = torch.empty(world * width, dtype=torch.int32, device=dev)
+        for t in arrays:
+            k = bounds[rank + 1] - bounds[rank]
+            mine_t[:k].copy_(t[bounds[rank]:bounds[rank + 1]])
+            dist.all_gather_into_tensor(allb, mine_t)
+            for r in range(world):
+                if r != rank and bounds[r + 1] > bounds[r]:
+                    t[bounds[r]:bounds[r + 1]].copy_(allb[r * width:r * width + bounds[r + 1] - bounds[r]])
+    else:
+        for t in arrays:
+            for r in range(world):
+                if bounds[r + 1] > bounds[r]:
+                    dist.broadcast(t[bounds[r]:bounds[r + 1]], src=r)
     if total:
         left = _alias(v.left, max(total, nl[rank]), 8, cuda)
         tmp = torch.empty(total, dtype=torch.int64, device=dev)
