@@ -1210,11 +1210,8 @@ __global__ void __launch_bounds__(CHB_THREADS) k_chain_big(ChainBigArgs a) {
 }
 static inline int launch_chain_big(Exec &ex, u32 nbig, size_t smem, ChainBigArgs a) {
     if (nbig == 0) return 0;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(k_chain_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    // (per device and cheap: set on every launch rather than remembered per process)
+    CUDA_TRY(cudaFuncSetAttribute(k_chain_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PROF_BEGIN(ex, "k_chain_big", 0.0);
     k_chain_big<<<nbig, CHB_THREADS, smem, ex.stream>>>(a);
     PROF_END(ex);
