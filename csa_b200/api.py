@@ -78,6 +78,13 @@ def _load(path):
     lib.csa_gpu_batch_suffix_array.argtypes = [vp, C.POINTER(C.c_uint), ip]
     lib.csa_gpu_batch_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
     lib.csa_gpu_debug_rounds.argtypes = [vp, i, ip]
+    lib.csa_gpu_multi_create.argtypes = [i, ip, C.POINTER(vp)]
+    lib.csa_gpu_multi_destroy.argtypes = [vp]
+    lib.csa_gpu_multi_destroy.restype = None
+    lib.csa_gpu_multi_size.argtypes = [vp]
+    lib.csa_gpu_multi_ctx.argtypes = [vp, i]
+    lib.csa_gpu_multi_ctx.restype = vp
+    lib.csa_gpu_multi_batch_rotations.argtypes = [vp, i, ip, C.POINTER(C.c_char_p), ip, i, C.c_uint, ip, C.POINTER(SetInfo)]
     lib.csa_gpu_shard_begin.argtypes = [vp, i, i]
     lib.csa_gpu_shard_view.argtypes = [vp, C.POINTER(ShardInfo)]
     lib.csa_gpu_shard_finish.argtypes = [vp, i, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
@@ -259,3 +266,48 @@ class RotationFinder:
 
     def find_rotations(self, seqs: Sequence[bytes], max_interval: int = INT_MAX, flags: int = 0) -> SetResult:
         return self.find_rotations_batch([seqs], max_interval, flags)[0]
+
+
+class MultiRotationFinder:
+    """csa_gpu_multi_*: ONE process driving several GPUs on one batch (the suffix-array stage sharded by buckets,
+    exchanged by peer copies).  Results are read from context 0, wrapped as `self.first` (a RotationFinder that
+    does not own its context)."""
+
+    def __init__(self, ngpus: int, devices: Sequence[int] = None, lib_path: str = DEFAULT_LIB):
+        self.lib = _load(lib_path)
+        self.m = C.c_void_p()
+        dev = None if devices is None else (C.c_int * ngpus)(*devices)
+        rc = self.lib.csa_gpu_multi_create(ngpus, dev, C.byref(self.m))
+        if rc != 0:
+            raise CsaGpuError(rc, self.lib.csa_gpu_last_error().decode(errors="replace"))
+        self.first = RotationFinder.__new__(RotationFinder)
+        self.first.lib = self.lib
+        self.first.ctx = C.c_void_p(self.lib.csa_gpu_multi_ctx(self.m, 0))
+        self.first.close = lambda: None  # owned by the multi object
+
+    def close(self):
+        if getattr(self, "m", None) and self.m.value:
+            self.lib.csa_gpu_multi_destroy(self.m)
+            self.m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def find_rotations_batch(self, sets: Sequence[Sequence[bytes]], max_interval: int = INT_MAX, flags: int = 0):
+        """returns (rotations per sequence, SetInfo per set); blocks through self.first.blocks()"""
+        batch = Batch(sets)
+        flat = [x for seqs in sets for x in seqs]
+        texts = (C.c_char_p * len(flat))(*flat)
+        sizes = (C.c_int * len(flat))(*[len(x) for x in flat])
+        rot = np.zeros(batch.nseqs, dtype=np.int32)
+        info = (SetInfo * batch.nsets)()
+        rc = self.lib.csa_gpu_multi_batch_rotations(self.m, batch.nsets, _ip(batch.set_start), texts, sizes, max_interval,
+                                                    flags, _ip(rot), info)
+        if rc != 0:
+            raise CsaGpuError(rc, self.lib.csa_gpu_last_error().decode(errors="replace"))
+        self.first._batch = batch
+        return rot, info
+

@@ -8,6 +8,7 @@
 #include <vector>
 #include <string>
 #include <new>
+#include <thread>
 
 thread_local char g_csa_err[512] = "";
 
@@ -949,6 +950,129 @@ extern "C" int csa_gpu_shard_finish(csa_gpu_ctx *c, int max_interval, unsigned f
     if (c->shard_phase != 1) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_shard_finish before csa_gpu_shard_begin");
     c->ws_left[0] = nleft; c->ws_left[1] = left_suffixes; c->ws_left[2] = min_depth; c->ws_left[3] = max_group;
     return run_phases(c, max_interval, flags, 2);
+}
+
+// ---- the same from ONE process that drives several GPUs (the C host: no NCCL, no Python) -------------------------
+// One host thread per GPU for the two compute phases; the bucket exchange by peer copies (NVLink when the GPUs
+// see each other), the lists of left-over groups through the host (they are tiny).
+struct csa_gpu_multi {
+    std::vector<csa_gpu_ctx *> ctx;
+    std::string err;
+};
+
+extern "C" int csa_gpu_multi_create(int ngpus, const int *devices, csa_gpu_multi **out) {
+    if (!out || ngpus < 1) CSA_FAIL(CSA_GPU_EINVAL, "csa_gpu_multi_create: bad argument");
+    *out = nullptr;
+    csa_gpu_multi *m = new (std::nothrow) csa_gpu_multi();
+    if (!m) CSA_FAIL(CSA_GPU_ENOMEM, "out of host memory");
+    for (int i = 0; i < ngpus; i++) {
+        csa_gpu_ctx *c = nullptr;
+        int rc = csa_gpu_create(devices ? devices[i] : i, &c);
+        if (rc) { for (csa_gpu_ctx *x : m->ctx) csa_gpu_destroy(x); delete m; return rc; }
+        m->ctx.push_back(c);
+    }
+#ifndef CSA_EMU
+    for (int i = 0; i < ngpus; i++) // direct loads/stores between the GPUs where the box allows them
+        for (int j = 0; j < ngpus; j++) {
+            if (i == j || m->ctx[i]->device == m->ctx[j]->device) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, m->ctx[i]->device, m->ctx[j]->device);
+            if (can) { cudaSetDevice(m->ctx[i]->device); cudaDeviceEnablePeerAccess(m->ctx[j]->device, 0); cudaGetLastError(); }
+        }
+#endif
+    *out = m;
+    return CSA_GPU_OK;
+}
+
+extern "C" void csa_gpu_multi_destroy(csa_gpu_multi *m) {
+    if (!m) return;
+    for (csa_gpu_ctx *c : m->ctx) csa_gpu_destroy(c);
+    delete m;
+}
+
+extern "C" int csa_gpu_multi_size(csa_gpu_multi *m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" csa_gpu_ctx *csa_gpu_multi_ctx(csa_gpu_multi *m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
+
+// run f(rank) on one host thread per context; the first failure's code and message come back
+template <class F> static int multi_parallel(csa_gpu_multi *m, F f) {
+    const int R = (int)m->ctx.size();
+    std::vector<int> rc(R, 0);
+    std::vector<std::string> msg(R);
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; r++)
+        th.emplace_back([&, r]() { rc[r] = f(r); if (rc[r]) msg[r] = g_csa_err; });
+    for (std::thread &t : th) t.join();
+    for (int r = 0; r < R; r++)
+        if (rc[r]) CSA_FAIL(rc[r], "GPU %d of %d: %s", r, R, msg[r].c_str());
+    return 0;
+}
+
+static int multi_copy(csa_gpu_ctx *dst, void *dp, csa_gpu_ctx *src, const void *sp, size_t bytes) {
+    if (!bytes) return 0;
+#ifdef CSA_EMU
+    (void)dst; (void)src;
+    memcpy(dp, sp, bytes);
+#else
+    CUDA_TRY(cudaMemcpyPeerAsync(dp, dst->device, sp, src->device, bytes, dst->ex.stream));
+#endif
+    return 0;
+}
+
+extern "C" int csa_gpu_multi_batch_rotations(csa_gpu_multi *m, int nsets, const int *set_start, const char *const *texts,
+                                             const int *textsizes, int max_interval, unsigned flags, int *rotations,
+                                             csa_gpu_set_info *info) {
+    if (!m || m->ctx.empty()) CSA_FAIL(CSA_GPU_EINVAL, "null argument");
+    const int R = (int)m->ctx.size();
+    if (R == 1) return csa_gpu_batch_rotations(m->ctx[0], nsets, set_start, texts, textsizes, max_interval, flags, rotations, info);
+    // every GPU: the whole batch, then its own bucket of the suffix array
+    TRY(multi_parallel(m, [&](int r) {
+        int rc = csa_gpu_batch_upload(m->ctx[r], nsets, set_start, texts, textsizes);
+        return rc ? rc : csa_gpu_shard_begin(m->ctx[r], r, R);
+    }));
+    std::vector<csa_gpu_shard_info> v(R);
+    for (int r = 0; r < R; r++) TRY(csa_gpu_shard_view(m->ctx[r], &v[r]));
+    const unsigned *b = v[0].bounds;
+    for (int r = 1; r < R; r++)
+        for (int q = 0; q <= R; q++)
+            if (v[r].bounds[q] != b[q]) CSA_FAIL(CSA_GPU_ECUDA, "bucket borders differ between GPUs (%u != %u)", v[r].bounds[q], b[q]);
+    // what the bucket sorts left, through the host
+    unsigned nleft = 0, left_suffixes = 0, min_depth = 0xFFFFFFFFu, max_group = 0;
+    std::vector<unsigned long long> left;
+    for (int r = 0; r < R; r++) {
+        const size_t at = left.size();
+        left.resize(at + v[r].nleft);
+        if (v[r].nleft) {
+#ifndef CSA_EMU
+            CUDA_TRY(cudaSetDevice(m->ctx[r]->device));
+#endif
+            TRY(d2h(m->ctx[r]->ex, left.data() + at, v[r].left, sizeof(unsigned long long) * v[r].nleft));
+        }
+        nleft += v[r].nleft; left_suffixes += v[r].left_suffixes;
+        min_depth = std::min(min_depth, v[r].min_depth); max_group = std::max(max_group, v[r].max_group);
+    }
+    // every bucket to every other GPU: suffix array and LCP, the group heads only when groups were left
+    for (int q = 0; q < R; q++) {
+#ifndef CSA_EMU
+        CUDA_TRY(cudaSetDevice(m->ctx[q]->device));
+#endif
+        for (int r = 0; r < R; r++) {
+            if (r == q || b[r + 1] == b[r]) continue;
+            const size_t off = (size_t)b[r] * sizeof(u32), bytes = (size_t)(b[r + 1] - b[r]) * sizeof(u32);
+            TRY(multi_copy(m->ctx[q], (char *)v[q].sa + off, m->ctx[r], (const char *)v[r].sa + off, bytes));
+            TRY(multi_copy(m->ctx[q], (char *)v[q].lcp + off, m->ctx[r], (const char *)v[r].lcp + off, bytes));
+            if (nleft) TRY(multi_copy(m->ctx[q], (char *)v[q].head + off, m->ctx[r], (const char *)v[r].head + off, bytes));
+        }
+        if (nleft) TRY(h2d(m->ctx[q]->ex, v[q].left, left.data(), sizeof(unsigned long long) * left.size()));
+    }
+    for (int q = 0; q < R; q++) {
+#ifndef CSA_EMU
+        CUDA_TRY(cudaSetDevice(m->ctx[q]->device));
+#endif
+        TRY(exec_sync(m->ctx[q]->ex));
+    }
+    // every GPU: the rest of the path (the results are the same everywhere; they are read from GPU 0)
+    TRY(multi_parallel(m, [&](int r) { return csa_gpu_shard_finish(m->ctx[r], max_interval, flags, nleft, left_suffixes, min_depth, max_group); }));
+    return csa_gpu_batch_download(m->ctx[0], rotations, info);
 }
 
 // tests: force every doubling round down the device-wide radix path (1) or let the tiles decide (0);

@@ -185,16 +185,34 @@ int main(int argc, char **argv) {
     fflush(stdout);
 
     /* ---- the hot path: one call ---- */
+    /* CSA_GPUS=<n> (n > 1): this one process drives n GPUs on the set -- suffix-array buckets sharded over them,
+       exchanged by peer copies (csa_gpu_multi_*); worth it for bacterial-scale sets */
     csa_gpu_ctx *ctx = NULL;
-    if (csa_gpu_create(device, &ctx) != CSA_GPU_OK) {
-        fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
-        die("No CUDA device (this build has no CPU path)");
-    }
+    csa_gpu_multi *multi = NULL;
+    int ngpus = getenv("CSA_GPUS") ? atoi(getenv("CSA_GPUS")) : 1;
     int *rotations = (int *)calloc((size_t)m, sizeof(int));
     csa_gpu_set_info info;
-    if (csa_gpu_find_rotations(ctx, m, (const char *const *)texts, sizes, INT_MAX, CSA_GPU_FLAG_STATS, rotations, &info) != CSA_GPU_OK) {
-        fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
-        die("GPU run failed");
+    if (ngpus > 1) {
+        int set_start[2] = {0, m};
+        if (csa_gpu_multi_create(ngpus, NULL, &multi) != CSA_GPU_OK) {
+            fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
+            die("Not that many CUDA devices (this build has no CPU path)");
+        }
+        ctx = csa_gpu_multi_ctx(multi, 0);
+        if (csa_gpu_multi_batch_rotations(multi, 1, set_start, (const char *const *)texts, sizes, INT_MAX, CSA_GPU_FLAG_STATS,
+                                          rotations, &info) != CSA_GPU_OK) {
+            fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
+            die("GPU run failed");
+        }
+    } else {
+        if (csa_gpu_create(device, &ctx) != CSA_GPU_OK) {
+            fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
+            die("No CUDA device (this build has no CPU path)");
+        }
+        if (csa_gpu_find_rotations(ctx, m, (const char *const *)texts, sizes, INT_MAX, CSA_GPU_FLAG_STATS, rotations, &info) != CSA_GPU_OK) {
+            fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
+            die("GPU run failed");
+        }
     }
     if (info.status == CSA_SET_DEGENERATE)
         die("A whole rotation of one sequence occurs in all the others (the reference's tree walk is undefined here)");
@@ -262,6 +280,6 @@ int main(int argc, char **argv) {
     if (nchains > ntoprint) printf(":: ... (%d total)\n", nchains);
     fclose(o);
     printf("> Done!\n");
-    csa_gpu_destroy(ctx);
+    if (multi) csa_gpu_multi_destroy(multi); else csa_gpu_destroy(ctx);
     return 0;
 }

@@ -149,6 +149,18 @@ int csa_gpu_shard_begin(csa_gpu_ctx *ctx, int rank, int nranks);
 int csa_gpu_shard_view(csa_gpu_ctx *ctx, csa_gpu_shard_info *out);
 int csa_gpu_shard_finish(csa_gpu_ctx *ctx, int max_interval, unsigned flags, unsigned nleft, unsigned left_suffixes,
                          unsigned min_depth, unsigned max_group);
+/* The same from ONE process that drives several GPUs (what the C host does: no NCCL, no Python).  One host thread
+ * per GPU for the compute phases, the bucket exchange by peer copies.  Results are read from context 0
+ * (csa_gpu_multi_ctx(m, 0)) with the csa_gpu_batch_* calls above. */
+typedef struct csa_gpu_multi csa_gpu_multi;
+int csa_gpu_multi_create(int ngpus, const int *devices /* NULL: 0 .. ngpus-1 */, csa_gpu_multi **out);
+void csa_gpu_multi_destroy(csa_gpu_multi *m);
+int csa_gpu_multi_size(csa_gpu_multi *m);
+csa_gpu_ctx *csa_gpu_multi_ctx(csa_gpu_multi *m, int i);
+int csa_gpu_multi_batch_rotations(csa_gpu_multi *m, int nsets, const int *set_start, const char *const *texts,
+                                  const int *textsizes, int max_interval, unsigned flags, int *rotations,
+                                  csa_gpu_set_info *info);
+
 /* tests: which of the equivalent ways the suffix-array stage takes (they must all give the same suffix array and
  * LCP array).  mode: -1 leaves the setting; 0 free choice (word sort when the groups of the first sort are small,
  * rank doubling otherwise); 1 device-wide radix rounds only; 2 tile rounds with doubling only (+ text-order LCP);

@@ -13,14 +13,15 @@ import pytest
 from common import EMU_DIR, ORACLE_BIN, ROOT, build_emu, build_oracle
 
 
-def run_cli(binary, case, tmp):
+def run_cli(binary, case, tmp, env=None):
     d = tempfile.mkdtemp(dir=tmp)
     with open(os.path.join(d, "in.fa"), "w") as f:
         for desc, s in zip(case["descs"], case["seqs"]):
             f.write(">" + desc + "\n")
             for i in range(0, len(s), 70):
                 f.write(s[i:i + 70] + "\n")
-    p = subprocess.run([binary, "R", "in.fa"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    p = subprocess.run([binary, "R", "in.fa"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120,
+                       env=None if env is None else dict(os.environ, **env))
     def rd(name):
         path = os.path.join(d, name)
         return open(path, "rb").read() if os.path.exists(path) else None
@@ -43,6 +44,16 @@ def check_cases(binary, cases, tmp):
 def test_cli_emu(golden, tmp_path):
     build_emu()
     check_cases(os.path.join(EMU_DIR, "CSA_emu"), golden[:2] + golden[2::6], str(tmp_path))
+
+
+def test_cli_emu_several_gpus(golden, tmp_path):
+    """CSA_GPUS=3: one process, three contexts (csa_gpu_multi_*), buckets exchanged by copies; output files and
+    stdout equal the one-GPU run's byte for byte"""
+    build_emu()
+    for case in golden[:2] + golden[3::9]:
+        one = run_cli(os.path.join(EMU_DIR, "CSA_emu"), case, str(tmp_path))
+        three = run_cli(os.path.join(EMU_DIR, "CSA_emu"), case, str(tmp_path), env={"CSA_GPUS": "3"})
+        assert one == three, case["name"]
 
 
 def test_cli_drops_rotation_duplicates(tmp_path):

@@ -96,3 +96,64 @@ def test_emu_degenerate_and_nonterminating_together(emu_finder):
     o = oracle_run(s)
     assert o["status"] == 3
     compare_with_oracle(emu_finder.find_rotations(s), o, s, "degenerate + nonterminating")
+
+
+def test_emu_shard_api_one_rank_and_errors(emu_finder):
+    """csa_gpu_shard_begin/_view/_finish: a job of one rank gives what csa_gpu_batch_run gives; calls out of order fail"""
+    from csa_b200.api import Batch, CsaGpuError
+    from csa_b200.shard import run_bucket_sharded
+    rng = random.Random(12)
+    sets = [gen_case(rng, max_n=900)[1] for _ in range(3)]
+    batch = Batch(sets)
+    ref = emu_finder.find_rotations_batch(batch)
+    emu_finder.upload(batch)
+    with pytest.raises(CsaGpuError):
+        emu_finder.shard_view()                      # before shard_begin
+    with pytest.raises(CsaGpuError):
+        emu_finder.shard_finish(2**31 - 1, 0, 0, 0, 0, 0)
+    with pytest.raises(CsaGpuError):
+        emu_finder.shard_begin(3, 2)                 # rank outside the job
+    bounds = run_bucket_sharded(emu_finder, 0, 1, cuda=False)
+    assert bounds == [0, batch.nbases]
+    rot, info = emu_finder.download()
+    for k, (r, s) in enumerate(zip(ref, sets)):
+        o = oracle_run(s)
+        assert info[k].status == o["status"] == r.status
+        if r.status == 0:
+            q0, q1 = int(batch.set_start[k]), int(batch.set_start[k + 1])
+            assert list(rot[q0:q1]) == list(o["rotations"])
+    with pytest.raises(CsaGpuError):
+        emu_finder.shard_view()                      # the sharded run is over
+
+
+@pytest.mark.parametrize("ngpus", [2, 3])
+def test_emu_one_process_several_gpus(ngpus):
+    """csa_gpu_multi_*: the C host's way to several GPUs (one thread per GPU, bucket exchange by peer copies), here
+    over the CPU single-stepper: rotations and block lists equal the oracle's"""
+    from common import EMU_LIB, build_emu
+    from csa_b200.api import MultiRotationFinder
+    build_emu()
+    mf = MultiRotationFinder(ngpus, lib_path=EMU_LIB)
+    rng = random.Random(50 + ngpus)
+    try:
+        for trial in range(5):
+            sets = [gen_case(rng, max_n=1500)[1] for _ in range(1 if trial < 3 else 3)]
+            mf.first.debug_rounds(4 if trial % 2 else 0)   # (set on GPU 0 only: the other GPUs keep the free choice)
+            rot, info = mf.find_rotations_batch(sets, flags=1)
+            (depth, size, total, interval, nxt), pos = mf.first.blocks()
+            b0 = 0
+            q = 0
+            for k, s in enumerate(sets):
+                o = oracle_run(s)
+                assert info[k].status == o["status"], (trial, k)
+                if o["status"] == 0:
+                    assert list(rot[q:q + len(s)]) == list(o["rotations"])
+                    nb = info[k].nblocks
+                    assert np.array_equal(depth[b0:b0 + nb], o["depth"]) and np.array_equal(size[b0:b0 + nb], o["size"])
+                    assert info[k].count_collected == o["count_collected"] and info[k].count_suffixfree == o["count_suffixfree"]
+                b0 += info[k].nblocks
+                q += len(s)
+    finally:
+        mf.first.debug_rounds(0)
+        mf.close()
+

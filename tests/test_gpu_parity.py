@@ -282,3 +282,34 @@ def test_gpu_randomized_sweep_all_paths(gpu_finder, seed0):
                     compare_with_oracle(r, o, s, f"seed {seed} mode {mode} case {i}")
     finally:
         gpu_finder.debug_rounds(0)
+
+
+def test_gpu_one_process_several_gpus():
+    """csa_gpu_multi_*: one process, one host thread per GPU, bucket exchange by peer copies; needs two GPUs
+    (skipped on a one-GPU box; tests/test_emu_pipeline.py covers the logic on the CPU single-stepper)"""
+    import torch
+    from csa_b200.api import MultiRotationFinder, RotationFinder
+    from csa_b200.workloads import make_batch, batch_sets
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU")
+    mf = MultiRotationFinder(min(n, 4))
+    one = RotationFinder(device=0)
+    try:
+        for batch in (make_batch(1, 6, 400_000, 0.01, 0.001, seed=31, population=True), workload_batch("mammals", 5, seed=32)):
+            sets = batch_sets(batch)
+            ref = one.find_rotations_batch(sets)
+            rot, info = mf.find_rotations_batch(sets)
+            (depth, size, total, interval, nxt), pos = mf.first.blocks()
+            b0 = 0
+            for k, r in enumerate(ref):
+                q0, q1 = int(batch.set_start[k]), int(batch.set_start[k + 1])
+                assert info[k].status == r.status == 0
+                assert np.array_equal(rot[q0:q1], r.rotations)
+                nb = info[k].nblocks
+                assert np.array_equal(depth[b0:b0 + nb], r.depth) and np.array_equal(size[b0:b0 + nb], r.size)
+                assert np.array_equal(nxt[b0:b0 + nb], r.next)
+                b0 += nb
+    finally:
+        mf.close()
+        one.close()
