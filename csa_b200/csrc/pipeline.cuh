@@ -2314,17 +2314,22 @@ static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
 // After the first sort every group holds the rotations that share their first L0 letters -- in a set of
 // related genomes mostly the m homologous copies of one place.  Prefix doubling would now shuffle RANKS
 // through HBM round after round.  The packed, doubled text of a whole batch, however, is a few tens of MB
-// and lives in the 126 MB L2, so a team of threads can simply read on: it takes a chunk of the suffix
-// array and, 32 letters (one u64 per suffix) at a time, splits every group by the next word until each
-// suffix stands alone or the depth limit is reached.  A split is a three-way partition around the word
-// of the group's first suffix (smaller | equal | larger, stable); the places come from warp ballots and
-// popcounts, not from comparisons between suffixes, and the partition is repeated at the same depth until
-// no group holds two different words.  The place where two neighbours part IS their LCP, so the LCP
-// array falls out of the same pass (gencycsuffixtrees.c:500: never more than the shorter rotation -- the
-// walk stops below the shortest sequence of the set; deeper groups are left to the doubling rounds).
+// and lives in the 126 MB L2, so the suffixes of a group can simply be compared letter word by letter word:
+// every pair of suffixes of a group once (see ws_pairs below), WS_STEP words of 32 letters per round trip.
+// A suffix's place in its group = the number of smaller ones; the most letters it shares with a smaller
+// one IS its LCP (its predecessor is the smaller suffix it shares most with), so the LCP array falls out
+// of the same pass (gencycsuffixtrees.c:500: never more than the shorter rotation -- pairs are followed
+// to below the shortest sequence of the set; pairs that agree that far count as equal and their groups
+// are left to the doubling rounds, as are groups of more than WS_BIG_CAP suffixes).
 //   k_wsort     one warp per chunk: the groups that start inside WS_NOM consecutive places (<= 128 suffixes)
 //   k_wsort_big one CTA per group that does not fit a warp's window (<= 1024 suffixes)
 // HBM traffic: head 4 B per suffix in; sa 4 B in, sa + head + lcp 12 B out per suffix of a group.
+// Cost: ~0.05 ns per pair on a B200.  Pairs grow with the square of the group, so this is the path for sets
+// of a handful of genomes (groups of ~m) and the host falls back on rank doubling when the groups hold too
+// many pairs (WS_PAIRS_PER_SUFFIX).  Two other designs were built and measured on the same data before this
+// one and lost: splitting the groups 32 letters at a time in lock step (partition places from ballots and
+// popcounts: ~100 warp-synchronous passes per chunk, 2-3 % of the lanes busy in the tail -- 18-25 ms where
+// this takes 4), and a literal insertion by binary search (more letters read than all pairs for m <= 16).
 #define WS_NOM 32    // SA places whose groups one warp takes
 #define WS_CAP 128   // suffixes a warp can hold
 #define WS_T 4
