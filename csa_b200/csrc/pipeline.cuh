@@ -2326,10 +2326,11 @@ static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
 // HBM traffic: head 4 B per suffix in; sa 4 B in, sa + head + lcp 12 B out per suffix of a group.
 // Cost: ~0.05 ns per pair on a B200.  Pairs grow with the square of the group, so this is the path for sets
 // of a handful of genomes (groups of ~m) and the host falls back on rank doubling when the groups hold too
-// many pairs (WS_PAIRS_PER_SUFFIX).  Two other designs were built and measured on the same data before this
-// one and lost: splitting the groups 32 letters at a time in lock step (partition places from ballots and
-// popcounts: ~100 warp-synchronous passes per chunk, 2-3 % of the lanes busy in the tail -- 18-25 ms where
-// this takes 4), and a literal insertion by binary search (more letters read than all pairs for m <= 16).
+// many pairs (WS_PAIRS_PER_SUFFIX).  Another design was built and measured on the same data before this one
+// and lost: splitting the groups 32 letters at a time in lock step, a warp per chunk (partition places by
+// counting, then from ballots and popcounts): ~100 warp-synchronous passes per chunk with 2-3 % of the lanes
+// busy in the tail -- 18-25 ms on 64 sets of 32 sequences, 2.8-4.2 ms on 160 Mammals-shaped sets where this
+// takes 1.4.
 #define WS_NOM 32    // SA places whose groups one warp takes
 #define WS_CAP 128   // suffixes a warp can hold
 #define WS_T 4
