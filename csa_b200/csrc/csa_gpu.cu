@@ -612,7 +612,7 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
             sorted_len *= 2;
         }
     }
-    TRY(d2d(ex, c->sa.p, c->valsA.p, sizeof(u32) * (size_t)N));
+    std::swap(c->sa, c->valsA); // (both N x u32: the sorted suffixes become `sa`, the old buffer the next sort's scratch)
     return 0;
 }
 
@@ -628,11 +628,11 @@ static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     TRY(dev_alloc(c->saidx0, sizeof(u32) * (size_t)c->N0));
     TRY(d2d(ex, c->saidx0.p, c->valsA.p, sizeof(u32) * (size_t)c->N0));
     { NextArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA), nxt, P<u32>(c->firstmax)}; launch_next(ex, N, a); }
-    { CoverArgs a{v, sa, nxt, P<u32>(c->firstmax), R}; launch_cover(ex, N, a); }
+    { CoverArgs a{v, sa, nxt, P<u32>(c->firstmax), R}; launch_cover(ex, N, a); launch_coverstart(ex, nsets, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, R, R, N)));
     u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3), *bidx = P<u32>(c->t4);
-    { BlockFindArgs a{v, sa, lcp, R, isblock, depth}; launch_blockfind(ex, N, a); }
-    { DegenArgs a{v, sa, lcp, R, P<u32>(c->set_flags)}; launch_degen(ex, N, a); }
+    { BlockFindArgs a{v, sa, lcp, R, isblock, depth, c->mmax}; launch_blockfind(ex, N, a); }
+    { DegenArgs a{v, sa, lcp, R, P<u32>(c->set_flags), c->batch_nmin}; launch_degen(ex, N, a); }
     TRY((scan_u32<ScanSum, false>(ex, c->ps, isblock, bidx, N)));
     u32 last_idx = 0, last_flag = 0;
     TRY(read_u32(c, bidx + (N - 1), &last_idx));

@@ -418,16 +418,16 @@ HD void next_body(long long j, const NextArgs &a) {
 MAP_KERNEL(next, NextArgs, 16)
 
 struct CoverArgs { BatchView v; const u32 *sa; const u32 *nxt; const u32 *firstmax; u32 *cover; };
-HD void cover_body(long long i, const CoverArgs &a) {
-    u32 s = set_of_pos(a.v, (u32)i);
-    u32 s0 = LDG(a.v.set_base0 + s);
-    a.cover[i] = ((u32)i == s0) ? a.firstmax[s] : a.nxt[i - 1];
-}
-MAP_KERNEL(cover, CoverArgs, 16)
+HD void cover_body(long long i, const CoverArgs &a) { a.cover[i] = i > 0 ? a.nxt[i - 1] : 0u; }
+MAP_KERNEL(cover, CoverArgs, 8)
+// ... and the first place of every set starts from the last first-occurrence of any colour (launched after k_cover,
+// one thread per set: no search for the set of every place)
+HD void coverstart_body(long long s, const CoverArgs &a) { a.cover[LDG(a.v.set_base0 + s)] = a.firstmax[s]; }
+MAP_KERNEL(coverstart, CoverArgs, 8)
 
 // blocks: LCP intervals of exactly m suffixes, one of every sequence, that cannot be extended to
 // the left by one and the same letter (csamsa.c:64,80,283).  One thread per left border.
-struct BlockFindArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *isblock; u32 *depth; };
+struct BlockFindArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *isblock; u32 *depth; u32 mmax; };
 HD unsigned letter_before_suffix(const BatchView &v, u32 g) {
     u32 k = seq_of_few(v, g);
     u32 off = LDG(v.seq_off + k), n = LDG(v.seq_off + k + 1) - off;
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(256) k_blockfind(long long n, BlockFindArgs a)
     const unsigned lane = threadIdx.x & 31u;
     u32 lb = (u32)i, s0 = 0, s1 = 0, m = 0;
     bool cand = false;
-    if (i < n) {
+    if (i < n && a.R[lb] - lb < a.mmax) { // (a window wider than the largest set's m holds a repeat: no search for the set)
         u32 s = set_of_pos(a.v, lb);
         s0 = LDG(a.v.set_base0 + s); s1 = LDG(a.v.set_base0 + s + 1);
         m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
@@ -529,9 +529,10 @@ static inline void launch_blockfind(Exec &ex, long long n, BlockFindArgs a) {
 
 // a whole rotation of the shortest sequence occurs in every sequence: the reference walks off its
 // tree (undefined behaviour).  Maximal runs of lcp >= nmin that hold every sequence.
-struct DegenArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *set_flags; };
+struct DegenArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *set_flags; u32 batch_nmin; };
 HD void degen_body(long long i, const DegenArgs &a) {
     u32 lb = (u32)i;
+    if (lb + 1 >= a.v.N || a.lcp[lb + 1] < a.batch_nmin) return; // (no set's shortest sequence is shorter: no search needed)
     u32 s = set_of_pos(a.v, lb);
     u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
     u32 nmin = LDG(a.v.set_nmin + s);
