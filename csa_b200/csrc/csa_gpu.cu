@@ -46,7 +46,7 @@ struct csa_gpu_ctx {
     u32 B = 0, E = 0;
     long long launches = 0;
     // ---- device ----
-    DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, seq_nmin, dbl_off, z0;
+    DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, dbl_off, z0;
     DevMem rs_start, rs_count, rs_cbase, rs_stride;
     u32 rs_nblocks = 0;
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, t5, counter, tiles;
@@ -84,7 +84,7 @@ static BatchView view_of(csa_gpu_ctx *c) {
     v.nsets = c->nsets; v.M = c->M; v.N = c->N;
     v.seq_off = P<u32>(c->seq_off); v.seq_set = P<u32>(c->seq_set);
     v.set_seq0 = P<u32>(c->set_seq0); v.set_base0 = P<u32>(c->set_base0);
-    v.set_nmin = P<u32>(c->set_nmin); v.seq_nmin = P<u32>(c->seq_nmin); v.dbl_off = P<u64>(c->dbl_off);
+    v.set_nmin = P<u32>(c->set_nmin); v.dbl_off = P<u64>(c->dbl_off);
     v.seqof = P<u32>(c->seqof); v.code = P<unsigned char>(c->code);
     v.p2 = P<u64>(c->p2); v.pm = P<u32>(c->pm);
     return v;
@@ -137,7 +137,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
     cudaStreamSynchronize(c->ex.stream);
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
-                     &c->set_nmin, &c->seq_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
+                     &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
                      &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->bk_hist, &c->chb_sets, &c->chb_evbase, &c->chb_events, &c->chb_work, &c->chb_redo, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
                      &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->blk_lb,
@@ -251,13 +251,6 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     TRY(h2d(ex, c->set_seq0.p, c->h_set_seq0.data(), sizeof(u32) * (nsets + 1)));
     TRY(h2d(ex, c->set_base0.p, c->h_set_base0.data(), sizeof(u32) * (nsets + 1)));
     TRY(h2d(ex, c->set_nmin.p, c->h_set_nmin.data(), sizeof(u32) * nsets));
-    {
-        std::vector<u32> sn((size_t)M);
-        for (long long k = 0; k < M; k++) sn[k] = c->h_set_nmin[c->h_seq_set[k]];
-        TRY(dev_alloc(c->seq_nmin, sizeof(u32) * M));
-        TRY(h2d(ex, c->seq_nmin.p, sn.data(), sizeof(u32) * M));
-        TRY(exec_sync(ex)); // sn goes out of scope
-    }
     TRY(h2d(ex, c->dbl_off.p, c->h_dbl_off.data(), sizeof(u64) * (M + 1)));
     TRY(h2d(ex, c->z0.p, c->h_z0.data(), sizeof(u32) * (nsets + 1)));
     {   // tile-blocks of the first (segmented) sort: none straddles a set

@@ -29,7 +29,6 @@ struct BatchView {
     const u32 *set_seq0;       // [nsets+1] first sequence of set s
     const u32 *set_base0;      // [nsets+1] first base (== first SA index) of set s
     const u32 *set_nmin;       // [nsets] shortest sequence of set s
-    const u32 *seq_nmin;       // [M] the same, by sequence (one lookup instead of two)
     const u64 *dbl_off;        // [M+1] first base of sequence k in the doubled, packed text
     u32 *seqof;                // [N] sequence of base g
     unsigned char *code;       // [N] letter codes 0..4
@@ -2796,7 +2795,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
             s.x[t] = LDG(a.v.dbl_off + k) + (g - LDG(a.v.seq_off + k));
             s.g[t] = g;
             s.ct[t] = 0; s.best[t] = 0; s.clsz[t] = 0;
-            const u32 nm = LDG(a.v.seq_nmin + k);
+            const u32 nm = LDG(a.v.set_nmin + LDG(a.v.seq_set + k));
             nmin = nm < nmin ? nm : nmin;
         }
     }
@@ -2835,7 +2834,7 @@ __global__ void __launch_bounds__(WS_BIG_WARPS * 32) k_wsort_big(WSortArgs a) {
             s.ct[t] = 0; s.best[t] = 0; s.clsz[t] = 0;
         }
     }
-    const u32 nmin = LDG(a.v.seq_nmin + seq_of(a.v, a.sa[start])); // a group never leaves its set
+    const u32 nmin = LDG(a.v.set_nmin + LDG(a.v.seq_set + seq_of(a.v, a.sa[start]))); // a group never leaves its set
     __syncthreads();
     ws_pairs<MASKS, WS_BIG_WARPS>(a, s, tid, start, act, nmin < a.depth_cap ? nmin : a.depth_cap);
 }
