@@ -312,7 +312,18 @@ HD void lcp_body(long long t, const LcpArgs &a) {
     u32 k = CSA_NONE, off = 0, n = 0, s0 = 0;
     u64 dk = 0;
     u32 h = 0;
+    // the chain inverse SA entry -> predecessor -> its sequence is three trips to memory per suffix: a three-stage
+    // pipeline in registers -- the entry of the suffix three on, the predecessor of the one two on and the sequence
+    // of the next one's predecessor are fetched while this suffix is compared
+    u32 r_0 = a.isa[g0], r_1 = g0 + 1 < g1 ? a.isa[g0 + 1] : 0u, r_2 = g0 + 2 < g1 ? a.isa[g0 + 2] : 0u;
+    u32 b_0 = r_0 > 0 ? a.sa[r_0 - 1] : 0u, b_1 = (g0 + 1 < g1 && r_1 > 0) ? a.sa[r_1 - 1] : 0u;
+    u32 kb_0 = seq_of(a.v, b_0);
     for (u32 g = g0; g < g1; g++) {
+        const u32 r_3 = g + 3 < g1 ? a.isa[g + 3] : 0u;
+        const u32 b_2 = (g + 2 < g1 && r_2 > 0) ? a.sa[r_2 - 1] : 0u;
+        const u32 kb_1 = g + 1 < g1 ? seq_of(a.v, b_1) : 0u;
+        const u32 r = r_0, b = b_0, kb = kb_0;
+        r_0 = r_1; r_1 = r_2; r_2 = r_3; b_0 = b_1; b_1 = b_2; kb_0 = kb_1;
         u32 kg = seq_of(a.v, g);
         if (kg != k) { // a new sequence begins: nothing carries over
             k = kg;
@@ -322,10 +333,7 @@ HD void lcp_body(long long t, const LcpArgs &a) {
             dk = LDG(a.v.dbl_off + k);
             h = 0;
         }
-        u32 r = a.isa[g];
         if (r == s0) { a.lcp[r] = 0; h = 0; continue; } // first suffix of its set
-        u32 b = a.sa[r - 1];
-        u32 kb = seq_of(a.v, b);
         u32 ob = LDG(a.v.seq_off + kb), nb = LDG(a.v.seq_off + kb + 1) - ob;
         u32 cap = n < nb ? n : nb;
         if (h > cap) h = cap;
