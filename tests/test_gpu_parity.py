@@ -313,3 +313,26 @@ def test_gpu_one_process_several_gpus():
     finally:
         mf.close()
         one.close()
+
+
+@pytest.mark.parametrize("name,nsets", [("bacterial", 1), ("mammals", 480), ("sets32", 192)])
+def test_gpu_full_size_paths_agree(gpu_finder, name, nsets):
+    """BASELINE.json's full sizes (80-100 M suffixes per batch), where the oracle is out of reach: the two independent
+    ways to the suffix array -- rank doubling + LCP kernels, word sort with its own LCPs -- must give the same
+    rotations, suffix array, LCP array and block lists (they share only the first sort)"""
+    batch = workload_batch(name, nsets, seed=1000)
+    out = {}
+    try:
+        for mode in (5, 6):
+            gpu_finder.debug_rounds(mode)
+            gpu_finder.upload(batch)
+            gpu_finder.run()
+            rot, info = gpu_finder.download()
+            sa, lcp = gpu_finder.suffix_array()
+            (depth, size, total, interval, nxt), pos = gpu_finder.blocks()
+            out[mode] = (rot, sa, lcp[1:], depth, size, total, interval, nxt, pos, np.array([i.status for i in info]))
+    finally:
+        gpu_finder.debug_rounds(0)
+    assert (out[5][9] == 0).all()
+    for x, y in zip(out[5], out[6]):
+        assert np.array_equal(x, y)
