@@ -50,6 +50,7 @@ class SetResult:
     interval: np.ndarray = field(default=None)
     next: np.ndarray = field(default=None)
     positions: np.ndarray = field(default=None)   # nblocks x nseqs
+    letters: list = field(default=None)           # per block: its letters as blockLabel spells them (with_letters=True)
 
 
 def _load(path):
@@ -73,6 +74,8 @@ def _load(path):
     lib.csa_gpu_batch_num_positions.argtypes = [vp]
     lib.csa_gpu_batch_num_positions.restype = C.c_longlong
     lib.csa_gpu_batch_blocks.argtypes = [vp, ip, ip, ip, ip, ip, ip]
+    lib.csa_gpu_batch_block_letters.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong)]
+    lib.csa_gpu_batch_block_letters.restype = C.c_longlong
     lib.csa_gpu_batch_num_suffixes.argtypes = [vp]
     lib.csa_gpu_batch_num_suffixes.restype = C.c_longlong
     lib.csa_gpu_batch_suffix_array.argtypes = [vp, C.POINTER(C.c_uint), ip]
@@ -207,6 +210,21 @@ class RotationFinder:
         self._check(self.lib.csa_gpu_batch_blocks(self.ctx, *[_ip(a) for a in arrs], _ip(pos)))
         return [a[:nb] for a in arrs], pos[:ne]
 
+    def block_letters(self):
+        """per block of the batch (final list order): its letters as nodeslinkedlists.c:128 blockLabel spells them"""
+        nb = self.lib.csa_gpu_batch_num_blocks(self.ctx)
+        off = (C.c_longlong * (nb + 1))()
+        total = self.lib.csa_gpu_batch_block_letters(self.ctx, None, off)
+        if total < 0:
+            self._check(int(total))
+        buf = C.create_string_buffer(max(int(total), 1))
+        if total:
+            rc = self.lib.csa_gpu_batch_block_letters(self.ctx, buf, None)
+            if rc < 0:
+                self._check(int(rc))
+        raw = buf.raw
+        return [raw[off[b]:off[b + 1]] for b in range(nb)]
+
     def suffix_array(self):
         n = self.lib.csa_gpu_batch_num_suffixes(self.ctx)
         sa = np.zeros(n, dtype=np.uint32)
@@ -240,7 +258,7 @@ class RotationFinder:
 
     # ---- whole calls ----
     def find_rotations_batch(self, sets: Sequence[Sequence[bytes]], max_interval: int = INT_MAX,
-                             flags: int = 0, with_blocks: bool = True) -> List[SetResult]:
+                             flags: int = 0, with_blocks: bool = True, with_letters: bool = False) -> List[SetResult]:
         batch = sets if isinstance(sets, Batch) else Batch(sets)
         self.upload(batch)
         self.run(max_interval, flags)
@@ -248,6 +266,7 @@ class RotationFinder:
         out = []
         if with_blocks:
             (depth, size, total, interval, nxt), pos = self.blocks()
+        letters = self.block_letters() if with_blocks and with_letters else None
         p = 0
         for s in range(batch.nsets):
             q0, q1 = int(batch.set_start[s]), int(batch.set_start[s + 1])
@@ -260,12 +279,15 @@ class RotationFinder:
                 r.depth, r.size, r.totalsize = depth[b0:b0 + nb], size[b0:b0 + nb], total[b0:b0 + nb]
                 r.interval, r.next = interval[b0:b0 + nb], nxt[b0:b0 + nb]
                 r.positions = pos[p:p + nb * m].reshape(nb, m)
+                if letters is not None:
+                    r.letters = letters[b0:b0 + nb]
                 p += nb * m
             out.append(r)
         return out
 
-    def find_rotations(self, seqs: Sequence[bytes], max_interval: int = INT_MAX, flags: int = 0) -> SetResult:
-        return self.find_rotations_batch([seqs], max_interval, flags)[0]
+    def find_rotations(self, seqs: Sequence[bytes], max_interval: int = INT_MAX, flags: int = 0,
+                       with_letters: bool = False) -> SetResult:
+        return self.find_rotations_batch([seqs], max_interval, flags, with_letters=with_letters)[0]
 
 
 class MultiRotationFinder:

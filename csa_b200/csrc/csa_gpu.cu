@@ -3,6 +3,7 @@
 // (With -DCSA_EMU and g++ the same file gives tests/emu/libcsa_emu.so, a CPU single-stepper of
 // the kernel bodies used by the CPU-only tests; it is never part of the product.)
 #include "pipeline.cuh"
+#include "rare.cuh"
 #include "../../include/csa_gpu.h"
 #include <algorithm>
 #include <vector>
@@ -65,10 +66,13 @@ struct csa_gpu_ctx {
     int rounds_tiled = 0, rounds_global = 0, rounds_quad = 0, force_global_rounds = 0, no_quad_rounds = 0;
     DevMem pyr, sa0, saidx0, leaf_set, lcp0, psv, nsv, pse, parent, nsize, minpos, val, up, val2, up2;
     DevMem set_nblocks, set_blk0, set_pos0, set_flags, set_nchains, set_cyclic, firstmax, set_collected, set_suffixfree;
+    DevMem set_neff, seq_per, rare_collected, rare_suffixfree; // rare.cuh
+    u32 *dfs = nullptr;         // DFS numbers of the sequence-0 tree's nodes (one of val/val2) after stage_seq0_tree
     bool have_stats = false;
     std::vector<u32> h_set_collected, h_set_suffixfree;
     DevMem blk_lb, blk_depth, blk_set, order, o_depth, o_set, o_pos, elem_blk, seghead, succ_lo, succ_hi;
     DevMem next, gap, size, total, interval, inv, f_depth, f_size, f_total, f_interval, f_next, f_pos, rotations;
+    DevMem blk_leaf, f_leaf, f_set, let_off, let_out; // csa_gpu_batch_block_letters
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
     // per-kernel profile of the last run (csa_gpu_profile_*)
@@ -140,10 +144,10 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
                      &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
                      &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->bk_hist, &c->chb_sets, &c->chb_evbase, &c->chb_events, &c->chb_work, &c->chb_redo, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
                      &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
-                     &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->blk_lb,
+                     &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->set_neff, &c->seq_per, &c->rare_collected, &c->rare_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
                      &c->succ_lo, &c->succ_hi, &c->next, &c->gap, &c->size, &c->total, &c->interval, &c->inv, &c->f_depth,
-                     &c->f_size, &c->f_total, &c->f_interval, &c->f_next, &c->f_pos, &c->rotations};
+                     &c->f_size, &c->f_total, &c->f_interval, &c->f_next, &c->f_pos, &c->rotations, &c->blk_leaf, &c->f_leaf, &c->f_set, &c->let_off, &c->let_out};
     for (DevMem *m : all) dev_free(*m);
     for (int i = 0; i < 4; i++) dev_free(c->ps.block_sums[i]);
     dev_free(c->ps.counts);
@@ -609,6 +613,7 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     return 0;
 }
 
+// cover array and block candidates (collectNodes / removeSuffixNodes / removeNonUniqueNodes on ordinary sets)
 static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
     u32 N = c->N;
@@ -623,9 +628,18 @@ static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     { NextArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA), nxt, P<u32>(c->firstmax)}; launch_next(ex, N, a); }
     { CoverArgs a{v, sa, nxt, P<u32>(c->firstmax), R}; launch_cover(ex, N, a); launch_coverstart(ex, nsets, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, R, R, N)));
-    u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3), *bidx = P<u32>(c->t4);
+    u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3);
     { BlockFindArgs a{v, sa, lcp, R, isblock, depth, c->mmax}; launch_blockfind(ex, N, a); }
-    { DegenArgs a{v, sa, lcp, R, P<u32>(c->set_flags), c->batch_nmin}; launch_degen(ex, N, a); }
+    return 0;
+}
+
+// the block borders compacted into the batch's block list (after rare.cuh had its say on marked sets)
+static int stage_emit_blocks(csa_gpu_ctx *c, const BatchView &v) {
+    Exec &ex = c->ex;
+    u32 N = c->N;
+    int nsets = c->nsets;
+    u32 *sa = P<u32>(c->sa);
+    u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3), *bidx = P<u32>(c->t4);
     TRY((scan_u32<ScanSum, false>(ex, c->ps, isblock, bidx, N)));
     u32 last_idx = 0, last_flag = 0;
     TRY(read_u32(c, bidx + (N - 1), &last_idx));
@@ -671,13 +685,26 @@ static int stage_stats(csa_gpu_ctx *c, const BatchView &v) {
     c->h_set_collected.assign(nsets, 0); c->h_set_suffixfree.assign(nsets, 0);
     TRY(d2h(ex, c->h_set_collected.data(), c->set_collected.p, sizeof(u32) * nsets));
     TRY(d2h(ex, c->h_set_suffixfree.data(), c->set_suffixfree.p, sizeof(u32) * nsets));
+    {   // marked sets: the counts of the literal list walk (rare.cuh)
+        std::vector<u32> fl(nsets), rc(nsets), rs(nsets);
+        TRY(d2h(ex, fl.data(), c->set_flags.p, sizeof(u32) * nsets));
+        bool any = false;
+        for (u32 f : fl) any |= (f & CSA_FLAG_RARE) != 0;
+        if (any) {
+            TRY(d2h(ex, rc.data(), c->rare_collected.p, sizeof(u32) * nsets));
+            TRY(d2h(ex, rs.data(), c->rare_suffixfree.p, sizeof(u32) * nsets));
+            for (int s = 0; s < nsets; s++)
+                if (fl[s] & CSA_FLAG_RARE) { c->h_set_collected[s] = rc[s]; c->h_set_suffixfree[s] = rs[s]; }
+        }
+    }
     c->have_stats = true;
     return 0;
 }
 
-static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
+// the LCP-interval tree of sequence 0 of every set and the DFS number of each of its nodes (c->dfs)
+static int stage_seq0_tree(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
-    u32 N = c->N, N0 = c->N0, B = c->B;
+    u32 N0 = c->N0;
     u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t5);
     size_t n1 = sizeof(u32) * (size_t)N0, n2 = 2 * n1;
     DevMem *one[] = {&c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv, &c->pse};
@@ -728,9 +755,18 @@ static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
             if (!m) break;
         }
     }
+    c->dfs = val;
+    return 0;
+}
+
+static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
+    Exec &ex = c->ex;
+    u32 N0 = c->N0, B = c->B;
+    u32 *sa = P<u32>(c->sa);
     // order the blocks: DFS number descending, then stably (set, depth descending)
-    BlockKeyArgs k{v, sa, P<u32>(c->saidx0), P<u32>(c->z0), val, N0, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set),
-                   P<u64>(c->keysA), P<u32>(c->valsA), 0};
+    TRY(dev_alloc(c->blk_leaf, sizeof(u32) * (size_t)B));
+    BlockKeyArgs k{v, sa, P<u32>(c->saidx0), P<u32>(c->z0), c->dfs, N0, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set),
+                   P<u64>(c->keysA), P<u32>(c->valsA), 0, P<u32>(c->blk_leaf)};
     launch_blockkey(ex, B, k);
     TRY(sort_pairs(c, B, 0, 32));
     k.keys = P<u64>(c->keysA); k.vals = P<u32>(c->valsA); k.pass = 1;
@@ -747,7 +783,7 @@ static int stage_chain(csa_gpu_ctx *c, const BatchView &v, int max_interval) {
     int nsets = c->nsets;
     size_t nb = sizeof(u32) * (size_t)B, ne = sizeof(u32) * (size_t)E;
     DevMem *perblock[] = {&c->o_depth, &c->o_set, &c->succ_lo, &c->succ_hi, &c->next, &c->gap, &c->size, &c->total,
-                          &c->interval, &c->inv, &c->f_depth, &c->f_size, &c->f_total, &c->f_interval, &c->f_next};
+                          &c->interval, &c->inv, &c->f_depth, &c->f_size, &c->f_total, &c->f_interval, &c->f_next, &c->f_leaf, &c->f_set};
     for (DevMem *m : perblock) TRY(dev_alloc(*m, nb));
     DevMem *perelem[] = {&c->o_pos, &c->elem_blk, &c->seghead, &c->f_pos};
     for (DevMem *m : perelem) TRY(dev_alloc(*m, ne));
@@ -768,6 +804,11 @@ static int stage_chain(csa_gpu_ctx *c, const BatchView &v, int max_interval) {
     TRY(dev_zero(ex, c->succ_hi.p, nb));
     { LinkArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->seghead), P<u32>(c->o_depth), ebits, P<u32>(c->succ_lo), P<u32>(c->succ_hi)};
       launch_link(ex, E, a); }
+    { RareWalkArgs a{v, sa, P<u32>(c->t5), P<u32>(c->t1), P<u32>(c->set_flags), P<u32>(c->set_neff), P<u32>(c->seq_per), P<u32>(c->t2),
+                     set_blk0, set_pos0, P<u32>(c->o_depth), P<int>(c->o_pos),
+                     {P<u32>(c->keysA), P<u32>(c->keysA) + c->N, P<u32>(c->keysB), P<u32>(c->keysB) + c->N, P<u32>(c->valsA), P<u32>(c->valsB)},
+                     P<u32>(c->succ_lo), P<u32>(c->succ_hi)};
+      launch_rarewalk(ex, nsets, a); }
     { GapArgs a{v, P<u32>(c->succ_lo), P<u32>(c->succ_hi), P<u32>(c->o_depth), P<u32>(c->o_set), P<int>(c->o_pos), set_blk0, set_pos0,
                 max_interval, P<int>(c->next), P<int>(c->gap)};
       launch_gap(ex, B, a); }
@@ -821,8 +862,10 @@ static int stage_chain(csa_gpu_ctx *c, const BatchView &v, int max_interval) {
     { InvArgs a{P<u32>(c->valsA), P<u32>(c->inv)}; launch_inv(ex, B, a); }
     { FinalArgs a{v, P<u32>(c->valsA), P<u32>(c->inv), P<u32>(c->o_depth), P<u32>(c->o_set), P<int>(c->o_pos), P<int>(c->size),
                   P<int>(c->total), P<int>(c->interval), P<int>(c->next), set_blk0, set_pos0, P<int>(c->f_depth), P<int>(c->f_size),
-                  P<int>(c->f_total), P<int>(c->f_interval), P<int>(c->f_next), P<int>(c->f_pos)};
+                  P<int>(c->f_total), P<int>(c->f_interval), P<int>(c->f_next), P<int>(c->f_pos),
+                  P<u32>(c->order), P<u32>(c->blk_leaf), P<u32>(c->f_leaf)};
       launch_final(ex, B, a); }
+    TRY(d2d(ex, c->f_set.p, c->o_set.p, nb)); // (sets are contiguous in both orders: block i of the final list belongs to o_set[i])
     return 0;
 }
 
@@ -839,12 +882,15 @@ static int run_phases(csa_gpu_ctx *c, int max_interval, unsigned flags, int phas
     u32 N = c->N;
     int nsets = c->nsets;
     size_t n4 = sizeof(u32) * (size_t)N;
-    TRY(dev_alloc(c->keysA, 2 * n4)); TRY(dev_alloc(c->keysB, 2 * n4));
-    TRY(dev_alloc(c->valsA, n4)); TRY(dev_alloc(c->valsB, n4)); TRY(dev_alloc(c->sa, n4));
+    // (the sort buffers also serve the sequence-0 tree: 2 N0 nodes, more than N when a set's first sequence is its longest by far)
+    size_t nk = sizeof(u32) * (size_t)std::max<u64>(N, 2ull * c->N0);
+    TRY(dev_alloc(c->keysA, 2 * nk)); TRY(dev_alloc(c->keysB, 2 * nk));
+    TRY(dev_alloc(c->valsA, nk)); TRY(dev_alloc(c->valsB, nk)); TRY(dev_alloc(c->sa, nk)); // (sa and valsA trade places after the suffix sort)
     TRY(dev_alloc(c->t0, n4)); TRY(dev_alloc(c->t1, n4)); TRY(dev_alloc(c->t2, n4)); TRY(dev_alloc(c->t3, n4)); TRY(dev_alloc(c->t4, n4)); TRY(dev_alloc(c->t5, n4));
     TRY(dev_alloc(c->counter, 256));
     DevMem *perset[] = {&c->set_nblocks, &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax,
-                        &c->set_collected, &c->set_suffixfree};
+                        &c->set_collected, &c->set_suffixfree, &c->set_neff, &c->rare_collected, &c->rare_suffixfree};
+    TRY(dev_alloc(c->seq_per, sizeof(u32) * (size_t)c->M));
     for (DevMem *m : perset) TRY(dev_alloc(*m, sizeof(u32) * (nsets + 1)));
     TRY(dev_alloc(c->rotations, sizeof(int) * (size_t)c->M));
     TRY(dev_alloc(c->shard_bounds, sizeof(u32) * ((size_t)c->shard_nranks + 2)));
@@ -882,7 +928,18 @@ static int run_phases(csa_gpu_ctx *c, int max_interval, unsigned flags, int phas
     }
     mark(c, 2);
     TRY(dev_zero(ex, c->set_flags.p, sizeof(u32) * nsets));
+    // sets whose tree is not their suffix array (rare.cuh): marked here, redone by one thread each further down
+    { LeafScanArgs a{v, P<u32>(c->t5), P<u32>(c->set_flags), c->batch_nmin}; launch_leafscan(ex, N, a); }
+    { RareCollapseArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->set_flags), P<u32>(c->t2), P<u32>(c->set_neff), P<u32>(c->seq_per)};
+      launch_rarecollapse(ex, nsets, a); }
     TRY(stage_common_blocks(c, v));
+    TRY(stage_seq0_tree(c, v));
+    { RareBlocksArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->t1), P<u32>(c->set_flags), P<u32>(c->set_neff), P<u32>(c->seq_per), P<u32>(c->t2),
+                       P<u32>(c->saidx0), P<u32>(c->z0), c->dfs, c->N0,
+                       {P<u32>(c->keysA), P<u32>(c->keysA) + N, P<u32>(c->keysB), P<u32>(c->keysB) + N, P<u32>(c->valsA), P<u32>(c->valsB)},
+                       P<u32>(c->t0), P<u32>(c->t3), P<u32>(c->rare_collected), P<u32>(c->rare_suffixfree)};
+      launch_rareblocks(ex, nsets, a); }
+    TRY(stage_emit_blocks(c, v));
     c->have_stats = false;
     if (flags & CSA_GPU_FLAG_STATS) TRY(stage_stats(c, v));
     mark(c, 3);
@@ -1128,10 +1185,11 @@ extern "C" int csa_gpu_batch_download(csa_gpu_ctx *c, int *rotations, csa_gpu_se
     for (int s = 0; s < nsets; s++) {
         int status = CSA_SET_OK;
         u32 fl = c->h_set_flags[s];
-        // the order of the reference's exits: the tree walk (csamsa.c:64) comes before the counts
-        if (fl & 1u) status = CSA_SET_DEGENERATE;
+        // in the order in which the reference gets there (csamsa.c:324 analyzeTree)
+        if (fl & CSA_FLAG_UNDEFINED) status = CSA_SET_UNDEFINED;
         else if (c->h_set_nblocks[s] == 0) status = CSA_SET_NO_UNIQUE;
-        else if (fl & 2u) status = CSA_SET_NONTERMINATING;
+        else if (fl & CSA_FLAG_DEGENERATE) status = CSA_SET_DEGENERATE;
+        else if (fl & CSA_FLAG_HANG) status = CSA_SET_NONTERMINATING;
         if (rotations && status != CSA_SET_OK)
             for (u32 k = c->h_set_seq0[s]; k < c->h_set_seq0[s + 1]; k++) rotations[k] = 0;
         if (info) {
@@ -1167,6 +1225,33 @@ extern "C" int csa_gpu_batch_blocks(csa_gpu_ctx *c, int *depth, int *size, int *
     if (next) TRY(d2h(ex, next, c->f_next.p, nb));
     if (positions) TRY(d2h(ex, positions, c->f_pos.p, sizeof(int) * (size_t)c->E));
     return CSA_GPU_OK;
+}
+
+// the letters of every block, spelled as the reference's blockLabel spells them
+extern "C" long long csa_gpu_batch_block_letters(csa_gpu_ctx *c, char *letters, long long *offsets) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (!c->ran) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_block_letters before csa_gpu_batch_run");
+    Exec &ex = c->ex;
+    const u32 B = c->B;
+    std::vector<int> depth(B);
+    std::vector<unsigned long long> off((size_t)B + 1, 0);
+    if (B) TRY(d2h(ex, depth.data(), c->f_depth.p, sizeof(int) * (size_t)B));
+    for (u32 b = 0; b < B; b++) off[b + 1] = off[b] + (unsigned long long)depth[b];
+    if (offsets) for (u32 b = 0; b <= B; b++) offsets[b] = (long long)off[b];
+    const unsigned long long T = off[B];
+    if (!letters || T == 0) return (long long)T;
+#ifndef CSA_EMU
+    CUDA_TRY(cudaSetDevice(c->device));
+#endif
+    TRY(dev_alloc(c->let_off, sizeof(unsigned long long) * ((size_t)B + 1)));
+    TRY(dev_alloc(c->let_out, (size_t)T));
+    TRY(h2d(ex, c->let_off.p, off.data(), sizeof(unsigned long long) * ((size_t)B + 1)));
+    BlockLettersArgs a{view_of(c), P<unsigned char>(c->raw), P<u32>(c->z0), c->N0, P<u32>(c->parent), P<u32>(c->minpos), P<u32>(c->lcp0),
+                       P<int>(c->f_depth), P<int>(c->f_pos), P<u32>(c->f_leaf), P<u32>(c->f_set), P<u32>(c->set_blk0), P<u32>(c->set_pos0),
+                       P<unsigned long long>(c->let_off), B, P<char>(c->let_out)};
+    launch_blockletters(ex, (long long)T, a);
+    TRY(d2h(ex, letters, c->let_out.p, (size_t)T));
+    return (long long)T;
 }
 
 extern "C" int csa_gpu_batch_rotations(csa_gpu_ctx *c, int nsets, const int *set_start, const char *const *texts,

@@ -804,6 +804,7 @@ struct BlockKeyArgs {
     BatchView v; const u32 *sa; const u32 *saidx0; const u32 *z0; const u32 *dfs; u32 N0;
     const u32 *blk_lb; const u32 *blk_depth; const u32 *blk_set;
     u64 *keys; u32 *vals; int pass; // pass 0: dfs descending; pass 1: (set, depth descending)
+    u32 *blk_leaf;                  // pass 0: the block's leaf in the sequence-0 tree (k_blockletters climbs from it)
 };
 HD void blockkey_body(long long b, const BlockKeyArgs &a) {
     if (a.pass == 0) {
@@ -817,6 +818,7 @@ HD void blockkey_body(long long b, const BlockKeyArgs &a) {
                 u32 lo = 0, hi = n0;
                 while (lo < hi) { u32 mid = (lo + hi) >> 1; if (a.saidx0[z + mid] < j) lo = mid + 1; else hi = mid; }
                 d = a.dfs[a.N0 + z + lo];
+                a.blk_leaf[b] = z + lo;
             }
         a.keys[b] = 0xFFFFFFFFu - d;
         a.vals[b] = (u32)b;
@@ -1246,9 +1248,11 @@ struct FinalArgs {
     const int *size; const int *total; const int *interval; const int *next;
     const u32 *set_blk0; const u32 *set_pos0;
     int *f_depth; int *f_size; int *f_total; int *f_interval; int *f_next; int *f_pos;
+    const u32 *order0; const u32 *blk_leaf; u32 *f_leaf; // block b of the list order = block order0[b] of the emit order
 };
 HD void final_body(long long i, const FinalArgs &a) {
     u32 b = a.order[i];
+    a.f_leaf[i] = a.blk_leaf[a.order0[b]];
     u32 s = a.o_set[b];
     u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
     a.f_depth[i] = (int)a.o_depth[b];
@@ -1281,6 +1285,40 @@ HD void rot_body(long long s, const RotArgs &a) {
     if (cur != -1) a.set_cyclic[s] = 1;
 }
 MAP_KERNEL(rot, RotArgs, 8)
+
+// ---- the letters of a block as the reference prints them (nodeslinkedlists.c:128 blockLabel) -----------------
+// blockLabel spells a block from the labels of the tree edges on its path, i.e. from the text that CREATED each
+// edge (labelfrom/startpos, gencycsuffixtrees.c:160-218).  The edge that holds letter number j of block X was
+// created by the first rotation, in insertion order, that begins with X[0..j]: a rotation of sequence 0 (every
+// block occurs there), at the smallest such position p: letter = texts[0][p+j].  A, C, G, T are the same at every
+// occurrence; a letter outside ACGT is spelled as that first occurrence has it.  p = minpos of the highest node
+// of the sequence-0 tree at or above the block's leaf that is at least j+1 deep.
+struct BlockLettersArgs {
+    BatchView v; const unsigned char *raw; const u32 *z0; u32 N0; const u32 *parent; const u32 *minpos; const u32 *lcp0;
+    const int *f_depth; const int *f_pos; const u32 *f_leaf; const u32 *f_set; const u32 *set_blk0; const u32 *set_pos0;
+    const unsigned long long *offsets; u32 B; char *out;
+};
+HD void blockletters_body(long long t, const BlockLettersArgs &a) {
+    u32 lo = 0, hi = a.B; // block of letter t: last b with offsets[b] <= t
+    while (lo < hi) { u32 mid = (lo + hi) >> 1; if (a.offsets[mid] <= (unsigned long long)t) lo = mid + 1; else hi = mid; }
+    const u32 b = lo - 1, j = (u32)((unsigned long long)t - a.offsets[b]);
+    const u32 s = a.f_set[b];
+    const u32 k0 = LDG(a.v.set_seq0 + s), m = LDG(a.v.set_seq0 + s + 1) - k0;
+    const u32 off = LDG(a.v.seq_off + k0), n0 = LDG(a.v.seq_off + k0 + 1) - off;
+    const u32 p0 = (u32)a.f_pos[pos_offset(a.set_blk0, a.set_pos0, s, m, b)];
+    unsigned char c = a.raw[off + (p0 + j) % n0];
+    if (code_of_letter(c) > 3) {
+        u32 x = a.N0 + a.f_leaf[b];
+        for (;;) {
+            const u32 p = a.parent[x];
+            if (p == x || p == CSA_NONE || a.lcp0[p] < j + 1) break;
+            x = p;
+        }
+        c = a.raw[off + (a.minpos[x] + j) % n0];
+    }
+    a.out[t] = (char)c;
+}
+MAP_KERNEL(blockletters, BlockLettersArgs, 2)
 
 // ---- optional: the counts the reference prints (csamsa.c:332 "nodes found", :338 "nodes left") ------------
 // collectNodes keeps the DEEPEST nodes that hold every sequence.  With W(l) = [l, R[l]] the shortest

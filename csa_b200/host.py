@@ -75,9 +75,22 @@ def drop_rotation_duplicates(descs: Sequence[str], seqs: Sequence[bytes]):
     return kd, ks, dropped
 
 
+def chain_is_ring(res: SetResult, b: int) -> bool:
+    """the chain that starts at block b closes into a ring: blockLabel (nodeslinkedlists.c:150) never returns"""
+    cur, steps = b, 0
+    while cur != -1:
+        steps += 1
+        if steps > len(res.depth):
+            return True
+        cur = int(res.next[cur])
+    return False
+
+
 def block_label(res: SetResult, b: int, seqs: Sequence[bytes]) -> str:
-    """nodeslinkedlists.c:144 blockLabel: the blocks of a chain spelled out, gaps as '-' (up to 7)
-    or '-(n)-'; a negative gap eats letters back.  Letters come from sequence 0."""
+    """nodeslinkedlists.c:128 blockLabel: the blocks of a chain spelled out, gaps as '-' (up to 7)
+    or '-(n)-'; a negative gap eats letters back.  The letters of a block are those of res.letters
+    (csa_gpu_batch_block_letters: spelled from the text that created each tree edge); without them the
+    letters of the block's place in sequence 0, which differ only where a block holds a letter outside ACGT."""
     s0, n0 = seqs[0], len(seqs[0])
     label = bytearray()
     ln = 0
@@ -85,7 +98,10 @@ def block_label(res: SetResult, b: int, seqs: Sequence[bytes]) -> str:
     nb = len(res.depth)
     while cur != -1 and guard <= nb:
         d, p0 = int(res.depth[cur]), int(res.positions[cur][0])
-        piece = bytes(s0[(p0 + i) % n0] for i in range(d))
+        if getattr(res, "letters", None) is not None:
+            piece = bytes(res.letters[cur])
+        else:
+            piece = bytes(s0[(p0 + i) % n0] for i in range(d))
         label[ln:ln + d] = piece
         ln += d
         g = int(res.interval[cur])

@@ -9,9 +9,13 @@
  *   csamsa.c:324  analyzeTree            the four progress lines with their counts
  *   csamsa.c:421  saveRotatedSequences   <base>-Rotated.fasta, byte for byte
  *   csamsa.c:361  createImageAndShowResults: <base>-Blocks.csv and the chain list on stdout
- * Not produced: the .bmp picture and its -positions / -imagemap side files (graphics.c, bitmap.c;
- * drawing, outside the rotation path) and the other modes (A, I, C, S, M).
- * There is no CPU fallback: without a CUDA device the program stops with an error.
+ * Not produced HERE: the .bmp picture and its -positions / -imagemap side files (graphics.c, bitmap.c:
+ * drawing code) and the other modes (A, I, C, S, M).  csa_shim.c is the other way to the same library:
+ * linked with the reference's own objects it keeps the reference's main, loader and drawing code and
+ * writes all five files (INTEGRATION.md has the build recipe).
+ * There is no CPU fallback: without a CUDA device the program stops with an error (exit 70).
+ * Exit codes: 0 as the reference (its error messages included, csamsa.c:57 exits 0); 3, 4, 5, 6 where the
+ * reference itself would crash or never return (see CSA_SET_* in csa_gpu.h); 70 accelerator failure.
  */
 #include "../../include/csa_gpu.h"
 #include <limits.h>
@@ -26,6 +30,18 @@ static const char *inputfilename;
 static void die(const char *msg) { /* csamsa.c:57 exitMessage */
     printf("\n> ERROR: %s\n", msg);
     exit(0);
+}
+
+static void stop(int code, const char *why) { /* where the reference itself would die or hang */
+    printf("\n> CSA_GPU: %s\n", why);
+    fflush(stdout);
+    exit(code);
+}
+
+static void fail_gpu(const char *what) {
+    fflush(stdout);
+    fprintf(stderr, "> ERROR: %s: %s (this build has no CPU path)\n", what, csa_gpu_last_error());
+    exit(70);
 }
 
 static char *output_name(const char *extra) { /* csamsa.c:41 newOutputFilename */
@@ -53,21 +69,21 @@ static int is_rotation(const char *a, const char *b, int n) {
     return hit;
 }
 
-/* nodeslinkedlists.c:144 blockLabel: the chain spelled with the letters of sequence 0, gaps as
- * dashes (up to 7) or -(n)-; a negative gap steps back over letters already written */
-static char *chain_label(int b, int nblocks, int m, const int *depth, const int *interval, const int *next,
-                         const int *positions, const char *text0, int n0) {
+/* nodeslinkedlists.c:128 blockLabel: the blocks of the chain, each spelled as the reference's tree spells it
+ * (csa_gpu_batch_block_letters), gaps as dashes (up to 7) or -(n)-; a negative gap steps back over letters
+ * already written */
+static char *chain_label(int b, const int *depth, const int *interval, const int *next, const char *letters,
+                         const long long *off) {
     size_t cap = 256, len = 0;
     char *label = (char *)calloc(cap, 1);
-    int guard = 0;
-    for (int cur = b; cur != -1 && guard <= nblocks; cur = next[cur], guard++) {
-        int d = depth[cur], p0 = positions[(size_t)cur * m];
+    for (int cur = b; cur != -1; cur = next[cur]) {
+        int d = depth[cur];
         while (len + (size_t)d + 32 > cap) {
             label = (char *)realloc(label, cap * 2);
             memset(label + cap, 0, cap);
             cap *= 2;
         }
-        for (int i = 0; i < d; i++) label[len + i] = text0[(p0 + i) % n0];
+        memcpy(label + len, letters + off[cur], (size_t)d);
         len += (size_t)d;
         int g = interval[cur];
         if (g < 0) len = ((long long)len + g < 0) ? 0 : len + g;
@@ -76,6 +92,13 @@ static char *chain_label(int b, int nblocks, int m, const int *depth, const int 
     }
     label[len] = 0;
     return label;
+}
+
+static int chain_is_ring(int b, int nblocks, const int *next) {
+    int steps = 0;
+    for (int cur = b; cur != -1; cur = next[cur])
+        if (++steps > nblocks) return 1;
+    return 0;
 }
 
 int main(int argc, char **argv) {
@@ -195,38 +218,36 @@ int main(int argc, char **argv) {
     if (ngpus > 1) {
         int set_start[2] = {0, m};
         if (csa_gpu_multi_create(ngpus, NULL, &multi) != CSA_GPU_OK) {
-            fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
-            die("Not that many CUDA devices (this build has no CPU path)");
+            fail_gpu("not that many CUDA devices");
         }
         ctx = csa_gpu_multi_ctx(multi, 0);
         if (csa_gpu_multi_batch_rotations(multi, 1, set_start, (const char *const *)texts, sizes, INT_MAX, CSA_GPU_FLAG_STATS,
-                                          rotations, &info) != CSA_GPU_OK) {
-            fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
-            die("GPU run failed");
-        }
+                                          rotations, &info) != CSA_GPU_OK)
+            fail_gpu("GPU run failed");
     } else {
-        if (csa_gpu_create(device, &ctx) != CSA_GPU_OK) {
-            fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
-            die("No CUDA device (this build has no CPU path)");
-        }
-        if (csa_gpu_find_rotations(ctx, m, (const char *const *)texts, sizes, INT_MAX, CSA_GPU_FLAG_STATS, rotations, &info) != CSA_GPU_OK) {
-            fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
-            die("GPU run failed");
-        }
+        if (csa_gpu_create(device, &ctx) != CSA_GPU_OK) fail_gpu("no CUDA device");
+        if (csa_gpu_find_rotations(ctx, m, (const char *const *)texts, sizes, INT_MAX, CSA_GPU_FLAG_STATS, rotations, &info) != CSA_GPU_OK)
+            fail_gpu("GPU run failed");
     }
-    if (info.status == CSA_SET_DEGENERATE)
-        die("A whole rotation of one sequence occurs in all the others (the reference's tree walk is undefined here)");
     printf("> Collecting maximum common subsequences... ");
+    fflush(stdout);
     if (info.count_collected == 0) die("No common subsequences found");
     printf("%d nodes found\n", info.count_collected);
     printf("> Removing suffixes... ");
+    fflush(stdout);
+    if (info.status == CSA_SET_UNDEFINED)
+        stop(6, "removeSuffixNodes (csamsa.c:80) frees the list item it stands on here; the reference's answer is not defined");
     printf("%d nodes left\n", info.count_suffixfree);
     printf("> Removing repeats... ");
+    fflush(stdout);
     if (info.count_unique == 0) die("No unique subsequences found");
     printf("%d nodes left\n", info.count_unique);
-    if (info.status == CSA_SET_NONTERMINATING)
-        die("The common blocks form a cycle without gaps (the reference does not terminate on this input)");
     printf("> Connecting block chains... ");
+    fflush(stdout);
+    if (info.status == CSA_SET_DEGENERATE)
+        stop(3, "collectNodeChains walks off a leaf here (csamsa.c:153): a whole rotation of the shortest sequence occurs in all others");
+    if (info.status == CSA_SET_NONTERMINATING)
+        stop(4, "collectNodeChains (csamsa.c:197) does not terminate on this input: the common blocks form a cycle");
     printf("%d chains found\n", info.count_chains);
 
     /* ---- saveRotatedSequences ---- */
@@ -248,10 +269,12 @@ int main(int argc, char **argv) {
     int *depth = (int *)calloc((size_t)nb, sizeof(int)), *size = (int *)calloc((size_t)nb, sizeof(int));
     int *total = (int *)calloc((size_t)nb, sizeof(int)), *interval = (int *)calloc((size_t)nb, sizeof(int));
     int *next = (int *)calloc((size_t)nb, sizeof(int)), *positions = (int *)calloc((size_t)nb * (size_t)m, sizeof(int));
-    if (csa_gpu_batch_blocks(ctx, depth, size, total, interval, next, positions) != CSA_GPU_OK) {
-        fprintf(stderr, "csa_gpu: %s\n", csa_gpu_last_error());
-        die("GPU run failed");
-    }
+    long long *off = (long long *)calloc((size_t)nb + 1, sizeof(long long));
+    if (csa_gpu_batch_blocks(ctx, depth, size, total, interval, next, positions) != CSA_GPU_OK) fail_gpu("GPU run failed");
+    long long nletters = csa_gpu_batch_block_letters(ctx, NULL, off);
+    if (nletters < 0) fail_gpu("GPU run failed");
+    char *letters = (char *)calloc((size_t)nletters + 1, 1);
+    if (nletters && csa_gpu_batch_block_letters(ctx, letters, NULL) < 0) fail_gpu("GPU run failed");
     fn = output_name("-Blocks.csv");
     o = fopen(fn, "w");
     if (!o) die("Can't write original blocks file");
@@ -264,7 +287,11 @@ int main(int argc, char **argv) {
     printf("> Length, sequence and rotations for the first %d longest block chains:\n", ntoprint);
     for (int b = 0; b < nb; b++) {
         if (total[b] == -1) continue;
-        char *s = chain_label(b, nb, m, depth, interval, next, positions, texts[0], sizes[0]);
+        if (chain_is_ring(b, nb, next)) {
+            fclose(o);
+            stop(5, "this block chain closes into a ring: blockLabel (nodeslinkedlists.c:150) never returns in the reference");
+        }
+        char *s = chain_label(b, depth, interval, next, letters, off);
         if (nchains < ntoprint) {
             printf(":: (%d) ", size[b]);
             if ((int)strlen(s) < charstoprint) printf("%s", s);

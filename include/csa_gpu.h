@@ -40,10 +40,16 @@ extern "C" {
 #define CSA_SET_OK 0
 #define CSA_SET_NO_COMMON 1      /* csamsa.c:330 "No common subsequences found"              */
 #define CSA_SET_NO_UNIQUE 2      /* csamsa.c:346 "No unique subsequences found"              */
-#define CSA_SET_DEGENERATE 3     /* a whole rotation of one sequence occurs in all the others:
-                                    the reference walks off its tree there (undefined)       */
+#define CSA_SET_DEGENERATE 3     /* collectNodeChains' walk (csamsa.c:147-183) reaches a LEAF that holds every
+                                    sequence (a whole rotation of the shortest one inside all others): the
+                                    reference dereferences NULL (csamsa.c:153) or loops there.  A set with such
+                                    a leaf that the walk does not reach is answered like any other         */
 #define CSA_SET_NONTERMINATING 4 /* the reference loops forever in collectNodeChains
                                     (csamsa.c:197) on a block cycle whose gaps sum to <= 0   */
+
+#define CSA_SET_UNDEFINED 5      /* removeSuffixNodes (csamsa.c:80) frees the list item it stands on and reads
+                                    it afterwards (a sequence w^c whose rotations, followed round, lead back
+                                    to the one the walk started from): the reference's answer is not defined  */
 
 /* flags for csa_gpu_batch_run */
 #define CSA_GPU_FLAG_STATS 1u /* also count "nodes found"/"nodes left" (csamsa.c:332,338)    */
@@ -103,6 +109,13 @@ long long csa_gpu_batch_num_positions(csa_gpu_ctx *ctx);
  * Any pointer may be NULL. */
 int csa_gpu_batch_blocks(csa_gpu_ctx *ctx, int *depth, int *size, int *totalsize, int *interval,
                          int *next, int *positions);
+/* the letters of every block as blockLabel (nodeslinkedlists.c:128-165) spells them: it reads each tree edge's
+ * label from the text that CREATED the edge (labelfrom/startpos), so a letter outside ACGT -- all of which
+ * compare equal -- is printed as the FIRST occurrence in sequence 0 of the block's prefix up to that letter
+ * has it, not as the block's own place has it.  Block b (batch-wide index, final list order) owns
+ * letters[offsets[b] .. offsets[b+1]); offsets has num_blocks+1 entries.  Returns the total number of letters
+ * (call with letters == NULL to size the buffer), or a negative CSA_GPU_E* code. */
+long long csa_gpu_batch_block_letters(csa_gpu_ctx *ctx, char *letters, long long *offsets);
 /* upload + run + download in one call with host buffers (what bench.py times as e2e) */
 int csa_gpu_batch_rotations(csa_gpu_ctx *ctx, int nsets, const int *set_start,
                             const char *const *texts, const int *textsizes, int max_interval,

@@ -28,9 +28,13 @@ enum {
     CSA_ORACLE_OK = 0,
     CSA_ORACLE_NO_COMMON = 1,   /* csamsa.c:330 "No common subsequences found"      */
     CSA_ORACLE_NO_UNIQUE = 2,   /* csamsa.c:346 "No unique subsequences found"       */
-    CSA_ORACLE_DEGENERATE = 3,  /* a whole rotation of one sequence occurs in every other one;
-                                   the reference dereferences NULL / loops there      */
-    CSA_ORACLE_HANG = 4         /* reference would not terminate (zero-gap block cycle) */
+    CSA_ORACLE_DEGENERATE = 3,  /* collectNodeChains' walk (csamsa.c:147-183) reaches a LEAF that holds
+                                   every sequence (a whole rotation of the shortest one inside all
+                                   others): the reference dereferences NULL or loops there          */
+    CSA_ORACLE_HANG = 4,        /* reference would not terminate (zero-gap block cycle) */
+    CSA_ORACLE_UNDEFINED = 5    /* removeSuffixNodes (csamsa.c:80) frees the list item it stands on and
+                                   reads it afterwards (a sequence w^c whose rotations, followed round,
+                                   come back to the one the walk started from)                        */
 };
 
 typedef struct csa_oracle_result {
@@ -49,6 +53,7 @@ typedef struct csa_oracle_result {
     int *next;             /* index (in this list) of nextblock, -1 if none                */
     int *positions;        /* nblocks x m, positions[b*m+k]                                */
     int *rotations;        /* m; NULL unless status==OK                                    */
+    char **letters;        /* per block: its depth letters as nodeslinkedlists.c:154-165 spells them */
 } csa_oracle_result;
 
 /* texts: upper-case IUPAC letters as produced by the reference loader (csamsa.c:517);
@@ -59,8 +64,9 @@ int csa_oracle_run(int m, const char *const *texts, const int *textsizes, int ma
 void csa_oracle_free(csa_oracle_result *r);
 
 /* chain label exactly as nodeslinkedlists.c:144 blockLabel prints it (malloc'd). */
-char *csa_oracle_block_label(const csa_oracle_result *r, int b, const char *const *texts,
-                             const int *textsizes);
+char *csa_oracle_block_label(const csa_oracle_result *r, int b);
+/* 1 when the chain starting at block b closes into a ring (blockLabel never returns: the reference dies) */
+int csa_oracle_chain_is_ring(const csa_oracle_result *r, int b);
 
 /* flat helpers for ctypes users (tests/, bench.py): the generalized cyclic suffix array
  * and LCP of one set, global index = offset[k]+p.  Returns 0 on success. */

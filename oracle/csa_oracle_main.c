@@ -148,23 +148,31 @@ int main(int argc, char **argv) {
     printf("\n");
     csa_oracle_result r;
     csa_oracle_run(m, (const char *const *)texts, sizes, INT_MAX, &r);
-    if (r.status == CSA_ORACLE_DEGENERATE) {
-        printf("> ORACLE: degenerate input (a whole rotation of one sequence occurs in all others)\n");
-        return 3;
-    }
     printf("> Collecting maximum common subsequences... ");
     if (r.count_collected == 0) exit_message("No common subsequences found");
     printf("%d nodes found\n", r.count_collected);
     printf("> Removing suffixes... ");
+    fflush(stdout);
+    if (r.status == CSA_ORACLE_UNDEFINED) {
+        printf("\n> ORACLE: removeSuffixNodes (csamsa.c:80) frees the list item it stands on; what the reference does next is not defined\n");
+        return 6;
+    }
     printf("%d nodes left\n", r.count_suffixfree);
     printf("> Removing repeats... ");
     if (r.count_unique == 0) exit_message("No unique subsequences found");
     printf("%d nodes left\n", r.count_unique);
+    printf("> Connecting block chains... ");
+    fflush(stdout);
+    /* exit codes 3, 4, 5: the oracle's statement that the reference does not get past this point
+     * (oracle/validate_against_ref.py checks that it indeed dies or hangs, and only then) */
+    if (r.status == CSA_ORACLE_DEGENERATE) {
+        printf("\n> ORACLE: the reference walks off a leaf here (csamsa.c:153; a whole rotation of the shortest sequence occurs in all others)\n");
+        return 3;
+    }
     if (r.status == CSA_ORACLE_HANG) {
-        printf("> ORACLE: the reference does not terminate on this input (zero-gap block cycle)\n");
+        printf("\n> ORACLE: the reference does not terminate on this input (block cycle, csamsa.c:197)\n");
         return 4;
     }
-    printf("> Connecting block chains... ");
     printf("%d chains found\n", r.count_chains);
     /* ---- csamsa.c:421 saveRotatedSequences ---- */
     char *fn = new_output_filename("-Rotated.fasta");
@@ -191,7 +199,13 @@ int main(int argc, char **argv) {
     printf("> Length, sequence and rotations for the first %d longest block chains:\n", ntoprint);
     for (int b = 0; b < r.nblocks; b++) {
         if (r.totalsize[b] == -1) continue;
-        char *s = csa_oracle_block_label(&r, b, (const char *const *)texts, sizes);
+        if (csa_oracle_chain_is_ring(&r, b)) {
+            fflush(stdout);
+            fclose(o);
+            printf("> ORACLE: this chain closes into a ring; blockLabel (nodeslinkedlists.c:150) never returns\n");
+            return 5;
+        }
+        char *s = csa_oracle_block_label(&r, b);
         if (nchains < ntoprint) {
             printf(":: (%d) ", r.size[b]);
             if ((int)strlen(s) < charstoprint) printf("%s", s);

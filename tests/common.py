@@ -26,7 +26,7 @@ class OracleResult(C.Structure):
                 ("count_unique", C.c_int), ("count_chains", C.c_int), ("nblocks", C.c_int),
                 ("depth", C.POINTER(C.c_int)), ("size", C.POINTER(C.c_int)), ("totalsize", C.POINTER(C.c_int)),
                 ("interval", C.POINTER(C.c_int)), ("next", C.POINTER(C.c_int)), ("positions", C.POINTER(C.c_int)),
-                ("rotations", C.POINTER(C.c_int))]
+                ("rotations", C.POINTER(C.c_int)), ("letters", C.POINTER(C.c_char_p))]
 
 
 def build_oracle():
@@ -70,7 +70,8 @@ def oracle_run(seqs, max_interval=INT_MAX):
     if r.status == 0:
         out.update(depth=arr(r.depth, nb), size=arr(r.size, nb), totalsize=arr(r.totalsize, nb),
                    interval=arr(r.interval, nb), next=arr(r.next, nb),
-                   positions=arr(r.positions, nb * m).reshape(nb, m), rotations=arr(r.rotations, m))
+                   positions=arr(r.positions, nb * m).reshape(nb, m), rotations=arr(r.rotations, m),
+                   letters=[r.letters[i] for i in range(nb)])
     lib.csa_oracle_free(C.byref(r))
     return out
 
@@ -118,8 +119,12 @@ def drop_rotation_duplicates(seqs):
     return out
 
 
-def gen_case(rng, max_n=3000):
-    kind = rng.choice(["variants", "variants", "variants", "random", "binary", "iupac", "many", "blocks", "ragged"])
+KINDS = ["variants", "variants", "variants", "random", "binary", "iupac", "many", "blocks", "ragged",
+         "periodic", "contained", "iupacruns"]
+
+
+def gen_case(rng, max_n=3000, kinds=KINDS):
+    kind = rng.choice(kinds)
     alphabet = "ACGT"
     if kind == "binary":
         alphabet = "AC"
@@ -143,6 +148,35 @@ def gen_case(rng, max_n=3000):
             for b in order:
                 s += blocks[b] + [rng.choice(alphabet) for _ in range(rng.randint(0, 30))]
             seqs.append(s)
+    elif kind == "periodic":
+        # powers w^c: the identical rotations of one sequence share a leaf (gencycsuffixtrees.c:507-517)
+        if rng.random() < 0.5:
+            alphabet = rng.choice(["AC", "ACG", "ACGT"])
+        w = [rng.choice(alphabet) for _ in range(rng.choice([1, 2, 3, rng.randint(2, 12), rng.randint(4, 80)]))]
+        whole = w * rng.randint(2, 5)
+        for _ in range(m):
+            r = rng.random()
+            if r < 0.35:
+                seqs.append(list(whole))
+            elif r < 0.5:
+                seqs.append(list(w * rng.randint(1, 4)))
+            elif r < 0.8:
+                seqs.append(mutate(rng, whole, rng.choice([0.0, 0.02, 0.1]), rng.choice([0.0, 0.02]), alphabet))
+            else:
+                seqs.append(mutate(rng, w * rng.randint(1, 3), 0.05, 0.02, alphabet))
+    elif kind == "contained":
+        # a whole rotation of one sequence inside the others (insertions only): leaves that hold every sequence
+        base = [rng.choice(alphabet) for _ in range(min(n, 300))]
+        for k in range(m):
+            s = list(base)
+            if k and rng.random() < 0.85:
+                for _ in range(rng.randint(1, 3)):
+                    p = rng.randrange(len(s) + 1)
+                    s[p:p] = [rng.choice(alphabet) for _ in range(rng.randint(1, 4))]
+            elif k and rng.random() < 0.5:
+                s = mutate(rng, s, 0.01, 0.0, alphabet)
+            seqs.append(s)
+        rng.shuffle(seqs)
     elif kind == "ragged":
         base = [rng.choice(alphabet) for _ in range(n)]
         for _ in range(m):
@@ -159,6 +193,14 @@ def gen_case(rng, max_n=3000):
                 for _ in range(rng.randint(0, 3)):
                     if s:
                         s[rng.randrange(len(s))] = rng.choice("NRYKM")
+        if kind == "iupacruns":
+            # the same places hold different ambiguity letters: blocks with a fifth letter inside
+            for _ in range(rng.randint(1, 6)):
+                p, ln = rng.randrange(n), rng.randint(1, 5)
+                for s in seqs:
+                    if rng.random() < 0.8:
+                        for q in range(p, min(p + ln, len(s))):
+                            s[q] = rng.choice("NRYKMSWBDHV")
     out = []
     for s in seqs:
         if len(s) < 2:
@@ -168,14 +210,14 @@ def gen_case(rng, max_n=3000):
         out.append("".join(s).encode())
     out = drop_rotation_duplicates(out)
     if len(out) < 2:
-        return gen_case(rng, max_n)
+        return gen_case(rng, max_n, kinds)
     return kind, out
 
 
 def compare_with_oracle(res, ora, seqs, where=""):
     """res: csa_b200.api.SetResult, ora: oracle_run() dict.  Bit-exact or AssertionError."""
     assert res.status == ora["status"], f"{where}: status {res.status} != oracle {ora['status']}"
-    if ora["status"] in (3, 4):
+    if ora["status"] in (3, 4, 5):
         return
     assert res.count_unique == ora["count_unique"], f"{where}: count_unique {res.count_unique} != {ora['count_unique']}"
     if res.count_collected >= 0:
@@ -189,3 +231,5 @@ def compare_with_oracle(res, ora, seqs, where=""):
         assert np.array_equal(a, b), f"{where}: blockslist.{name} differs\n got {a}\n exp {b}"
     assert np.array_equal(res.positions, ora["positions"]), f"{where}: block positions differ"
     assert np.array_equal(res.rotations, ora["rotations"]), f"{where}: rotations {res.rotations} != {ora['rotations']}"
+    if res.letters is not None:
+        assert [bytes(x) for x in res.letters] == [bytes(x) for x in ora["letters"]], f"{where}: block letters differ"

@@ -20,6 +20,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_edge():
+    import gzip, json
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "golden_edge.json.gz"), "rt") as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def emu_finder():
     """CPU single-stepper of the kernel bodies (tests/emu) -- logic tests only, never the product."""
     from common import build_emu, EMU_LIB

@@ -86,16 +86,21 @@ def test_emu_both_round_paths(emu_finder):
         compare_with_oracle(b, o, s, f"device-wide path set {i}")
 
 
-def test_emu_degenerate_and_nonterminating_together(emu_finder):
-    """a set that is degenerate (a whole rotation inside all others) AND whose block chain does not terminate keeps
-    the classification the tree walk reaches first (csamsa.c:64 runs before collectNodeChains): DEGENERATE.
-    Found by the randomized GPU sweep (the two flags used to be combined with max instead of or)."""
-    rng = random.Random(1000 + 9)
-    cases = [gen_case(rng, max_n=rng.choice([500, 1500, 6000]))[1] for _ in range(150)]
-    s = cases[94]
-    o = oracle_run(s)
-    assert o["status"] == 3
-    compare_with_oracle(emu_finder.find_rotations(s), o, s, "degenerate + nonterminating")
+def test_emu_sets_whose_tree_is_not_their_suffix_array(emu_finder):
+    """csa_b200/csrc/rare.cuh: sequences that are powers w^c (identical rotations share ONE leaf,
+    gencycsuffixtrees.c:507-517) and sets in which a whole rotation of the shortest sequence occurs in all others
+    (a LEAF on the block list: removeSuffixNodes csamsa.c:80 and the walk of csamsa.c:147-183 follow the leaf's
+    link to the next rotation).  Every status the reference can end in must turn up and be agreed on: answered
+    (0), no unique block (2), walks off a leaf (3), endless block cycle (4), frees the item it stands on (5);
+    counts, block list, letters and rotations bit-exact wherever there is an answer."""
+    rng = random.Random(20261018)
+    seen = {}
+    for i in range(400):
+        kind, s = gen_case(rng, max_n=400, kinds=["periodic", "contained", "ragged", "periodic", "contained"])
+        o = oracle_run(s)
+        seen[o["status"]] = seen.get(o["status"], 0) + 1
+        compare_with_oracle(emu_finder.find_rotations(s, flags=1, with_letters=True), o, s, f"case {i} ({kind})")
+    assert all(seen.get(st, 0) >= 3 for st in (0, 2, 3, 4, 5)), seen
 
 
 def test_emu_shard_api_one_rank_and_errors(emu_finder):

@@ -16,16 +16,65 @@ def test_gpu_golden_vectors(gpu_finder, golden):
     """BASELINE.json configs[0] (Primates.txt) and configs[1] (Mammals.txt) + 80 synthetic sets:
     outputs of the unmodified reference binary"""
     sets = [[s.encode() for s in c["seqs"]] for c in golden]
-    res = gpu_finder.find_rotations_batch(sets)
+    res = gpu_finder.find_rotations_batch(sets, flags=1, with_letters=True)
     for c, seqs, r in zip(golden, sets, res):
         assert r.status == 0, c["name"]
-        assert [r.count_unique, r.count_chains] == c["counts"][2:], c["name"]
+        assert [r.count_collected, r.count_suffixfree, r.count_unique, r.count_chains] == c["counts"], c["name"]
         assert list(r.rotations) == c["rotations"], c["name"]
         assert host.blocks_csv(r, seqs) == c["blocks_csv"], c["name"]
     # and one set at a time (the reference's own call shape)
     for c, seqs in list(zip(golden, sets))[:6]:
         r = gpu_finder.find_rotations(seqs)
         assert list(r.rotations) == c["rotations"], c["name"]
+
+
+def test_gpu_where_the_reference_does_not_finish(gpu_finder, golden_edge):
+    """tests/golden/golden_edge.json.gz: the reference died or never returned; the CUDA path classifies as the oracle does
+    (a ring in a printed chain when the reference got as far as -Rotated.fasta, else status 3 / 4 / 5)"""
+    import hashlib
+    sets = [[s.encode() for s in c["seqs"]] for c in golden_edge]
+    res = gpu_finder.find_rotations_batch(sets, flags=1)
+    for c, seqs, r in zip(golden_edge, sets, res):
+        o = oracle_run(seqs)
+        compare_with_oracle(r, o, seqs, c["name"])
+        if c["rotated_sha256"] is not None:
+            assert r.status == 0, c["name"]
+            assert hashlib.sha256(host.rotated_fasta(c["descs"], seqs, r.rotations)).hexdigest() == c["rotated_sha256"], c["name"]
+            assert any(host.chain_is_ring(r, b) for b in range(len(r.depth)) if r.totalsize[b] != -1), c["name"]
+        else:
+            assert r.status in ((3, 4) if c["outcome"] == "hangs" else (3, 5)), (c["name"], r.status)
+
+
+def test_gpu_sets_whose_tree_is_not_their_suffix_array(gpu_finder):
+    """csa_b200/csrc/rare.cuh on the device (see tests/test_emu_pipeline.py for what these sets are): powers w^c,
+    one sequence wholly inside all others; mixed into one batch with ordinary sets so that marked and unmarked sets
+    run side by side in the same launches.  Bit-exact with the oracle, every status, counts, letters."""
+    rng = random.Random(20261018)
+    cases = [gen_case(rng, max_n=400, kinds=["periodic", "contained", "ragged", "periodic", "contained", "variants"]) for _ in range(600)]
+    sets = [c[1] for c in cases]
+    res = gpu_finder.find_rotations_batch(sets, flags=1, with_letters=True)
+    seen = {}
+    for i, (r, s) in enumerate(zip(res, sets)):
+        o = oracle_run(s)
+        seen[o["status"]] = seen.get(o["status"], 0) + 1
+        compare_with_oracle(r, o, s, f"set {i} {cases[i][0]}")
+    assert all(seen.get(st, 0) >= 3 for st in (0, 2, 3, 4, 5)), seen
+    # one marked set alone (the reference's call shape), each kind
+    for i in (0, 1, 2, 3, 4, 5, 6, 7):
+        compare_with_oracle(gpu_finder.find_rotations(sets[i], flags=1, with_letters=True), oracle_run(sets[i]), sets[i], f"alone {i}")
+
+
+def test_gpu_first_sequence_the_longest(gpu_finder):
+    """a two-sequence set whose FIRST sequence is by far the longer: the sequence-0 tree has 2 N0 > N nodes and sorts in
+    the suffix array's buffers (round-1 advisor finding: they were sized for N)"""
+    rng = random.Random(77)
+    for n0, n1 in ((3000, 2000), (5000, 600), (40000, 9000)):
+        a = bytes(rng.choice(b"ACGT") for _ in range(n0))
+        b = bytearray(a[n0 // 6:n0 // 6 + n1])
+        for i in range(0, len(b), 97):
+            b[i] = rng.choice(b"ACGT")
+        s = [a, bytes(b)]
+        compare_with_oracle(gpu_finder.find_rotations(s, flags=1, with_letters=True), oracle_run(s), s, f"{n0}/{n1}")
 
 
 @pytest.mark.parametrize("seed", [21, 22, 23, 24])
@@ -36,6 +85,9 @@ def test_gpu_seeded_sets_vs_oracle(gpu_finder, seed):
     res = gpu_finder.find_rotations_batch(sets)
     for i, (r, s) in enumerate(zip(res, sets)):
         compare_with_oracle(r, oracle_run(s), s, f"seed {seed} set {i} {cases[i][0]}")
+    res = gpu_finder.find_rotations_batch(sets[:40], flags=1, with_letters=True)
+    for i, (r, s) in enumerate(zip(res, sets)):
+        compare_with_oracle(r, oracle_run(s), s, f"seed {seed} set {i} {cases[i][0]} (counts and letters)")
 
 
 def test_gpu_suffix_array_and_lcp(gpu_finder):
