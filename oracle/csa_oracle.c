@@ -625,6 +625,12 @@ static char *block_letters(const gtext *t, const char *const *texts, const int *
 
 int csa_oracle_run(int m, const char *const *texts, const int *textsizes, int max_interval,
                    csa_oracle_result *res) {
+    return csa_oracle_run_sa(m, texts, textsizes, max_interval, res, NULL, NULL);
+}
+
+/* the same, and the suffix array + LCP array it worked on (layout of csa_oracle_gsa) copied out */
+int csa_oracle_run_sa(int m, const char *const *texts, const int *textsizes, int max_interval,
+                      csa_oracle_result *res, int *sa_out, int *lcp_out) {
     gtext t;
     memset(res, 0, sizeof(*res));
     res->m = m;
@@ -634,7 +640,19 @@ int csa_oracle_run(int m, const char *const *texts, const int *textsizes, int ma
     int *lcp = (int *)malloc(sizeof(int) * N);
     build_gsa(&t, sa, isa);
     build_lcp(&t, sa, isa, lcp);
-    N = collapse_periodic(&t, sa, lcp);
+    if (sa_out) { /* dropped rotations behind all others, lcp 0 */
+        int nd = 0, *dups = (int *)malloc(sizeof(int) * (N ? N : 1));
+        for (int i = 0; i < N; i++) {
+            int k = t.seqof[sa[i]];
+            if (sa[i] - t.off[k] >= t.per[k]) dups[nd++] = sa[i];
+        }
+        int w = collapse_periodic(&t, sa, lcp);
+        memcpy(sa_out, sa, sizeof(int) * w); memcpy(lcp_out, lcp, sizeof(int) * w);
+        for (int j = 0; j < nd; j++) { sa_out[w + j] = dups[j]; lcp_out[w + j] = 0; }
+        free(dups);
+        N = w;
+    } else
+        N = collapse_periodic(&t, sa, lcp);
     for (int i = 0; i < N; i++) isa[sa[i]] = i;
     scan_out o;
     scan_intervals(&t, sa, lcp, N, &o);

@@ -61,6 +61,8 @@ typedef struct csa_oracle_result {
  * (gencycsuffixtrees.c:283).  max_interval: csamsa.c:27 (INT_MAX on the R path). */
 int csa_oracle_run(int m, const char *const *texts, const int *textsizes, int max_interval,
                    csa_oracle_result *out);
+int csa_oracle_run_sa(int m, const char *const *texts, const int *textsizes, int max_interval,
+                      csa_oracle_result *out, int *sa_out, int *lcp_out);
 void csa_oracle_free(csa_oracle_result *r);
 
 /* chain label exactly as nodeslinkedlists.c:144 blockLabel prints it (malloc'd). */
