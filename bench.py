@@ -2,7 +2,12 @@
 """bench.py -- the rotation-finding hot path of fjdf/CSA (`./CSA R`) on B200, one process per GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mammals|sets32|variants256|bacterial]
-                    [--sets S] [--impl reference]
+                    [--sets S] [--impl reference] [--only-headline]
+
+The headline (metric/value/e2e/roofline) is BASELINE.json's configs[1]; the same line carries, under "workloads", the other
+configs (configs[3] sets of 32, configs[2] 256 variants, configs[4] 16 x 5 Mb -- with N > 1 its suffix-array buckets
+sharded over the ranks, strong scaling) with value / ms_per_step / e2e / dominant kernel each, and under "single_set" what ONE
+call on one Mammals-shaped set costs.
 
 A step = one pass of the whole path (suffix array, LCP, common blocks, block order, chaining,
 rotations) over one batch of S independent synthetic sequence sets per GPU.
@@ -150,6 +155,7 @@ def main():
     ap.add_argument("--sets", type=int, default=0, help="sets per GPU per step")
     ap.add_argument("--cpu-sets", type=int, default=0, help="sets of the CPU sample (default 12 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-headline", action="store_true", help="skip the other BASELINE configs and the single-set latency")
     ap.add_argument("--e2e-contexts", type=int, default=2, help="contexts (host threads) feeding the GPU in the e2e loop")
     a = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -212,136 +218,190 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # One bacterial-scale set does not split into independent sets: with N > 1 its suffix-array stage is sharded by
-    # buckets (csa_gpu_shard_*, csa_b200/shard.py): every rank holds the same set, total work is fixed ("strong").
-    buckets = a.workload == "bacterial" and world > 1
-    batch = workload_batch(a.workload, nsets, seed=1000 + (0 if buckets else rank))  # every rank its own sets
-    rf = RotationFinder(device=local)
-    stream = torch.cuda.current_stream()
-    rf.set_stream(stream.cuda_stream)
-    if buckets:
-        from csa_b200.shard import run_bucket_sharded
-        rf_run = lambda: run_bucket_sharded(rf, rank, world, dist)
-    else:
-        rf_run = rf.run
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    e2e_contexts = a.e2e_contexts
 
-    # ---- value: inputs resident in HBM, csa_gpu_batch_run only ----
-    rf.upload(batch)
-    for _ in range(a.warmup):
+    def measure(workload, nsets, steps, warmup):
+        """one workload: resident value, e2e through the C ABI with host buffers, per-kernel profile"""
+        # One bacterial-scale set does not split into independent sets: with N > 1 its suffix-array stage is sharded by
+        # buckets (csa_gpu_shard_*, csa_b200/shard.py): every rank holds the same set, total work is fixed ("strong").
+        buckets = workload == "bacterial" and world > 1
+        batch = workload_batch(workload, nsets, seed=1000 + (0 if buckets else rank))  # every rank its own sets
+        rf = RotationFinder(device=local)
+        stream = torch.cuda.current_stream()
+        rf.set_stream(stream.cuda_stream)
+        if buckets:
+            from csa_b200.shard import run_bucket_sharded
+            rf_run = lambda: run_bucket_sharded(rf, rank, world, dist)
+        else:
+            rf_run = rf.run
+
+        # ---- value: inputs resident in HBM, csa_gpu_batch_run only ----
+        rf.upload(batch)
+        for _ in range(warmup):
+            rf_run()
+        clocks = ClockSampler(local)
+        barrier()
+        clocks.start()
+        t_wall0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        launches = 0
+        stage_ms = [0.0] * 6
+        for _ in range(steps):
+            rf_run()
+            ms, l = rf.timings()
+            launches += l
+            stage_ms = [x + y for x, y in zip(stage_ms, ms)]
+        e1.record(stream)
+        barrier()
+        t_wall1 = time.perf_counter()
+        dev_ms = allmax(e0.elapsed_time(e1))
+        clk = clocks.stop(t_wall0, t_wall1)
+        total_bases = (batch.nbases if buckets else allsum(batch.nbases)) * steps
+        value = total_bases / (dev_ms / 1e3)
+        rot, info = rf.download()
+        ok_sets = sum(1 for i in info if i.status == 0)
+
+        # ---- e2e: host buffers in, rotations out, through the C ABI ----
+        pinned = rf.pin(batch)  # "from pinned host memory": the copy engine reads the caller's buffer in place
+        # Independent sets: two contexts on the GPU, each fed by its own host thread through the same three C-ABI calls
+        # (upload -> run -> download, every step its own copies), so that one batch's host->device copy runs under the
+        # other batch's kernels -- what a service in front of the library does.  One large set sharded over ranks: one
+        # context, the steps one after the other.
+        nctx = 1 if buckets else max(1, e2e_contexts)
+        ctxs = [rf]
+        for _ in range(nctx - 1):
+            r2 = RotationFinder(device=local)
+            s2 = torch.cuda.Stream()
+            r2.set_stream(s2.cuda_stream)
+            r2._stream_keepalive = s2
+            ctxs.append(r2)
+        for c2 in ctxs:
+            for _ in range(max(1, warmup // 2)):
+                c2.upload(batch); (rf_run() if c2 is rf else c2.run()); c2.download()
+        last = [None] * nctx
+        def feed(i, nsteps):
+            torch.cuda.set_device(local)
+            for _ in range(nsteps):
+                ctxs[i].upload(batch)
+                rf_run() if (buckets and i == 0) else ctxs[i].run()
+                last[i] = ctxs[i].download()[0]
+        share = [steps // nctx + (1 if i < steps % nctx else 0) for i in range(nctx)]
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        if nctx == 1:
+            feed(0, steps)
+        else:
+            th = [threading.Thread(target=feed, args=(i, share[i])) for i in range(nctx)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize()  # every context's stream is idle: the event below closes the whole region
+        e3.record(stream)
+        barrier()
+        e2e_ms = allmax(e2.elapsed_time(e3))
+        rf.unpin(pinned)
+        for i in range(nctx):
+            if share[i]:
+                assert np.array_equal(rot, last[i])
+        for c2 in ctxs[1:]:
+            c2.close()
+        if buckets:  # the bucket-sharded run against the same set on this GPU alone
+            rf.upload(batch); rf.run()
+            rot3, _ = rf.download()
+            assert np.array_equal(rot, rot3), "bucket-sharded rotations differ from the single-GPU run"
+        h2d = batch.nbases + 4 * (2 * batch.nseqs + 4 * batch.nsets + 8) + 8 * (batch.nseqs + 1)
+        d2h = 4 * batch.nseqs + 3 * 4 * batch.nsets
+        e2e_value = total_bases / (e2e_ms / 1e3)
+
+        # ---- roofline: a separate profiled pass, CUDA events around every launch ----
+        rf.profile_enable(True)
         rf_run()
-    clocks = ClockSampler(local)
-    barrier()
-    clocks.start()
-    t_wall0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    launches = 0
-    stage_ms = [0.0] * 6
-    for _ in range(a.steps):
-        rf_run()
-        ms, l = rf.timings()
-        launches += l
-        stage_ms = [x + y for x, y in zip(stage_ms, ms)]
-    e1.record(stream)
-    barrier()
-    t_wall1 = time.perf_counter()
-    dev_ms = allmax(e0.elapsed_time(e1))
-    clk = clocks.stop(t_wall0, t_wall1)
-    total_bases = (batch.nbases if buckets else allsum(batch.nbases)) * a.steps
-    value = total_bases / (dev_ms / 1e3)
-    rot, info = rf.download()
-    ok_sets = sum(1 for i in info if i.status == 0)
+        rows = rf.profile()
+        rf.profile_enable(False)
+        roofline, kernels = None, []
+        if rows:
+            tot = sum(r[2] for r in rows)
+            rows.sort(key=lambda r: -r[2])
+            if os.environ.get("CSA_BENCH_ALL_KERNELS"):
+                for name, n, ms, by in rows:
+                    print("  %-18s n=%-4d %8.3f ms %5.1f%% %8.1f GB/s" % (name, n, ms, 100 * ms / tot, by / ms / 1e6 if ms > 0 else 0), file=sys.stderr)
+            for name, n, ms, by in rows[:12]:
+                kernels.append({"kernel": name, "launches": n, "ms": round(ms, 3), "share": round(ms / tot, 4),
+                                "algorithmic_GBps": round(by / ms / 1e6, 1) if ms > 0 else None,
+                                "frac": round(by / ms / 1e6 / peak, 3) if ms > 0 else None})
+            name, n, ms, by = rows[0]
+            ach = by / ms / 1e6
+            # DRAM bytes per launch from the committed ncu capture of this kernel (profiles/traffic.json holds
+            # dram__bytes_read+write per suffix), scaled to this run's launch size
+            traffic, traffic_src = None, None
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+                if tr:
+                    traffic, traffic_src = tr["dram_bytes_per_item"] * batch.nbases, tr["source"]
+            except (OSError, ValueError, KeyError):
+                pass
+            roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": n, "avg_launch_ms": ms / n,
+                        "algorithmic_bytes_per_launch": by / n, "share_of_step": ms / tot}
 
-    # ---- e2e: host buffers in, rotations out, through the C ABI ----
-    pinned = rf.pin(batch)  # "from pinned host memory": the copy engine reads the caller's buffer in place
-    # Independent sets: two contexts on the GPU, each fed by its own host thread through the same three C-ABI calls
-    # (upload -> run -> download, every step its own copies), so that one batch's host->device copy runs under the
-    # other batch's kernels -- what a service in front of the library does.  One large set sharded over ranks: one
-    # context, the steps one after the other.
-    nctx = 1 if buckets else max(1, a.e2e_contexts)
-    ctxs = [rf]
-    for _ in range(nctx - 1):
-        r2 = RotationFinder(device=local)
-        s2 = torch.cuda.Stream()
-        r2.set_stream(s2.cuda_stream)
-        r2._stream_keepalive = s2
-        ctxs.append(r2)
-    for c2 in ctxs:
-        for _ in range(max(1, a.warmup // 2)):
-            c2.upload(batch); (rf_run() if c2 is rf else c2.run()); c2.download()
-    last = [None] * nctx
-    def feed(i, nsteps):
-        torch.cuda.set_device(local)
-        for _ in range(nsteps):
-            ctxs[i].upload(batch)
-            rf_run() if (buckets and i == 0) else ctxs[i].run()
-            last[i] = ctxs[i].download()[0]
-    share = [a.steps // nctx + (1 if i < a.steps % nctx else 0) for i in range(nctx)]
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    if nctx == 1:
-        feed(0, a.steps)
-    else:
-        th = [threading.Thread(target=feed, args=(i, share[i])) for i in range(nctx)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        torch.cuda.synchronize()  # every context's stream is idle: the event below closes the whole region
-    e3.record(stream)
-    barrier()
-    e2e_ms = allmax(e2.elapsed_time(e3))
-    rf.unpin(pinned)
-    for i in range(nctx):
-        if share[i]:
-            assert np.array_equal(rot, last[i])
-    for c2 in ctxs[1:]:
-        c2.close()
-    if buckets:  # the bucket-sharded run against the same set on this GPU alone
-        rf.upload(batch); rf.run()
-        rot3, _ = rf.download()
-        assert np.array_equal(rot, rot3), "bucket-sharded rotations differ from the single-GPU run"
-    h2d = batch.nbases + 4 * (2 * batch.nseqs + 4 * batch.nsets + 8) + 8 * (batch.nseqs + 1)
-    d2h = 4 * batch.nseqs + 3 * 4 * batch.nsets
-    e2e_value = total_bases / (e2e_ms / 1e3)
 
-    # ---- roofline: a separate profiled pass, CUDA events around every launch ----
-    rf.profile_enable(True)
-    rf_run()
-    rows = rf.profile()
-    rf.profile_enable(False)
-    roofline, kernels = None, []
-    if rows:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except (OSError, ValueError):
-            pass
-        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        tot = sum(r[2] for r in rows)
-        rows.sort(key=lambda r: -r[2])
-        if os.environ.get("CSA_BENCH_ALL_KERNELS"):
-            for name, n, ms, by in rows:
-                print("  %-18s n=%-4d %8.3f ms %5.1f%% %8.1f GB/s" % (name, n, ms, 100 * ms / tot, by / ms / 1e6 if ms > 0 else 0), file=sys.stderr)
-        for name, n, ms, by in rows[:12]:
-            kernels.append({"kernel": name, "launches": n, "ms": round(ms, 3), "share": round(ms / tot, 4),
-                            "algorithmic_GBps": round(by / ms / 1e6, 1) if ms > 0 else None,
-                            "frac": round(by / ms / 1e6 / peak, 3) if ms > 0 else None})
-        name, n, ms, by = rows[0]
-        ach = by / ms / 1e6
-        # DRAM bytes per launch from the committed ncu capture of this kernel (profiles/traffic.json holds
-        # dram__bytes_read+write per suffix), scaled to this run's launch size
-        traffic, traffic_src = None, None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
-            if tr:
-                traffic, traffic_src = tr["dram_bytes_per_item"] * batch.nbases, tr["source"]
-        except (OSError, ValueError, KeyError):
-            pass
-        roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": n, "avg_launch_ms": ms / n,
-                    "algorithmic_bytes_per_launch": by / n, "share_of_step": ms / tot}
+        res = {"value": value, "ms_per_step": dev_ms / steps, "e2e_value": e2e_value, "e2e_ms_per_step": e2e_ms / steps, "h2d": h2d, "d2h": d2h,
+               "nctx": nctx, "launches": launches, "clk": clk, "roofline": roofline, "kernels": kernels, "ok_sets": ok_sets,
+               "stage_ms": [round(x / steps, 3) for x in stage_ms], "buckets": buckets, "batch": batch, "steps": steps}
+        rf.close()
+        return res
+
+    head = measure(a.workload, nsets, a.steps, a.warmup)
+    batch = head["batch"]
+
+    # ---- every other BASELINE config, fewer steps each (parity of their rotations is the -m gpu tests' business) ----
+    others = {}
+    if not a.only_headline:
+        k_other, w_other = max(3, a.steps // 4), max(3, min(a.warmup, 3))
+        for name in DEFAULT_SETS:
+            if name == a.workload:
+                continue
+            r = measure(name, DEFAULT_SETS[name], k_other, w_other)
+            top = r["roofline"] or {}
+            others[name] = {"workload": WORKLOADS[name][5], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+                            "scaling": "strong" if r["buckets"] else "weak", "sets_per_gpu_per_step": DEFAULT_SETS[name],
+                            "bases_per_gpu_per_step": r["batch"].nbases, "sets_ok": r["ok_sets"],
+                            "e2e": {"value": r["e2e_value"], "unit": UNIT, "ms_per_step": r["e2e_ms_per_step"],
+                                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                            "gpu_launches": r["launches"], "stage_ms_per_step": r["stage_ms"],
+                            "dominant_kernel": {k2: top.get(k2) for k2 in ("kernel", "frac", "achieved", "share_of_step", "avg_launch_ms")},
+                            "kernels": r["kernels"][:6],
+                            "parallelism": (f"one set, suffix-array buckets sharded over {world} GPUs (csa_gpu_shard_*), rotations checked against "
+                                            f"the one-GPU run") if r["buckets"] else f"sets sharded over {world} GPU(s), no collective"}
+            del r
+
+    # ---- what ONE call of the drop-in costs: csa_gpu_find_rotations on one Mammals-shaped set, host buffers in, rotations out ----
+    single = None
+    if rank == 0:
+        one = batch_sets(workload_batch("mammals", 1, seed=1000))[0]
+        rf1 = RotationFinder(device=local)
+        for _ in range(3):
+            rf1.find_rotations(one, with_blocks=False)
+        ts = []
+        for _ in range(15):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r1 = rf1.find_rotations(one, with_blocks=False)
+            ts.append(1e3 * (time.perf_counter() - t0))
+        _, l1 = rf1.timings()
+        rf1.close()
+        single = {"ms": statistics.median(ts), "min_ms": min(ts), "calls": len(ts), "bases": sum(len(x) for x in one), "gpu_launches": l1,
+                  "what": "wall clock of one csa_gpu_find_rotations (upload + all kernels + download) on ONE Mammals-shaped set of 12 mitogenomes, "
+                          "host buffers in, rotations out: what `./CSA R` spends in the library per call (the reference needs ~0.3 s for the same set)"}
 
     # ---- the reference on this box's host cores (rank 0, N=1 only) ----
     cpu = None
@@ -353,8 +413,9 @@ def main():
             cpu["seconds"] = round(r["seconds"], 2)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "strong" if buckets else "weak", "vs_baseline": None,
+        buckets = head["buckets"]
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong" if buckets else "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": what, "sets_per_gpu_per_step": nsets, "bases_per_gpu_per_step": batch.nbases,
                            "sequences_per_set": int(batch.set_start[1]),
@@ -362,16 +423,16 @@ def main():
                                            f"per rank, buckets broadcast over NCCL, the rest on every rank") if buckets
                                           else f"sets sharded over {world} GPU(s), no collective",
                            "l2": "per-step working set (~55 B/base) far above the 126 MB L2; no flush needed",
-                           "sets_ok": ok_sets, "stage_ms_per_step": [round(x / a.steps, 3) for x in stage_ms],
+                           "sets_ok": head["ok_sets"], "stage_ms_per_step": head["stage_ms"],
                            "stages": ["suffix array", "lcp", "common blocks", "block order", "chaining+rotations", "whole run"]},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / a.steps, "contexts": nctx},
-                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+                "e2e": {"value": head["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
+                        "ms_per_step": head["e2e_ms_per_step"], "contexts": head["nctx"]},
+                "gpu_launches": head["launches"], "clocks": head["clk"], "roofline": head["roofline"], "cpu_baseline": cpu,
+                "kernels": head["kernels"], "workloads": others, "single_set": single}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
-    rf.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

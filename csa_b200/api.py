@@ -16,7 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(HERE, "csrc", "libcsa_gpu.so")
 
-SET_OK, SET_NO_COMMON, SET_NO_UNIQUE, SET_DEGENERATE, SET_NONTERMINATING = 0, 1, 2, 3, 4
+SET_OK, SET_NO_COMMON, SET_NO_UNIQUE, SET_DEGENERATE, SET_NONTERMINATING, SET_UNDEFINED = 0, 1, 2, 3, 4, 5
 FLAG_STATS = 1
 INT_MAX = 2**31 - 1
 
@@ -286,8 +286,8 @@ class RotationFinder:
         return out
 
     def find_rotations(self, seqs: Sequence[bytes], max_interval: int = INT_MAX, flags: int = 0,
-                       with_letters: bool = False) -> SetResult:
-        return self.find_rotations_batch([seqs], max_interval, flags, with_letters=with_letters)[0]
+                       with_letters: bool = False, with_blocks: bool = True) -> SetResult:
+        return self.find_rotations_batch([seqs], max_interval, flags, with_blocks=with_blocks, with_letters=with_letters)[0]
 
 
 class MultiRotationFinder:

@@ -223,7 +223,7 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     c->batch_nmin = *std::min_element(c->h_set_nmin.begin(), c->h_set_nmin.end());
     c->max_set_bases = 0;
     for (int s = 0; s < nsets; s++) c->max_set_bases = std::max(c->max_set_bases, c->h_set_base0[s + 1] - c->h_set_base0[s]);
-    c->N = (u32)tot; c->N0 = z; c->nmax = nmax; c->n0max = n0max; c->mmax = mmax; c->TW = dbl / 32 + 2;
+    c->N = (u32)tot; c->N0 = z; c->nmax = nmax; c->n0max = n0max; c->mmax = mmax; c->TW = dbl / 32 + 8; // (guard words: the word sort stages 5 words at a time and may read past the last sequence)
     u32 N = c->N;
     // stage the letters in pinned memory -- unless the caller's buffer is one contiguous, page-locked
     // block already (cudaHostRegister / csa_gpu_pin_host): then the copy engine reads it in place

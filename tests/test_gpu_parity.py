@@ -388,3 +388,39 @@ def test_gpu_full_size_paths_agree(gpu_finder, name, nsets):
     assert (out[5][9] == 0).all()
     for x, y in zip(out[5], out[6]):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("name", ["variants256", "bacterial"])
+def test_gpu_full_size_against_the_oracle(gpu_finder, name):
+    """BASELINE.json configs[2] and configs[4] at their own size against tests/golden/fullsize.json: ONE run of the
+    oracle on exactly these bytes (tests/golden/make_fullsize.py; 80 M suffixes for the bacterial set): counts,
+    rotations, sha256 of the whole sorted block list and of the suffix array and LCP array.  For the bacterial set
+    also through the bucket-sharded entry points (csa_gpu_shard_*, one rank)."""
+    import hashlib, json, os
+    from common import GOLDEN
+    from csa_b200.api import Batch
+    fx = json.load(open(os.path.join(GOLDEN, "fullsize.json")))[name]
+    batch = workload_batch(name, 1, seed=fx["seed"])
+    assert batch.nbases == fx["nbases"]
+    sha = lambda x: hashlib.sha256(np.ascontiguousarray(x, dtype=np.int32).tobytes()).hexdigest()
+
+    def check(what):
+        rot, info = gpu_finder.download()
+        assert info[0].status == fx["status"] == 0, what
+        assert [info[0].count_collected, info[0].count_suffixfree, info[0].count_unique, info[0].count_chains] == fx["counts"], what
+        assert [int(x) for x in rot] == fx["rotations"], what
+        (depth, size, total, interval, nxt), pos = gpu_finder.blocks()
+        got = dict(depth=sha(depth), size=sha(size), totalsize=sha(total), interval=sha(interval), next=sha(nxt), positions=sha(pos))
+        sa, lcp = gpu_finder.suffix_array()
+        got["sa"], got["lcp"] = sha(sa.astype(np.int64)), sha(lcp)
+        for k, v in got.items():
+            assert v == fx["sha256"][k], (what, k)
+
+    gpu_finder.upload(batch)
+    gpu_finder.run(flags=1)
+    check("one GPU")
+    if name == "bacterial":
+        from csa_b200.shard import run_bucket_sharded
+        gpu_finder.upload(batch)
+        run_bucket_sharded(gpu_finder, 0, 1, cuda=True, flags=1)
+        check("bucket entry points, one rank")
