@@ -16,6 +16,8 @@ def main():
     for name, nsets in zip(args[::2], args[1::2]):
         batch = workload_batch(name, int(nsets), seed=1000)
         rf = RotationFinder(device=0)
+        if os.environ.get("KBENCH_MODE"):
+            rf.debug_rounds(int(os.environ["KBENCH_MODE"]))  # csa_gpu_debug_rounds: force one of the equivalent suffix-array paths
         rf.upload(batch)
         for _ in range(3):
             rf.run()
