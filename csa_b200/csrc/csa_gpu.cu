@@ -64,10 +64,10 @@ struct csa_gpu_ctx {
     int force_kasai = 0;
     int rounds_list = 0, round_mode = 0;
     int rounds_tiled = 0, rounds_global = 0, rounds_quad = 0, force_global_rounds = 0, no_quad_rounds = 0;
-    DevMem pyr, sa0, saidx0, leaf_set, lcp0, psv, nsv, pse, parent, nsize, minpos, val, up, val2, up2;
+    DevMem pyr, pyr2, sa0, saidx0, leaf_set, lcp0;
+    Seq0Q q0{};                 // sequence 0 of every set (stage_seq0)
     DevMem set_nblocks, set_blk0, set_pos0, set_flags, set_nchains, set_cyclic, firstmax, set_collected, set_suffixfree;
     DevMem set_neff, seq_per, rare_collected, rare_suffixfree; // rare.cuh
-    u32 *dfs = nullptr;         // DFS numbers of the sequence-0 tree's nodes (one of val/val2) after stage_seq0_tree
     bool have_stats = false;
     std::vector<u32> h_set_collected, h_set_suffixfree;
     DevMem blk_lb, blk_depth, blk_set, order, o_depth, o_set, o_pos, elem_blk, seghead, succ_lo, succ_hi;
@@ -142,8 +142,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
                      &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
-                     &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->bk_hist, &c->chb_sets, &c->chb_evbase, &c->chb_events, &c->chb_work, &c->chb_redo, &c->counter, &c->tiles, &c->pyr, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv,
-                     &c->pse, &c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2, &c->set_nblocks,
+                     &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->bk_hist, &c->chb_sets, &c->chb_evbase, &c->chb_events, &c->chb_work, &c->chb_redo, &c->counter, &c->tiles, &c->pyr, &c->pyr2, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->set_nblocks,
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->set_neff, &c->seq_per, &c->rare_collected, &c->rare_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
                      &c->succ_lo, &c->succ_hi, &c->next, &c->gap, &c->size, &c->total, &c->interval, &c->inv, &c->f_depth,
@@ -701,79 +700,52 @@ static int stage_stats(csa_gpu_ctx *c, const BatchView &v) {
     return 0;
 }
 
-// the LCP-interval tree of sequence 0 of every set and the DFS number of each of its nodes (c->dfs)
-static int stage_seq0_tree(csa_gpu_ctx *c, const BatchView &v) {
+// sequence 0 of every set: its rotations in SA order (sa0), their LCPs (lcp0) and two pyramids of block minima over them --
+// all the block order, the literal list walk (rare.cuh) and the block letters need of the reference's tree (Seq0Q)
+static int build_pyramid(csa_gpu_ctx *c, DevMem &mem, const u32 *level0, u32 n, Pyramid &py) {
+    Exec &ex = c->ex;
+    size_t tot = 0;
+    for (u32 sz = n; sz > 32;) { sz = (sz + 31) / 32; tot += sz; }
+    TRY(dev_alloc(mem, sizeof(u32) * (tot + 32)));
+    py.nlev = 1; py.lev[0] = level0; py.size[0] = n;
+    u32 *next = P<u32>(mem);
+    while (py.size[py.nlev - 1] > 32 && py.nlev < PYR_MAX) {
+        u32 nin = py.size[py.nlev - 1], nout = (nin + 31) / 32;
+        PyrArgs a{py.lev[py.nlev - 1], next, nin};
+        launch_pyr(ex, nout, a);
+        py.lev[py.nlev] = next; py.size[py.nlev] = nout; py.nlev++;
+        next += nout;
+    }
+    for (int l = py.nlev; l < PYR_MAX; l++) { py.lev[l] = nullptr; py.size[l] = 0; }
+    return 0;
+}
+
+static int stage_seq0(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
     u32 N0 = c->N0;
     u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t5);
-    size_t n1 = sizeof(u32) * (size_t)N0, n2 = 2 * n1;
-    DevMem *one[] = {&c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->psv, &c->nsv, &c->pse};
+    size_t n1 = sizeof(u32) * (size_t)N0;
+    DevMem *one[] = {&c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0};
     for (DevMem *m : one) TRY(dev_alloc(*m, n1));
-    DevMem *two[] = {&c->parent, &c->nsize, &c->minpos, &c->val, &c->up, &c->val2, &c->up2};
-    for (DevMem *m : two) TRY(dev_alloc(*m, n2));
     { Seq0TakeArgs a{v, sa, P<u32>(c->saidx0), P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0take(ex, N0, a); }
     { Lcp0Args a{lcp, P<u32>(c->saidx0), P<u32>(c->leaf_set), P<u32>(c->z0), P<u32>(c->lcp0)}; launch_lcp0(ex, N0, a); }
-    Seq0View q{N0, P<u32>(c->z0), P<u32>(c->leaf_set), P<u32>(c->lcp0)};
-    Pyramid py;
-    {   // block minima of lcp0, factor 32 per level, all levels in one buffer
-        size_t tot = 0;
-        for (u32 sz = N0; sz > 32;) { sz = (sz + 31) / 32; tot += sz; }
-        TRY(dev_alloc(c->pyr, sizeof(u32) * (tot + 32)));
-        py.nlev = 1; py.lev[0] = P<u32>(c->lcp0); py.size[0] = N0;
-        u32 *next = P<u32>(c->pyr);
-        while (py.size[py.nlev - 1] > 32 && py.nlev < PYR_MAX) {
-            u32 nin = py.size[py.nlev - 1], nout = (nin + 31) / 32;
-            PyrArgs a{py.lev[py.nlev - 1], next, nin};
-            launch_pyr(ex, nout, a);
-            py.lev[py.nlev] = next; py.size[py.nlev] = nout; py.nlev++;
-            next += nout;
-        }
-        for (int l = py.nlev; l < PYR_MAX; l++) { py.lev[l] = nullptr; py.size[l] = 0; }
-    }
-    { AnsvArgs a{q, py, P<u32>(c->psv), P<u32>(c->nsv), P<u32>(c->pse)}; launch_ansv(ex, N0, a); }
-    { TreeArgs a{q, P<u32>(c->psv), P<u32>(c->nsv), P<u32>(c->pse), P<u32>(c->sa0), P<u32>(c->parent), P<u32>(c->nsize), P<u32>(c->minpos)};
-      launch_tree(ex, 2ll * N0, a); }
-    { MinposArgs a{N0, P<u32>(c->parent), P<u32>(c->minpos)}; launch_minpos(ex, N0, a); }
-    const int mbits = bits_for(c->n0max);
-    { ChildKeyArgs a{N0, P<u32>(c->parent), P<u32>(c->minpos), P<u64>(c->keysA), P<u32>(c->valsA), mbits}; launch_childkey(ex, 2ll * N0, a); }
-    TRY(sort_pairs(c, 2ll * N0, 0, mbits + bits_for(2ull * N0)));
-    { BeforeArgs a{P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->nsize), P<u32>(c->val), P<u32>(c->up), P<u32>(c->parent), mbits};
-      launch_before(ex, 2ll * N0, a); }
-    // pointer jumping: the tree is as deep as log_4 of the set in practice, n0 at worst; stop when
-    // nobody moved (looked at every third round)
-    int rounds = bits_for(c->n0max) + 1;
-    u32 *val = P<u32>(c->val), *up = P<u32>(c->up), *val2 = P<u32>(c->val2), *up2 = P<u32>(c->up2);
-    u32 *moving = P<u32>(c->counter) + 12;
-    for (int r = 0; r < rounds; r++) { // (a round over 2 N0 nodes costs ten times a look at the flag: look after every round but the first three)
-        TRY(dev_zero(ex, moving, sizeof(u32)));
-        JumpArgs a{val, up, val2, up2, moving};
-        launch_jump(ex, 2ll * N0, a);
-        std::swap(val, val2); std::swap(up, up2);
-        if (r >= 3) {
-            u32 m = 0;
-            TRY(read_u32(c, moving, &m));
-            if (!m) break;
-        }
-    }
-    c->dfs = val;
+    c->q0.N0 = N0; c->q0.z0 = P<u32>(c->z0); c->q0.leaf_set = P<u32>(c->leaf_set); c->q0.saidx0 = P<u32>(c->saidx0);
+    TRY(build_pyramid(c, c->pyr, P<u32>(c->lcp0), N0, c->q0.lcp));
+    TRY(build_pyramid(c, c->pyr2, P<u32>(c->sa0), N0, c->q0.pos));
     return 0;
 }
 
 static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
-    u32 N0 = c->N0, B = c->B;
+    u32 B = c->B;
     u32 *sa = P<u32>(c->sa);
-    // order the blocks: DFS number descending, then stably (set, depth descending)
+    // (set, depth descending), stable; then the blocks of equal depth of a set by the DFS that met them
     TRY(dev_alloc(c->blk_leaf, sizeof(u32) * (size_t)B));
-    BlockKeyArgs k{v, sa, P<u32>(c->saidx0), P<u32>(c->z0), c->dfs, N0, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set),
-                   P<u64>(c->keysA), P<u32>(c->valsA), 0, P<u32>(c->blk_leaf)};
-    launch_blockkey(ex, B, k);
-    TRY(sort_pairs(c, B, 0, 32));
-    k.keys = P<u64>(c->keysA); k.vals = P<u32>(c->valsA); k.pass = 1;
-    launch_blockkey(ex, B, k);
-    TRY(sort_pairs(c, B, 0, 32 + bits_for((u64)c->nsets - 1)));
     TRY(dev_alloc(c->order, sizeof(u32) * (size_t)B));
-    TRY(d2d(ex, c->order.p, c->valsA.p, sizeof(u32) * (size_t)B));
+    { BlockKeyArgs k{v, sa, c->q0, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set), P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->blk_leaf)};
+      launch_blockkey(ex, B, k); }
+    TRY(sort_pairs(c, B, 0, 32 + bits_for((u64)c->nsets - 1)));
+    { BlockRankArgs r{c->q0, P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->blk_leaf), B, P<u32>(c->order)}; launch_blockrank(ex, B, r); }
     return 0;
 }
 
@@ -933,9 +905,9 @@ static int run_phases(csa_gpu_ctx *c, int max_interval, unsigned flags, int phas
     { RareCollapseArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->set_flags), P<u32>(c->t2), P<u32>(c->set_neff), P<u32>(c->seq_per)};
       launch_rarecollapse(ex, nsets, a); }
     TRY(stage_common_blocks(c, v));
-    TRY(stage_seq0_tree(c, v));
+    TRY(stage_seq0(c, v));
     { RareBlocksArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->t1), P<u32>(c->set_flags), P<u32>(c->set_neff), P<u32>(c->seq_per), P<u32>(c->t2),
-                       P<u32>(c->saidx0), P<u32>(c->z0), c->dfs, c->N0,
+                       c->q0,
                        {P<u32>(c->keysA), P<u32>(c->keysA) + N, P<u32>(c->keysB), P<u32>(c->keysB) + N, P<u32>(c->valsA), P<u32>(c->valsB)},
                        P<u32>(c->t0), P<u32>(c->t3), P<u32>(c->rare_collected), P<u32>(c->rare_suffixfree)};
       launch_rareblocks(ex, nsets, a); }
@@ -1246,7 +1218,7 @@ extern "C" long long csa_gpu_batch_block_letters(csa_gpu_ctx *c, char *letters, 
     TRY(dev_alloc(c->let_off, sizeof(unsigned long long) * ((size_t)B + 1)));
     TRY(dev_alloc(c->let_out, (size_t)T));
     TRY(h2d(ex, c->let_off.p, off.data(), sizeof(unsigned long long) * ((size_t)B + 1)));
-    BlockLettersArgs a{view_of(c), P<unsigned char>(c->raw), P<u32>(c->z0), c->N0, P<u32>(c->parent), P<u32>(c->minpos), P<u32>(c->lcp0),
+    BlockLettersArgs a{view_of(c), P<unsigned char>(c->raw), c->q0,
                        P<int>(c->f_depth), P<int>(c->f_pos), P<u32>(c->f_leaf), P<u32>(c->f_set), P<u32>(c->set_blk0), P<u32>(c->set_pos0),
                        P<unsigned long long>(c->let_off), B, P<char>(c->let_out)};
     launch_blockletters(ex, (long long)T, a);

@@ -697,137 +697,84 @@ HD u32 next_below(const Pyramid &py, u32 i, u32 v) {
     }
 }
 
-struct AnsvArgs { Seq0View q; Pyramid py; u32 *psv; u32 *nsv; u32 *pse; };
-HD void ansv_body(long long ti, const AnsvArgs &a) {
-    u32 t = (u32)ti;
-    u32 s = a.q.leaf_set[t];
-    u32 z0 = LDG(a.q.z0 + s), z1 = LDG(a.q.z0 + s + 1);
-    if (t == z0) { a.psv[t] = z0; a.nsv[t] = z1; a.pse[t] = z0; return; }
-    u32 v = a.q.lcp0[t];
-    u32 j = prev_below(a.py, t, v, true);
-    a.pse[t] = (j == CSA_NONE || j < z0) ? z0 : j; // z0 = none
-    j = prev_below(a.py, t, v, false);
-    a.psv[t] = (j == CSA_NONE || j < z0) ? z0 : j;
-    j = next_below(a.py, t, v);
-    a.nsv[t] = (j == CSA_NONE || j > z1) ? z1 : j; // z1 = none
-}
-MAP_KERNEL(ansv, AnsvArgs, 16)
-
-// Node numbering: internal node = its representative border t (the leftmost border of the node
-// whose value is the node's depth), leaf t = N0 + t.  parent[] of both kinds; the root points at
-// itself.  size[] = leaves below, minpos[] = first occurrence in sequence 0.
-HD u32 rep_of(const u32 *psv, const u32 *pse, u32 t) {
-    while (pse[t] != psv[t]) t = pse[t];
-    return t;
-}
-HD u32 parent_of_span(const Seq0View &q, const u32 *psv, const u32 *pse, u32 z0, u32 z1, u32 lb, u32 rb, u32 self) {
-    long long vl = (lb == z0) ? -1 : (long long)q.lcp0[lb];
-    long long vr = (rb + 1 == z1) ? -1 : (long long)q.lcp0[rb + 1];
-    if (vl < 0 && vr < 0) return self; // the root
-    if (vl >= vr) return rep_of(psv, pse, lb);
-    return rb + 1;
-}
-struct TreeArgs { Seq0View q; const u32 *psv; const u32 *nsv; const u32 *pse; const u32 *sa0; u32 *parent; u32 *size; u32 *minpos; };
-HD void tree_body(long long x, const TreeArgs &a) {
-    u32 N0 = a.q.N0;
-    if ((u32)x < N0) { // border x: an internal node iff x is a representative
-        u32 t = (u32)x;
-        u32 s = a.q.leaf_set[t];
-        u32 z0 = LDG(a.q.z0 + s), z1 = LDG(a.q.z0 + s + 1);
-        a.minpos[t] = 0xFFFFFFFFu;
-        if (t == z0 || a.pse[t] != a.psv[t]) { a.parent[t] = CSA_NONE; a.size[t] = 0; return; }
-        u32 lb = a.psv[t], rb = a.nsv[t] - 1;
-        a.parent[t] = parent_of_span(a.q, a.psv, a.pse, z0, z1, lb, rb, t);
-        a.size[t] = rb - lb + 1;
-    } else {
-        u32 t = (u32)x - N0;
-        u32 s = a.q.leaf_set[t];
-        u32 z0 = LDG(a.q.z0 + s), z1 = LDG(a.q.z0 + s + 1);
-        a.parent[x] = parent_of_span(a.q, a.psv, a.pse, z0, z1, t, t, (u32)x);
-        a.size[x] = 1;
-        a.minpos[x] = a.sa0[t];
+// What the block order needs of the LCP-interval tree of sequence 0 -- which of two leaves the DFS of csamsa.c:64 meets
+// first -- is answered from two pyramids of block minima (over lcp0 and over the positions sa0), without building the tree:
+// the node where leaves a < b part has depth d = min lcp0(a+1..b]; the child of that node that holds a leaf t is the widest
+// range of leaves round t inside which lcp0 stays above d; children are met in the order of their first occurrence in
+// sequence 0 (creation order, gencycsuffixtrees.c:193) = the smallest sa0 of the range.  (Round 1 built the whole tree --
+// nearest smaller values, parents, first occurrences by atomics, children sorted by a 5-pass radix sort, DFS numbers by
+// pointer jumping over 2 N0 nodes, 3.4 ms of an 18 ms step -- to number ALL rotations of sequence 0, of which a few hundred
+// per set, the blocks, were ever looked up.)
+struct Seq0Q {
+    u32 N0; const u32 *z0; const u32 *leaf_set; const u32 *saidx0;
+    Pyramid lcp; // over lcp0
+    Pyramid pos; // over sa0
+};
+// smallest value of level 0 in [lo, hi), lo < hi
+HD u32 pyr_min(const Pyramid &py, u32 lo, u32 hi) {
+    u32 m = 0xFFFFFFFFu;
+    int level = 0;
+    while (lo < hi) {
+        while (lo < hi && (lo & 31u)) { const u32 x = py.lev[level][lo]; m = x < m ? x : m; lo++; }
+        while (lo < hi && (hi & 31u)) { hi--; const u32 x = py.lev[level][hi]; m = x < m ? x : m; }
+        if (lo >= hi) break;
+        if (level + 1 >= py.nlev) { for (; lo < hi; lo++) { const u32 x = py.lev[level][lo]; m = x < m ? x : m; } break; }
+        lo >>= 5; hi >>= 5; level++;
     }
+    return m;
 }
-MAP_KERNEL(tree, TreeArgs, 24)
-
-// first occurrence of every node: each leaf climbs while it lowers the minimum
-struct MinposArgs { u32 N0; const u32 *parent; u32 *minpos; };
-HD void minpos_body(long long t, const MinposArgs &a) {
-    u32 x = a.N0 + (u32)t;
-    u32 val = a.minpos[x];
-    u32 p = a.parent[x];
-    while (p != x) {
-        u32 old = ATOMIC_MIN(a.minpos + p, val);
-        if (old <= val) break;
-        x = p;
-        p = a.parent[x];
-    }
+// first occurrence in sequence 0 of the string of the child, below a node of depth d, that holds leaf t
+HD u32 seq0_child_minpos(const Seq0Q &q, u32 t, u32 d) {
+    u32 pl = prev_below(q.lcp, t + 1, d, true); // (lcp0 is 0 at the first leaf of every set: found inside the set)
+    if (pl == CSA_NONE) pl = 0;
+    u32 pr = next_below(q.lcp, t, d + 1);
+    if (pr == CSA_NONE) pr = q.N0;
+    return pyr_min(q.pos, pl, pr);
 }
-MAP_KERNEL(minpos, MinposArgs, 12)
-
-// children grouped by parent and ordered by first occurrence: sort key (parent, minpos)
-struct ChildKeyArgs { u32 N0; const u32 *parent; const u32 *minpos; u64 *keys; u32 *vals; int mbits; };
-HD void childkey_body(long long x, const ChildKeyArgs &a) {
-    u32 p = a.parent[x];
-    // borders that are no node, and roots, sort to the end; minpos < 2^mbits (a position in sequence 0)
-    bool live = (p != CSA_NONE) && (p != (u32)x);
-    a.keys[x] = live ? (((u64)p << a.mbits) | a.minpos[x]) : ~0ull;
-    a.vals[x] = (u32)x;
+// does the DFS of csamsa.c:64 meet leaf t1 before leaf t2 (two leaves of one set)?
+HD bool seq0_before(const Seq0Q &q, u32 t1, u32 t2) {
+    if (t1 == t2) return false;
+    const u32 a = t1 < t2 ? t1 : t2, b = t1 < t2 ? t2 : t1;
+    const u32 d = pyr_min(q.lcp, a + 1, b + 1);
+    const bool a_first = seq0_child_minpos(q, a, d) < seq0_child_minpos(q, b, d);
+    return t1 < t2 ? a_first : !a_first;
 }
-MAP_KERNEL(childkey, ChildKeyArgs, 20)
-
-struct BeforeArgs { const u64 *keys; const u32 *vals; const u32 *size; u32 *val; u32 *up; const u32 *parent; int mbits; };
-HD void before_body(long long j, const BeforeArgs &a) {
-    u64 key = a.keys[j];
-    u32 x = a.vals[j];
-    if (key == ~0ull) { a.val[x] = 0; a.up[x] = (a.parent[x] == CSA_NONE) ? x : a.parent[x]; return; }
-    u32 p = (u32)(key >> a.mbits);
-    u32 sum = 0;
-    for (long long q = j - 1; q >= 0 && a.keys[q] != ~0ull && (u32)(a.keys[q] >> a.mbits) == p; q--) sum += a.size[a.vals[q]];
-    a.val[x] = sum;
-    a.up[x] = p;
+// the first leaf of set s at or behind SA place i
+HD u32 seq0_leaf_at(const Seq0Q &q, u32 s, u32 i) {
+    const u32 z = LDG(q.z0 + s), n0 = LDG(q.z0 + s + 1) - z;
+    u32 lo = 0, hi = n0;
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (q.saidx0[z + mid] < i) lo = mid + 1; else hi = mid; }
+    return z + lo;
 }
-MAP_KERNEL(before, BeforeArgs, 24)
 
-struct JumpArgs { const u32 *val; const u32 *up; u32 *val2; u32 *up2; u32 *moving; };
-HD void jump_body(long long x, const JumpArgs &a) {
-    u32 u = a.up[x];
-    u32 uu = a.up[u];
-    a.val2[x] = a.val[x] + a.val[u];
-    a.up2[x] = uu;
-    if (uu != u) *a.moving = 1u; // somebody has not reached its root yet (same value from every writer)
-}
-MAP_KERNEL(jump, JumpArgs, 16)
-
-// per block: its sort keys and its positions (one per sequence of the set)
+// per block: its leaf in sequence 0 and the key (set, depth descending); after the (stable) sort by that key the blocks of
+// equal set and depth are put in the order the reference's list has them: the one the DFS meets LATER first
+// (nodeslinkedlists.c:36 inserts in front of equal depths)
 struct BlockKeyArgs {
-    BatchView v; const u32 *sa; const u32 *saidx0; const u32 *z0; const u32 *dfs; u32 N0;
+    BatchView v; const u32 *sa; Seq0Q q;
     const u32 *blk_lb; const u32 *blk_depth; const u32 *blk_set;
-    u64 *keys; u32 *vals; int pass; // pass 0: dfs descending; pass 1: (set, depth descending)
-    u32 *blk_leaf;                  // pass 0: the block's leaf in the sequence-0 tree (k_blockletters climbs from it)
+    u64 *keys; u32 *vals; u32 *blk_leaf;
 };
 HD void blockkey_body(long long b, const BlockKeyArgs &a) {
-    if (a.pass == 0) {
-        u32 lb = a.blk_lb[b];
-        u32 s = a.blk_set[b];
-        u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
-        u32 d = 0;
-        const u32 k0 = LDG(a.v.set_seq0 + s), z = LDG(a.z0 + s), n0 = LDG(a.z0 + s + 1) - z;
-        for (u32 j = lb; j < lb + m; j++)
-            if (seq_of(a.v, a.sa[j]) == k0) { // the block's place in sequence 0: its leaf = the one with SA place j
-                u32 lo = 0, hi = n0;
-                while (lo < hi) { u32 mid = (lo + hi) >> 1; if (a.saidx0[z + mid] < j) lo = mid + 1; else hi = mid; }
-                d = a.dfs[a.N0 + z + lo];
-                a.blk_leaf[b] = z + lo;
-            }
-        a.keys[b] = 0xFFFFFFFFu - d;
-        a.vals[b] = (u32)b;
-    } else {
-        u32 ob = a.vals[b];
-        a.keys[b] = ((u64)a.blk_set[ob] << 32) | (0xFFFFFFFFu - a.blk_depth[ob]);
-    }
+    const u32 lb = a.blk_lb[b], s = a.blk_set[b];
+    const u32 k0 = LDG(a.v.set_seq0 + s), m = LDG(a.v.set_seq0 + s + 1) - k0;
+    for (u32 j = lb; j < lb + m; j++)
+        if (seq_of(a.v, a.sa[j]) == k0) a.blk_leaf[b] = seq0_leaf_at(a.q, s, j); // the block's place in sequence 0
+    a.keys[b] = ((u64)s << 32) | (0xFFFFFFFFu - a.blk_depth[b]);
+    a.vals[b] = (u32)b;
 }
 MAP_KERNEL(blockkey, BlockKeyArgs, 16)
+
+struct BlockRankArgs { Seq0Q q; const u64 *keys; const u32 *vals; const u32 *blk_leaf; u32 B; u32 *order; };
+HD void blockrank_body(long long i, const BlockRankArgs &a) {
+    const u64 key = a.keys[i];
+    const u32 me = a.vals[i], leaf = a.blk_leaf[me];
+    u32 c0 = (u32)i, later = 0;
+    while (c0 > 0 && a.keys[c0 - 1] == key) { c0--; if (seq0_before(a.q, leaf, a.blk_leaf[a.vals[c0]])) later++; }
+    for (u32 j = (u32)i + 1; j < a.B && a.keys[j] == key; j++) if (seq0_before(a.q, leaf, a.blk_leaf[a.vals[j]])) later++;
+    a.order[c0 + later] = me;
+}
+MAP_KERNEL(blockrank, BlockRankArgs, 16)
 
 // blocks in list order: gather fields, write positions
 struct BlockGatherArgs {
@@ -1291,10 +1238,10 @@ MAP_KERNEL(rot, RotArgs, 8)
 // edge (labelfrom/startpos, gencycsuffixtrees.c:160-218).  The edge that holds letter number j of block X was
 // created by the first rotation, in insertion order, that begins with X[0..j]: a rotation of sequence 0 (every
 // block occurs there), at the smallest such position p: letter = texts[0][p+j].  A, C, G, T are the same at every
-// occurrence; a letter outside ACGT is spelled as that first occurrence has it.  p = minpos of the highest node
-// of the sequence-0 tree at or above the block's leaf that is at least j+1 deep.
+// occurrence; a letter outside ACGT is spelled as that first occurrence has it.  p = the smallest position among
+// the rotations of sequence 0 that share the block's first j+1 letters (seq0_child_minpos).
 struct BlockLettersArgs {
-    BatchView v; const unsigned char *raw; const u32 *z0; u32 N0; const u32 *parent; const u32 *minpos; const u32 *lcp0;
+    BatchView v; const unsigned char *raw; Seq0Q q;
     const int *f_depth; const int *f_pos; const u32 *f_leaf; const u32 *f_set; const u32 *set_blk0; const u32 *set_pos0;
     const unsigned long long *offsets; u32 B; char *out;
 };
@@ -1307,15 +1254,8 @@ HD void blockletters_body(long long t, const BlockLettersArgs &a) {
     const u32 off = LDG(a.v.seq_off + k0), n0 = LDG(a.v.seq_off + k0 + 1) - off;
     const u32 p0 = (u32)a.f_pos[pos_offset(a.set_blk0, a.set_pos0, s, m, b)];
     unsigned char c = a.raw[off + (p0 + j) % n0];
-    if (code_of_letter(c) > 3) {
-        u32 x = a.N0 + a.f_leaf[b];
-        for (;;) {
-            const u32 p = a.parent[x];
-            if (p == x || p == CSA_NONE || a.lcp0[p] < j + 1) break;
-            x = p;
-        }
-        c = a.raw[off + (a.minpos[x] + j) % n0];
-    }
+    // (the rotations that begin with the block's first j+1 letters: the child, below depth j, that holds the block's leaf)
+    if (code_of_letter(c) > 3) c = a.raw[off + (seq0_child_minpos(a.q, a.f_leaf[b], j) + j) % n0];
     a.out[t] = (char)c;
 }
 MAP_KERNEL(blockletters, BlockLettersArgs, 2)

@@ -71,7 +71,7 @@ MAP_KERNEL(rarecollapse, RareCollapseArgs, 0)
 struct RareBlocksArgs {
     BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *set_flags; const u32 *set_neff; const u32 *seq_per;
     u32 *isa;                                    // [N] written here for the set's range
-    const u32 *saidx0; const u32 *z0; const u32 *dfs; u32 N0; // sequence-0 tree: SA places of its leaves, DFS numbers
+    Seq0Q q;                                     // sequence 0 of every set: which of two leaves the DFS meets first
     u32 *w[6];                                   // scratch, N entries each; a set uses its own range
     u32 *isblock; u32 *depth;
     u32 *rare_collected; u32 *rare_suffixfree;
@@ -83,23 +83,34 @@ HD void rare_span(const u32 *lcp, u32 lo, u32 hi, u32 r, u32 len, u32 *l_out, u3
     while (r + 1 < hi && lcp[r + 1] >= len) r++;
     *l_out = l; *r_out = r;
 }
-// heap sort of idx[0..n) by the pair (hi[idx], lo[idx]), DESCENDING (a min-heap emptied towards the end)
-HD bool rare_less(const u32 *hi, const u32 *lo, u32 x, u32 y) { return hi[x] != hi[y] ? hi[x] < hi[y] : lo[x] < lo[y]; }
-HD void rare_sift(const u32 *hi, const u32 *lo, u32 *idx, u32 root, u32 n) {
+// heap sort of idx[0..n), DESCENDING by `less` (a min-heap emptied towards the end)
+template <class Less> HD void rare_sift(const Less &less, u32 *idx, u32 root, u32 n) {
     for (;;) {
         u32 c = 2 * root + 1;
         if (c >= n) return;
-        if (c + 1 < n && rare_less(hi, lo, idx[c + 1], idx[c])) c++;
-        if (!rare_less(hi, lo, idx[c], idx[root])) return;
+        if (c + 1 < n && less(idx[c + 1], idx[c])) c++;
+        if (!less(idx[c], idx[root])) return;
         u32 t = idx[root]; idx[root] = idx[c]; idx[c] = t;
         root = c;
     }
 }
-HD void rare_sort_desc(const u32 *hi, const u32 *lo, u32 *idx, u32 n) {
+template <class Less> HD void rare_sort_desc(const Less &less, u32 *idx, u32 n) {
     for (u32 i = 0; i < n; i++) idx[i] = i;
-    for (u32 i = n / 2; i-- > 0;) rare_sift(hi, lo, idx, i, n);
-    for (u32 x = n; x > 1; x--) { u32 t = idx[0]; idx[0] = idx[x - 1]; idx[x - 1] = t; rare_sift(hi, lo, idx, 0, x - 1); }
+    for (u32 i = n / 2; i-- > 0;) rare_sift(less, idx, i, n);
+    for (u32 x = n; x > 1; x--) { u32 t = idx[0]; idx[0] = idx[x - 1]; idx[x - 1] = t; rare_sift(less, idx, 0, x - 1); }
 }
+// list order of two nodes (nodeslinkedlists.c:36): deeper first, of equal depth the one the DFS meets LATER first
+struct RareNodeLess {
+    const u32 *depth; const u32 *leaf; const Seq0Q *q;
+    HDM bool operator()(u32 x, u32 y) const { // x stands BEHIND y in the list ("smaller")
+        if (depth[x] != depth[y]) return depth[x] < depth[y];
+        return seq0_before(*q, leaf[x], leaf[y]);
+    }
+};
+struct RarePairLess {
+    const u32 *hi; const u32 *lo;
+    HDM bool operator()(u32 x, u32 y) const { return hi[x] != hi[y] ? hi[x] < hi[y] : lo[x] < lo[y]; }
+};
 HD void rareblocks_body(long long si, const RareBlocksArgs &a) {
     const u32 s = (u32)si;
     if (!(a.set_flags[s] & CSA_FLAG_RARE)) return;
@@ -134,16 +145,13 @@ HD void rareblocks_body(long long si, const RareBlocksArgs &a) {
     if (C == 0) return;
     // -- list order (nodeslinkedlists.c:36): depth descending, then the node met LATER in the DFS first
     // (the stack is done, its arrays are free again)
-    u32 *c_dfs = st_lcp, *ord = st_child, *nxt = c_lb + H, *prv = c_rb + H, *gone = c_depth + H;
+    u32 *c_leaf = st_lcp, *ord = st_child, *nxt = c_lb + H, *prv = c_rb + H, *gone = c_depth + H;
     (void)st_lb;
     {
-        const u32 z = LDG(a.z0 + s), n0 = LDG(a.z0 + s + 1) - z;
-        for (u32 c = 0; c < C; c++) {
-            u32 lo = 0, hi = n0; // first leaf of sequence 0 at or behind the node's left border: it lies below the node
-            while (lo < hi) { u32 mid = (lo + hi) >> 1; if (a.saidx0[z + mid] < c_lb[c]) lo = mid + 1; else hi = mid; }
-            c_dfs[c] = a.dfs[a.N0 + z + lo];
-        }
-        rare_sort_desc(c_depth, c_dfs, ord, C);
+        // (the first leaf of sequence 0 at or behind a node's left border lies below the node)
+        for (u32 c = 0; c < C; c++) c_leaf[c] = seq0_leaf_at(a.q, s, c_lb[c]);
+        const RareNodeLess less{c_depth, c_leaf, &a.q};
+        rare_sort_desc(less, ord, C);
     }
     // ord[i] = node at list place i
     for (u32 i = 0; i < C; i++) { nxt[i] = i + 1 < C ? i + 1 : CSA_NONE; prv[i] = i ? i - 1 : CSA_NONE; gone[i] = 0; }
@@ -234,7 +242,7 @@ HD void rarewalk_body(long long si, const RareWalkArgs &a) {
                 ev_e[ne] = e; ev_b[ne] = b;
                 ne++;
             }
-        rare_sort_desc(ev_e, ev_b, ord, ne); // read backwards: ascending by (place, block)
+        { const RarePairLess less{ev_e, ev_b}; rare_sort_desc(less, ord, ne); } // read backwards: ascending by (place, block)
         u32 limit = n, prev = CSA_NONE;
         bool first = true;
         for (u32 x = ne; x-- > 0;) {
