@@ -72,7 +72,7 @@ struct csa_gpu_ctx {
     std::vector<u32> h_set_collected, h_set_suffixfree;
     DevMem blk_lb, blk_depth, blk_set, order, o_depth, o_set, o_pos, elem_blk, seghead, succ_lo, succ_hi;
     DevMem next, gap, size, total, interval, inv, f_depth, f_size, f_total, f_interval, f_next, f_pos, rotations;
-    DevMem blk_leaf, f_leaf, f_set, let_off, let_out; // csa_gpu_batch_block_letters
+    DevMem blk_leaf, blk_tab, f_leaf, f_set, let_off, let_out; // block order; csa_gpu_batch_block_letters
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
     // per-kernel profile of the last run (csa_gpu_profile_*)
@@ -146,7 +146,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->set_neff, &c->seq_per, &c->rare_collected, &c->rare_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
                      &c->succ_lo, &c->succ_hi, &c->next, &c->gap, &c->size, &c->total, &c->interval, &c->inv, &c->f_depth,
-                     &c->f_size, &c->f_total, &c->f_interval, &c->f_next, &c->f_pos, &c->rotations, &c->blk_leaf, &c->f_leaf, &c->f_set, &c->let_off, &c->let_out};
+                     &c->f_size, &c->f_total, &c->f_interval, &c->f_next, &c->f_pos, &c->rotations, &c->blk_leaf, &c->blk_tab, &c->f_leaf, &c->f_set, &c->let_off, &c->let_out};
     for (DevMem *m : all) dev_free(*m);
     for (int i = 0; i < 4; i++) dev_free(c->ps.block_sums[i]);
     dev_free(c->ps.counts);
@@ -745,7 +745,12 @@ static int stage_block_order(csa_gpu_ctx *c, const BatchView &v) {
     { BlockKeyArgs k{v, sa, c->q0, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set), P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->blk_leaf)};
       launch_blockkey(ex, B, k); }
     TRY(sort_pairs(c, B, 0, 32 + bits_for((u64)c->nsets - 1)));
-    { BlockRankArgs r{c->q0, P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->blk_leaf), B, P<u32>(c->order)}; launch_blockrank(ex, B, r); }
+    u32 *cstart = P<u32>(c->valsB); // (free between sorts)
+    { BlockClassArgs k{P<u64>(c->keysA), cstart}; launch_blockclass(ex, B, k); }
+    TRY((scan_u32<ScanMax, true>(ex, c->ps, cstart, cstart, B)));
+    TRY(dev_alloc(c->blk_tab, sizeof(u32) * (size_t)B * BR_DEPTHS));
+    { BlockTabArgs t{c->q0, P<u32>(c->blk_leaf), P<u32>(c->blk_tab)}; launch_blocktab(ex, (long long)B * BR_DEPTHS, t); }
+    { BlockRankArgs r{c->q0, P<u64>(c->keysA), P<u32>(c->valsA), P<u32>(c->blk_leaf), B, cstart, P<u32>(c->blk_tab), P<u32>(c->order)}; launch_blockrank(ex, B, r); }
     return 0;
 }
 

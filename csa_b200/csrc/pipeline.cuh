@@ -765,16 +765,67 @@ HD void blockkey_body(long long b, const BlockKeyArgs &a) {
 }
 MAP_KERNEL(blockkey, BlockKeyArgs, 16)
 
-struct BlockRankArgs { Seq0Q q; const u64 *keys; const u32 *vals; const u32 *blk_leaf; u32 B; u32 *order; };
+// cstart[i] = first place of the class (equal set and depth) of sorted place i: flags here, a max-scan by the host
+struct BlockClassArgs { const u64 *keys; u32 *cstart; };
+HD void blockclass_body(long long i, const BlockClassArgs &a) { a.cstart[i] = (i > 0 && a.keys[i - 1] != a.keys[i]) ? (u32)i : 0u; }
+MAP_KERNEL(blockclass, BlockClassArgs, 12)
+
+// Two blocks of a class mostly part high up in the tree (two random places of a 5 Mb genome share ~11 letters): the first
+// occurrences of a block's ancestors' children down to depth BR_DEPTHS are looked up once per block (k_blocktab), a
+// comparison is then one range minimum (where the two leaves part) and two table reads.
+#define BR_DEPTHS 16
+struct BlockTabArgs { Seq0Q q; const u32 *blk_leaf; u32 *tab; };
+HD void blocktab_body(long long x, const BlockTabArgs &a) {
+    const u32 b = (u32)(x / BR_DEPTHS), d = (u32)(x % BR_DEPTHS);
+    a.tab[x] = seq0_child_minpos(a.q, a.blk_leaf[b], d);
+}
+MAP_KERNEL(blocktab, BlockTabArgs, 4)
+
+struct BlockRankArgs { Seq0Q q; const u64 *keys; const u32 *vals; const u32 *blk_leaf; u32 B; const u32 *cstart; const u32 *tab; u32 *order; };
+// does the DFS meet block x (leaf tx) before block y?
+HD bool block_before(const BlockRankArgs &a, u32 x, u32 tx, u32 y, u32 ty) {
+    const u32 lo = tx < ty ? tx : ty, hi = tx < ty ? ty : tx;
+    const u32 d = pyr_min(a.q.lcp, lo + 1, hi + 1);
+    if (d < (u32)BR_DEPTHS) return a.tab[(size_t)x * BR_DEPTHS + d] < a.tab[(size_t)y * BR_DEPTHS + d];
+    return seq0_child_minpos(a.q, tx, d) < seq0_child_minpos(a.q, ty, d);
+}
+#ifdef CSA_EMU
 HD void blockrank_body(long long i, const BlockRankArgs &a) {
     const u64 key = a.keys[i];
-    const u32 me = a.vals[i], leaf = a.blk_leaf[me];
-    u32 c0 = (u32)i, later = 0;
-    while (c0 > 0 && a.keys[c0 - 1] == key) { c0--; if (seq0_before(a.q, leaf, a.blk_leaf[a.vals[c0]])) later++; }
-    for (u32 j = (u32)i + 1; j < a.B && a.keys[j] == key; j++) if (seq0_before(a.q, leaf, a.blk_leaf[a.vals[j]])) later++;
+    const u32 me = a.vals[i], leaf = a.blk_leaf[me], c0 = a.cstart[i];
+    u32 later = 0;
+    for (u32 j = c0; j < a.B && a.keys[j] == key; j++)
+        if (j != (u32)i && block_before(a, me, leaf, a.vals[j], a.blk_leaf[a.vals[j]])) later++;
     a.order[c0 + later] = me;
 }
 MAP_KERNEL(blockrank, BlockRankArgs, 16)
+#else
+// one WARP per block: the lanes take the other blocks of its class in turn (a class can hold thousands of blocks -- the
+// short ones of a bacterial set)
+__global__ void __launch_bounds__(256) k_blockrank(long long n, BlockRankArgs a) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    if (i >= n) return;
+    const u64 key = a.keys[i];
+    const u32 me = a.vals[i], leaf = a.blk_leaf[me], c0 = a.cstart[i];
+    u32 later = 0;
+    for (u32 j0 = c0;; j0 += 32u) {
+        const u32 j = j0 + lane;
+        const bool in = j < a.B && a.keys[j] == key;
+        if (in && j != (u32)i) { const u32 other = a.vals[j]; if (block_before(a, me, leaf, other, a.blk_leaf[other])) later++; }
+        if (!__all_sync(0xffffffffu, in)) break;
+    }
+    later = __reduce_add_sync(0xffffffffu, later);
+    if (lane == 0) a.order[c0 + later] = me;
+}
+static inline void launch_blockrank(Exec &ex, long long n, BlockRankArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_blockrank", 16.0 * n);
+    k_blockrank<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
 
 // blocks in list order: gather fields, write positions
 struct BlockGatherArgs {
