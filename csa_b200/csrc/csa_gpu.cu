@@ -59,6 +59,7 @@ struct csa_gpu_ctx {
     DevMem bk_hist;
     DevMem shard_bounds; std::vector<u32> h_shard_bounds;
     DevMem chb_sets, chb_evbase, chb_events, chb_work, chb_redo;
+    bool use_cover = true; int force_cover = 0; // blocks through the cover array R[] (counts asked for, sets of > 64 sequences) or straight from the LCP array
     int no_chain_big = 0, chain_redone = 0; u32 ws_depth_cap = WS_DEPTH_CAP; u32 ws_left[6] = {0, 0, 0, 0, 0, 0};
     double lcp_mean_sample = 0;
     int force_kasai = 0;
@@ -612,22 +613,27 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     return 0;
 }
 
-// cover array and block candidates (collectNodes / removeSuffixNodes / removeNonUniqueNodes on ordinary sets)
+// block candidates (collectNodes / removeSuffixNodes / removeNonUniqueNodes on ordinary sets): through the cover array R[]
+// when the counts are asked for or a set holds more than 64 sequences, else straight from the LCP array (k_blockfind2)
 static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
     u32 N = c->N;
     int nsets = c->nsets;
     u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t5), *nxt = P<u32>(c->t0), *R = P<u32>(c->t1);
+    u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3);
+    TRY(dev_alloc(c->saidx0, sizeof(u32) * (size_t)c->N0));
+    if (!c->use_cover) {
+        { BlockFind2Args a{v, sa, lcp, isblock, depth, c->mmax}; launch_blockfind2(ex, N, a); }
+        return 0;
+    }
     TRY(dev_zero(ex, c->firstmax.p, sizeof(u32) * nsets));
     { ColorKeyArgs a{v, sa, P<u64>(c->keysA), P<u32>(c->valsA)}; launch_colorkey(ex, N, a); }
     TRY(sort_pairs(c, N, 0, bits_for((u64)c->mmax - 1)));
     // colour 0 first: the SA places of sequence 0 of every set, kept for the block-order stage (k_seq0take)
-    TRY(dev_alloc(c->saidx0, sizeof(u32) * (size_t)c->N0));
     TRY(d2d(ex, c->saidx0.p, c->valsA.p, sizeof(u32) * (size_t)c->N0));
     { NextArgs a{v, P<u64>(c->keysA), P<u32>(c->valsA), nxt, P<u32>(c->firstmax)}; launch_next(ex, N, a); }
     { CoverArgs a{v, sa, nxt, P<u32>(c->firstmax), R}; launch_cover(ex, N, a); launch_coverstart(ex, nsets, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, R, R, N)));
-    u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3);
     { BlockFindArgs a{v, sa, lcp, R, isblock, depth, c->mmax}; launch_blockfind(ex, N, a); }
     return 0;
 }
@@ -727,7 +733,14 @@ static int stage_seq0(csa_gpu_ctx *c, const BatchView &v) {
     size_t n1 = sizeof(u32) * (size_t)N0;
     DevMem *one[] = {&c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0};
     for (DevMem *m : one) TRY(dev_alloc(*m, n1));
-    { Seq0TakeArgs a{v, sa, P<u32>(c->saidx0), P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0take(ex, N0, a); }
+    if (c->use_cover) { // (the colour sort left the SA places of sequence 0 first)
+        Seq0TakeArgs a{v, sa, P<u32>(c->saidx0), P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0take(ex, N0, a);
+    } else {            // flag the rotations of sequence 0 (a range check), number them, write them out
+        u32 *flag = P<u32>(c->t4), *idx = P<u32>(c->t1);
+        { Seq0FlagArgs a{v, sa, flag}; launch_seq0flag(ex, c->N, a); }
+        TRY((scan_u32<ScanSum, false>(ex, c->ps, flag, idx, c->N)));
+        { Seq0EmitArgs a{v, sa, flag, idx, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0emit(ex, c->N, a); }
+    }
     { Lcp0Args a{lcp, P<u32>(c->saidx0), P<u32>(c->leaf_set), P<u32>(c->z0), P<u32>(c->lcp0)}; launch_lcp0(ex, N0, a); }
     c->q0.N0 = N0; c->q0.z0 = P<u32>(c->z0); c->q0.leaf_set = P<u32>(c->leaf_set); c->q0.saidx0 = P<u32>(c->saidx0);
     TRY(build_pyramid(c, c->pyr, P<u32>(c->lcp0), N0, c->q0.lcp));
@@ -909,9 +922,10 @@ static int run_phases(csa_gpu_ctx *c, int max_interval, unsigned flags, int phas
     { LeafScanArgs a{v, P<u32>(c->t5), P<u32>(c->set_flags), c->batch_nmin}; launch_leafscan(ex, N, a); }
     { RareCollapseArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->set_flags), P<u32>(c->t2), P<u32>(c->set_neff), P<u32>(c->seq_per)};
       launch_rarecollapse(ex, nsets, a); }
+    c->use_cover = (flags & CSA_GPU_FLAG_STATS) || c->mmax > 64 || c->force_cover;
     TRY(stage_common_blocks(c, v));
     TRY(stage_seq0(c, v));
-    { RareBlocksArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->t1), P<u32>(c->set_flags), P<u32>(c->set_neff), P<u32>(c->seq_per), P<u32>(c->t2),
+    { RareBlocksArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->t1), c->use_cover ? 1 : 0, P<u32>(c->set_flags), P<u32>(c->set_neff), P<u32>(c->seq_per), P<u32>(c->t2),
                        c->q0,
                        {P<u32>(c->keysA), P<u32>(c->keysA) + N, P<u32>(c->keysB), P<u32>(c->keysB) + N, P<u32>(c->valsA), P<u32>(c->valsB)},
                        P<u32>(c->t0), P<u32>(c->t3), P<u32>(c->rare_collected), P<u32>(c->rare_suffixfree)};
@@ -1122,6 +1136,7 @@ extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds
         c->ws_force = force_global == 6; // 6: word sort whatever the groups look like
         c->no_chain_big = force_global == 7; // 7: free choice, but long block lists walked by one thread (k_chain) as short ones are
         c->shard_full_sort = force_global == 8; // 8: sharded runs of one set sort the whole set on every rank (as batches of sets do)
+        c->force_cover = force_global == 9;     // 9: free choice, blocks always through the cover array R[]
         if (force_global >= 6) c->round_mode = 0;
         c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; c->force_kasai = force_global == 2;
     }

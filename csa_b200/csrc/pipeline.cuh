@@ -534,6 +534,132 @@ static inline void launch_blockfind(Exec &ex, long long n, BlockFindArgs a) {
 }
 #endif
 
+// ---- the same blocks without the cover array (sets of up to 64 sequences, no counts asked for) ------------------------------
+// A block is a window of exactly m suffix-array places: an LCP interval (the smallest lcp inside above both lcps at its
+// borders), one rotation of every sequence (m places, m different sequences), not preceded by one and the same letter
+// everywhere.  The LCP conditions need the LCP array alone and leave few candidates; only those have their m sequences
+// looked up.  This path skips k_colorkey, the colour sort, k_next, k_cover and the scan that builds R[] (3.4 ms of a
+// 15.8 ms step); R[] is still built when the counts of csamsa.c:332,338 are asked for (k_windepth, k_plateau work on it)
+// or a set holds more than 64 sequences.
+struct BlockFind2Args { BatchView v; const u32 *sa; const u32 *lcp; u32 *isblock; u32 *depth; u32 mmax; };
+HD bool blockfind2_screen(const BlockFind2Args &a, u32 lb, u32 *s0_out, u32 *s1_out, u32 *m_out) {
+    const u32 s = set_of_pos(a.v, lb);
+    const u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
+    const u32 m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
+    *s0_out = s0; *s1_out = s1; *m_out = m;
+    if (m < 2 || lb + m > s1) return false;
+    const u32 rb = lb + m - 1;
+    // the borders first: lcp rises behind the left one and falls behind the right one
+    if (lb != s0 && a.lcp[lb] >= a.lcp[lb + 1]) return false;
+    if (rb + 1 != s1 && a.lcp[rb + 1] >= a.lcp[rb]) return false;
+    return true;
+}
+#ifdef CSA_EMU
+HD void blockfind2_body(long long i, const BlockFind2Args &a) {
+    const u32 lb = (u32)i;
+    a.isblock[lb] = 0;
+    u32 s0, s1, m;
+    if (!blockfind2_screen(a, lb, &s0, &s1, &m)) return;
+    const u32 rb = lb + m - 1;
+    const long long outer_l = (lb == s0) ? -1 : (long long)a.lcp[lb];
+    const long long outer_r = (rb + 1 == s1) ? -1 : (long long)a.lcp[rb + 1];
+    const long long outer = outer_l > outer_r ? outer_l : outer_r;
+    u32 inner = 0xFFFFFFFFu;
+    for (u32 j = lb + 1; j <= rb; j++) { const u32 l = a.lcp[j]; if (l < inner) inner = l; }
+    if ((long long)inner <= outer) return;
+    u64 seen = 0;
+    bool same = true;
+    unsigned c0 = 0;
+    const u32 q0 = LDG(a.v.set_seq0 + set_of_pos(a.v, lb));
+    for (u32 j = lb; j <= rb; j++) {
+        const u32 g = a.sa[j], k = seq_of(a.v, g);
+        seen |= 1ull << (k - q0);
+        const unsigned c = letter_before_suffix(a.v, g);
+        if (j == lb) c0 = c; else if (c != c0) same = false;
+    }
+    if (seen != (m == 64 ? ~0ull : (1ull << m) - 1ull)) return; // a sequence twice, another one missing
+    if (inner > 0 && same) return;                              // csamsa.c:80 (csamsa.c:85: depth 0 is left alone)
+    a.isblock[lb] = 1;
+    a.depth[lb] = inner;
+}
+MAP_KERNEL(blockfind2, BlockFind2Args, 12)
+#else
+// set of SA place i for the threads of one CTA: one search for the CTA's first place, then a step or two forward
+__device__ __forceinline__ u32 set_of_pos_cta(const BatchView &v, long long i, u32 *s_first) {
+    if (threadIdx.x == 0) *s_first = set_of_pos(v, (u32)((long long)blockIdx.x * blockDim.x));
+    __syncthreads();
+    u32 s = *s_first;
+    while (s + 1 < (u32)v.nsets && (u32)i >= LDG(v.set_base0 + s + 1)) s++;
+    return s;
+}
+__global__ void __launch_bounds__(256) k_blockfind2(long long n, BlockFind2Args a) {
+    __shared__ u32 s_first;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const u32 lb = (u32)i;
+    const u32 s = set_of_pos_cta(a.v, i < n ? i : n - 1, &s_first);
+    u32 m = 0, inner = 0;
+    bool cand = false;
+    if (i < n) {
+        // every lane screens its own window with the LCP array alone: borders first, then the smallest lcp inside
+        const u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
+        m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
+        if (m >= 2 && lb + m <= s1) {
+            const u32 rb = lb + m - 1;
+            const long long outer_l = (lb == s0) ? -1 : (long long)a.lcp[lb];
+            const long long outer_r = (rb + 1 == s1) ? -1 : (long long)a.lcp[rb + 1];
+            if (outer_l < (long long)a.lcp[lb + 1] && outer_r < (long long)a.lcp[rb]) {
+                const long long outer = outer_l > outer_r ? outer_l : outer_r;
+                inner = 0xFFFFFFFFu;
+                for (u32 j = lb + 1; j <= rb && (long long)inner > outer; j++) { const u32 l = a.lcp[j]; inner = l < inner ? l : inner; }
+                cand = (long long)inner > outer;
+            }
+        }
+    }
+    u32 res = 0;
+    unsigned todo = __ballot_sync(0xffffffffu, cand);
+    while (todo) { // the LCP intervals of exactly m places: the whole warp looks up the m sequences and the letters before
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1;
+        const u32 clb = __shfl_sync(0xffffffffu, lb, src), cm = __shfl_sync(0xffffffffu, m, src);
+        const u32 cinner = __shfl_sync(0xffffffffu, inner, src), cs = __shfl_sync(0xffffffffu, s, src);
+        const u32 crb = clb + cm - 1, q0 = LDG(a.v.set_seq0 + cs);
+        u32 seen_lo = 0, seen_hi = 0, c0 = 0xFFu;
+        bool same = true;
+        for (u32 j = clb + lane; j <= crb; j += 32) {
+            // the suffix's sequence by a search in the set's own few sequence starts, the letter before it from the packed
+            // text: both sit in L1/L2, where the gathers seqof[g] and code[g-1] go to HBM for every suffix of a batch
+            const u32 g = a.sa[j];
+            u32 lo = q0, hi = q0 + cm;
+            while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (LDG(a.v.seq_off + mid) <= g) lo = mid; else hi = mid; }
+            const u32 col = lo - q0, off = LDG(a.v.seq_off + lo), nk = LDG(a.v.seq_off + lo + 1) - off;
+            if (col < 32u) seen_lo |= 1u << col; else seen_hi |= 1u << (col - 32u);
+            const u64 xp = LDG(a.v.dbl_off + lo) + (g - off) + nk - 1u; // (the doubled text holds s s s[0..64): the letter before place p is at p+n-1)
+            const unsigned c = (LDG(a.v.pm + (xp >> 5)) >> (xp & 31u) & 1u) ? 4u : (unsigned)(LDG(a.v.p2 + (xp >> 5)) >> (2u * (xp & 31u))) & 3u;
+            if (c0 == 0xFFu) c0 = c; else if (c != c0) same = false;
+        }
+        seen_lo = __reduce_or_sync(0xffffffffu, seen_lo);
+        seen_hi = __reduce_or_sync(0xffffffffu, seen_hi);
+        const unsigned have = __ballot_sync(0xffffffffu, c0 != 0xFFu);
+        const u32 first = __shfl_sync(0xffffffffu, c0, __ffs((int)have) - 1);
+        const bool all_same = __all_sync(0xffffffffu, same && (c0 == 0xFFu || c0 == first));
+        const bool ok = (u32)(__popc(seen_lo) + __popc(seen_hi)) == cm && !(cinner > 0 && all_same);
+        if ((int)lane == src) res = ok ? 1u : 0u;
+    }
+    if (i < n) {
+        a.isblock[lb] = res;
+        if (res) a.depth[lb] = inner;
+    }
+}
+static inline void launch_blockfind2(Exec &ex, long long n, BlockFind2Args a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_blockfind2", 12.0 * n);
+    k_blockfind2<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
+
 // a whole rotation of the shortest sequence occurs in every sequence: the reference walks off its
 // tree (undefined behaviour).  Maximal runs of lcp >= nmin that hold every sequence.
 struct DegenArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *set_flags; u32 batch_nmin; };
@@ -576,23 +702,61 @@ MAP_KERNEL(blockemit, BlockEmitArgs, 8)
 //   dfs(leaf) = sum over the nodes v on the path leaf..root of before(v),
 //   before(v) = leaves under the siblings of v whose first occurrence precedes v's.
 struct Seq0FlagArgs { BatchView v; const u32 *sa; u32 *flag; };
-HD void seq0flag_body(long long i, const Seq0FlagArgs &a) {
-    u32 k = seq_of(a.v, a.sa[i]);
-    a.flag[i] = (k == LDG(a.v.set_seq0 + LDG(a.v.seq_set + k))) ? 1u : 0u;
+HD void seq0flag_body(long long i, const Seq0FlagArgs &a) { // (a rotation of sequence 0 of its set: a range check, no gather)
+    const u32 s = set_of_pos(a.v, (u32)i), k0 = LDG(a.v.set_seq0 + s);
+    const u32 g = a.sa[i];
+    a.flag[i] = (g >= LDG(a.v.seq_off + k0) && g < LDG(a.v.seq_off + k0 + 1)) ? 1u : 0u;
 }
+#ifdef CSA_EMU
 MAP_KERNEL(seq0flag, Seq0FlagArgs, 12)
+#endif
 
 struct Seq0EmitArgs { BatchView v; const u32 *sa; const u32 *flag; const u32 *idx0; u32 *sa0; u32 *saidx0; u32 *leaf_set; };
 HD void seq0emit_body(long long i, const Seq0EmitArgs &a) {
     if (!a.flag[i]) return;
-    u32 t = a.idx0[i];
-    u32 g = a.sa[i];
-    u32 k = seq_of(a.v, g);
-    a.sa0[t] = g - LDG(a.v.seq_off + k);
+    const u32 t = a.idx0[i], s = set_of_pos(a.v, (u32)i);
+    a.sa0[t] = a.sa[i] - LDG(a.v.seq_off + LDG(a.v.set_seq0 + s)); // (sequence 0 of the set: no look-up of the suffix's sequence)
     a.saidx0[t] = (u32)i;
-    a.leaf_set[t] = LDG(a.v.seq_set + k);
+    a.leaf_set[t] = s;
 }
+#ifdef CSA_EMU
 MAP_KERNEL(seq0emit, Seq0EmitArgs, 8)
+#endif
+#ifndef CSA_EMU
+__global__ void __launch_bounds__(256) k_seq0flag(long long n, Seq0FlagArgs a) {
+    __shared__ u32 s_first;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 s = set_of_pos_cta(a.v, i < n ? i : n - 1, &s_first);
+    if (i >= n) return;
+    const u32 k0 = LDG(a.v.set_seq0 + s), g = a.sa[i];
+    a.flag[i] = (g >= LDG(a.v.seq_off + k0) && g < LDG(a.v.seq_off + k0 + 1)) ? 1u : 0u;
+}
+static inline void launch_seq0flag(Exec &ex, long long n, Seq0FlagArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_seq0flag", 8.0 * n);
+    k_seq0flag<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+__global__ void __launch_bounds__(256) k_seq0emit(long long n, Seq0EmitArgs a) {
+    __shared__ u32 s_first;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 s = set_of_pos_cta(a.v, i < n ? i : n - 1, &s_first);
+    if (i >= n || !a.flag[i]) return;
+    const u32 t = a.idx0[i];
+    a.sa0[t] = a.sa[i] - LDG(a.v.seq_off + LDG(a.v.set_seq0 + s));
+    a.saidx0[t] = (u32)i;
+    a.leaf_set[t] = s;
+}
+static inline void launch_seq0emit(Exec &ex, long long n, Seq0EmitArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_seq0emit", 8.0 * n);
+    k_seq0emit<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
+
 
 // The same three arrays without a pass over the whole suffix array: the stable radix pass by colour of stage 3
 // (k_colorkey) leaves the SA places of colour 0 -- sequence 0 of every set -- first, set by set and in SA order.

@@ -69,7 +69,8 @@ MAP_KERNEL(rarecollapse, RareCollapseArgs, 0)
 
 // ---- 2. collectNodes + removeSuffixNodes + removeNonUniqueNodes, the reference's way ----------------------
 struct RareBlocksArgs {
-    BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *set_flags; const u32 *set_neff; const u32 *seq_per;
+    BatchView v; const u32 *sa; const u32 *lcp; u32 *R; int have_R; // have_R == 0: the cover array was not built (k_blockfind2's path): made here for the set
+    u32 *set_flags; const u32 *set_neff; const u32 *seq_per;
     u32 *isa;                                    // [N] written here for the set's range
     Seq0Q q;                                     // sequence 0 of every set: which of two leaves the DFS meets first
     u32 *w[6];                                   // scratch, N entries each; a set uses its own range
@@ -119,6 +120,17 @@ HD void rareblocks_body(long long si, const RareBlocksArgs &a) {
     const u32 nmin = LDG(a.v.set_nmin + s);
     const u32 L = s1 - s0, H = (L + 1) / 2; // a set has at most L/2 collected nodes (each holds >= m >= 2 places)
     for (u32 i = s0; i < s1; i++) { a.isa[a.sa[i]] = i; a.isblock[i] = 0; }
+    if (!a.have_R) { // R[l] = smallest r such that [l, r] holds every sequence of the set (two pointers; counts in the depth slice, free until the end)
+        const u32 q0 = LDG(a.v.set_seq0 + s);
+        u32 *cnt = a.depth + s0;
+        for (u32 k = 0; k < m; k++) cnt[k] = 0;
+        u32 covered = 0, r = s0;
+        for (u32 l = s0; l < s1; l++) {
+            while (covered < m && r < end) { if (cnt[seq_of(a.v, a.sa[r]) - q0]++ == 0) covered++; r++; }
+            a.R[l] = (covered == m && l < end) ? r - 1 : s1;
+            if (l < end && --cnt[seq_of(a.v, a.sa[l]) - q0] == 0) covered--;
+        }
+    }
     // -- collectNodes (csamsa.c:64): the all-sequence LCP intervals without an all-sequence child
     u32 *st_lcp = a.w[0] + s0, *st_lb = a.w[1] + s0, *st_child = a.w[2] + s0; // stack: at most L deep
     u32 *c_lb = a.w[3] + s0, *c_rb = a.w[4] + s0, *c_depth = a.w[5] + s0;     // lower halves of their slices
