@@ -735,11 +735,22 @@ static int stage_seq0(csa_gpu_ctx *c, const BatchView &v) {
     for (DevMem *m : one) TRY(dev_alloc(*m, n1));
     if (c->use_cover) { // (the colour sort left the SA places of sequence 0 first)
         Seq0TakeArgs a{v, sa, P<u32>(c->saidx0), P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0take(ex, N0, a);
-    } else {            // flag the rotations of sequence 0 (a range check), number them, write them out
+    } else {            // the rotations of sequence 0 (a range check) picked out of the suffix array, in its order
+#ifdef CSA_EMU
         u32 *flag = P<u32>(c->t4), *idx = P<u32>(c->t1);
         { Seq0FlagArgs a{v, sa, flag}; launch_seq0flag(ex, c->N, a); }
         TRY((scan_u32<ScanSum, false>(ex, c->ps, flag, idx, c->N)));
         { Seq0EmitArgs a{v, sa, flag, idx, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0emit(ex, c->N, a); }
+#else
+        const long long nt = ((long long)c->N + CS_TILE - 1) / CS_TILE;
+        TRY(dev_alloc(c->ps.chain, sizeof(unsigned long long) * (size_t)(nt + 1)));
+        CUDA_TRY(cudaMemsetAsync(c->ps.chain.p, 0, sizeof(unsigned long long) * (size_t)(nt + 1), ex.stream));
+        Seq0CompactArgs a{v, sa, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set), (unsigned long long *)c->ps.chain.p};
+        PROF_BEGIN(ex, "k_seq0compact", 4.0 * c->N + 12.0 * N0);
+        k_seq0compact<<<(unsigned)nt, CS_THREADS, 0, ex.stream>>>((long long)c->N, a);
+        PROF_END(ex);
+        ex.launches++;
+#endif
     }
     { Lcp0Args a{lcp, P<u32>(c->saidx0), P<u32>(c->leaf_set), P<u32>(c->z0), P<u32>(c->lcp0)}; launch_lcp0(ex, N0, a); }
     c->q0.N0 = N0; c->q0.z0 = P<u32>(c->z0); c->q0.leaf_set = P<u32>(c->leaf_set); c->q0.saidx0 = P<u32>(c->saidx0);

@@ -707,9 +707,7 @@ HD void seq0flag_body(long long i, const Seq0FlagArgs &a) { // (a rotation of se
     const u32 g = a.sa[i];
     a.flag[i] = (g >= LDG(a.v.seq_off + k0) && g < LDG(a.v.seq_off + k0 + 1)) ? 1u : 0u;
 }
-#ifdef CSA_EMU
 MAP_KERNEL(seq0flag, Seq0FlagArgs, 12)
-#endif
 
 struct Seq0EmitArgs { BatchView v; const u32 *sa; const u32 *flag; const u32 *idx0; u32 *sa0; u32 *saidx0; u32 *leaf_set; };
 HD void seq0emit_body(long long i, const Seq0EmitArgs &a) {
@@ -719,41 +717,65 @@ HD void seq0emit_body(long long i, const Seq0EmitArgs &a) {
     a.saidx0[t] = (u32)i;
     a.leaf_set[t] = s;
 }
-#ifdef CSA_EMU
 MAP_KERNEL(seq0emit, Seq0EmitArgs, 8)
-#endif
 #ifndef CSA_EMU
-__global__ void __launch_bounds__(256) k_seq0flag(long long n, Seq0FlagArgs a) {
-    __shared__ u32 s_first;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 s = set_of_pos_cta(a.v, i < n ? i : n - 1, &s_first);
-    if (i >= n) return;
-    const u32 k0 = LDG(a.v.set_seq0 + s), g = a.sa[i];
-    a.flag[i] = (g >= LDG(a.v.seq_off + k0) && g < LDG(a.v.seq_off + k0 + 1)) ? 1u : 0u;
-}
-static inline void launch_seq0flag(Exec &ex, long long n, Seq0FlagArgs a) {
-    if (n <= 0) return;
-    PROF_BEGIN(ex, "k_seq0flag", 8.0 * n);
-    k_seq0flag<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
-    PROF_END(ex);
-    ex.launches++;
-}
-__global__ void __launch_bounds__(256) k_seq0emit(long long n, Seq0EmitArgs a) {
-    __shared__ u32 s_first;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 s = set_of_pos_cta(a.v, i < n ? i : n - 1, &s_first);
-    if (i >= n || !a.flag[i]) return;
-    const u32 t = a.idx0[i];
-    a.sa0[t] = a.sa[i] - LDG(a.v.seq_off + LDG(a.v.set_seq0 + s));
-    a.saidx0[t] = (u32)i;
-    a.leaf_set[t] = s;
-}
-static inline void launch_seq0emit(Exec &ex, long long n, Seq0EmitArgs a) {
-    if (n <= 0) return;
-    PROF_BEGIN(ex, "k_seq0emit", 8.0 * n);
-    k_seq0emit<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
-    PROF_END(ex);
-    ex.launches++;
+// the three kernels above in ONE pass over the suffix array (flag, running count by decoupled look-back as in k_scan_chain,
+// write-out): 4 B read per place instead of 28 B moved
+struct Seq0CompactArgs { BatchView v; const u32 *sa; u32 *sa0; u32 *saidx0; u32 *leaf_set; unsigned long long *state; };
+__global__ void __launch_bounds__(CS_THREADS) k_seq0compact(long long n, Seq0CompactArgs a) {
+    __shared__ u32 sm[33];
+    __shared__ u32 s_tile, s_prefix, s_set;
+    if (threadIdx.x == 0) s_tile = (u32)atomicAdd(a.state, 1ull); // state[0]: next tile number; state[1+t]: tile t
+    __syncthreads();
+    const u32 tile = s_tile;
+    volatile unsigned long long *st = a.state + 1;
+    const long long tile0 = (long long)tile * CS_TILE, base = tile0 + (long long)threadIdx.x * CS_ITEMS;
+    if (threadIdx.x == 0) s_set = set_of_pos(a.v, (u32)tile0);
+    __syncthreads();
+    u32 s = s_set;
+    u32 g[CS_ITEMS], sset[CS_ITEMS];
+    u32 cnt = 0, flags = 0;
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; j++) {
+        const long long i = base + j;
+        g[j] = 0; sset[j] = 0;
+        if (i < n) {
+            while (s + 1 < (u32)a.v.nsets && (u32)i >= LDG(a.v.set_base0 + s + 1)) s++;
+            const u32 k0 = LDG(a.v.set_seq0 + s), off = LDG(a.v.seq_off + k0);
+            const u32 x = a.sa[i];
+            if (x >= off && x < LDG(a.v.seq_off + k0 + 1)) { flags |= 1u << j; cnt++; g[j] = x - off; sset[j] = s; }
+        }
+    }
+    u32 total;
+    const u32 excl = block_scan_excl(cnt, total, ScanSum(), sm);
+    if (threadIdx.x == 0) {
+        st[tile] = ((unsigned long long)(tile == 0 ? 2u : 1u) << 32) | total;
+        if (tile == 0) s_prefix = 0;
+    }
+    if (tile > 0 && threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        u32 run = 0;
+        long long look = (long long)tile - 1;
+        for (;;) {
+            const long long t = look - lane;
+            unsigned long long w = (t >= 0) ? st[t] : (2ull << 32);
+            while (__any_sync(0xffffffffu, (w >> 32) == 0)) w = (t >= 0) ? st[t] : (2ull << 32);
+            const unsigned incl = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+            const int stop = incl ? (__ffs((int)incl) - 1) : 32;
+            u32 part = ((int)lane <= stop) ? (u32)w : 0u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            run += part;
+            if (incl) break;
+            look -= 32;
+        }
+        if (lane == 0) { s_prefix = run; st[tile] = (2ull << 32) | (run + total); }
+    }
+    __syncthreads();
+    u32 t = s_prefix + excl;
+#pragma unroll
+    for (int j = 0; j < CS_ITEMS; j++)
+        if (flags >> j & 1u) { a.sa0[t] = g[j]; a.saidx0[t] = (u32)(base + j); a.leaf_set[t] = sset[j]; t++; }
 }
 #endif
 
