@@ -345,7 +345,7 @@ def main():
             traffic, traffic_src = None, None
             try:
                 tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
-                if tr:
+                if tr and abs(batch.nbases - tr["items"]) <= 0.02 * tr["items"]:  # measured at this launch size, not scaled across the L2 cliff
                     traffic, traffic_src = tr["dram_bytes_per_item"] * batch.nbases, tr["source"]
             except (OSError, ValueError, KeyError):
                 pass
