@@ -74,8 +74,8 @@ struct csa_gpu_ctx {
     DevMem blk_lb, blk_depth, blk_set, order, o_depth, o_set, o_pos, elem_blk, seghead, succ_lo, succ_hi;
     DevMem next, gap, size, total, interval, inv, f_depth, f_size, f_total, f_interval, f_next, f_pos, rotations;
     DevMem blk_leaf, blk_tab, f_leaf, f_set, let_off, let_out; // block order; csa_gpu_batch_block_letters
-    void *pinned = nullptr;
-    size_t pinned_bytes = 0;
+    void *pinned = nullptr, *meta_pinned = nullptr;
+    size_t pinned_bytes = 0, meta_bytes = 0;
     // per-kernel profile of the last run (csa_gpu_profile_*)
     Profiler prof;
     struct ProfSum { std::string name; long long launches; double ms, bytes; };
@@ -154,12 +154,29 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
     dev_free(c->ps.chain);
 #ifndef CSA_EMU
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->meta_pinned) cudaFreeHost(c->meta_pinned);
     if (c->tm.ok) for (int i = 0; i < 8; i++) cudaEventDestroy(c->tm.ev[i]);
     cudaStreamDestroy(c->own_stream);
 #else
     free(c->pinned);
+    free(c->meta_pinned);
 #endif
     delete c;
+}
+
+static int meta_reserve(csa_gpu_ctx *c, size_t bytes) { // page-locked staging of the batch's small tables
+    if (c->meta_bytes >= bytes) return 0;
+#ifndef CSA_EMU
+    if (c->meta_pinned) cudaFreeHost(c->meta_pinned);
+    c->meta_pinned = nullptr; c->meta_bytes = 0;
+    CUDA_TRY(cudaMallocHost(&c->meta_pinned, bytes));
+#else
+    free(c->meta_pinned);
+    c->meta_pinned = malloc(bytes);
+    if (!c->meta_pinned) CSA_FAIL(CSA_GPU_ENOMEM, "out of host memory");
+#endif
+    c->meta_bytes = bytes;
+    return 0;
 }
 
 static int pinned_reserve(csa_gpu_ctx *c, size_t bytes) {
@@ -250,15 +267,8 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     TRY(dev_alloc(c->set_nmin, sizeof(u32) * nsets)); TRY(dev_alloc(c->dbl_off, sizeof(u64) * (M + 1)));
     TRY(dev_alloc(c->z0, sizeof(u32) * (nsets + 1)));
     TRY(h2d(ex, c->raw.p, src, N));
-    TRY(h2d(ex, c->seq_off.p, c->h_seq_off.data(), sizeof(u32) * (M + 1)));
-    TRY(h2d(ex, c->seq_set.p, c->h_seq_set.data(), sizeof(u32) * M));
-    TRY(h2d(ex, c->set_seq0.p, c->h_set_seq0.data(), sizeof(u32) * (nsets + 1)));
-    TRY(h2d(ex, c->set_base0.p, c->h_set_base0.data(), sizeof(u32) * (nsets + 1)));
-    TRY(h2d(ex, c->set_nmin.p, c->h_set_nmin.data(), sizeof(u32) * nsets));
-    TRY(h2d(ex, c->dbl_off.p, c->h_dbl_off.data(), sizeof(u64) * (M + 1)));
-    TRY(h2d(ex, c->z0.p, c->h_z0.data(), sizeof(u32) * (nsets + 1)));
-    {   // tile-blocks of the first (segmented) sort: none straddles a set
-        std::vector<u32> bs, bc, bb, bt;
+    std::vector<u32> bs, bc, bb, bt; // tile-blocks of the first (segmented) sort: none straddles a set
+    {
         u32 cbase = 0;
         for (int s = 0; s < nsets; s++) {
             u32 s0 = c->h_set_base0[s], s1 = c->h_set_base0[s + 1];
@@ -275,9 +285,26 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
         size_t bytes = sizeof(u32) * bs.size();
         TRY(dev_alloc(c->rs_start, bytes)); TRY(dev_alloc(c->rs_count, bytes));
         TRY(dev_alloc(c->rs_cbase, bytes)); TRY(dev_alloc(c->rs_stride, bytes));
-        TRY(h2d(ex, c->rs_start.p, bs.data(), bytes)); TRY(h2d(ex, c->rs_count.p, bc.data(), bytes));
-        TRY(h2d(ex, c->rs_cbase.p, bb.data(), bytes)); TRY(h2d(ex, c->rs_stride.p, bt.data(), bytes));
-        TRY(exec_sync(ex));
+    }
+    {   // the small tables: laid out one behind the other in page-locked memory, so that their copies are queued behind the
+        // letters' copy without the host waiting for any of them (a copy from pageable memory returns only when it is staged)
+        struct Tab { DevMem *dst; const void *src; size_t bytes; };
+        const Tab tabs[] = {
+            {&c->seq_off, c->h_seq_off.data(), sizeof(u32) * (M + 1)}, {&c->seq_set, c->h_seq_set.data(), sizeof(u32) * M},
+            {&c->set_seq0, c->h_set_seq0.data(), sizeof(u32) * (nsets + 1)}, {&c->set_base0, c->h_set_base0.data(), sizeof(u32) * (nsets + 1)},
+            {&c->set_nmin, c->h_set_nmin.data(), sizeof(u32) * nsets}, {&c->dbl_off, c->h_dbl_off.data(), sizeof(u64) * (M + 1)},
+            {&c->z0, c->h_z0.data(), sizeof(u32) * (nsets + 1)},
+            {&c->rs_start, bs.data(), sizeof(u32) * bs.size()}, {&c->rs_count, bc.data(), sizeof(u32) * bc.size()},
+            {&c->rs_cbase, bb.data(), sizeof(u32) * bb.size()}, {&c->rs_stride, bt.data(), sizeof(u32) * bt.size()}};
+        size_t total = 0;
+        for (const Tab &t : tabs) total += (t.bytes + 15) & ~(size_t)15;
+        TRY(meta_reserve(c, total));
+        size_t at = 0;
+        for (const Tab &t : tabs) {
+            memcpy((char *)c->meta_pinned + at, t.src, t.bytes);
+            TRY(h2d(ex, t.dst->p, (char *)c->meta_pinned + at, t.bytes));
+            at += (t.bytes + 15) & ~(size_t)15;
+        }
     }
     TRY(exec_sync(ex)); // the host vectors and the staging buffer may change after we return
     c->uploaded = true;
@@ -453,15 +480,24 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     c->lcp_state = 0;
     c->ws_runs = 0;
     if (words) TRY(dev_fill_ff(ex, lcp, sizeof(u32) * (size_t)N));
-    TRY(heads_and_ranks(c, head, nullptr, counter, &ngroups, !any_other, true, words ? lcp : nullptr, letters, lbits));
+    // group borders, heads, and what decides between the word sort and the doubling rounds -- the number of groups, the
+    // largest one, the pairs they hold -- all queued, then ONE wait for the four numbers
+    unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs[2] = {0, 0};
+    TRY(dev_zero(ex, counter, 4 * sizeof(u32)));
+    TRY(dev_zero(ex, pairs, 2 * sizeof(*pairs)));
+    { FlagArgs a{P<u64>(c->keysA), !any_other ? P<u32>(c->keysA) : nullptr, head, counter, words ? lcp : nullptr, letters, lbits,
+                 P<u32>(c->valsA), P<u32>(c->seqof), P<u32>(c->seq_off), c->batch_nmin < (u32)letters ? 1 : 0, 0u}; launch_flag(ex, N, a); }
+    { SetStartArgs a{view_of(c), head, counter, words ? lcp : nullptr}; launch_setstart(ex, c->nsets, a); }
+    TRY((scan_u32<ScanMax, true>(ex, c->ps, head, head, N)));
+    { MaxGroupArgs a{head, counter + 2, N, pairs}; launch_maxgroup(ex, N, a); }
+    {
+        u32 hc[26];
+        TRY(d2h(ex, hc, counter, sizeof(hc))); // [0] groups, [2] largest group, [22..25] pairs, suffixes that share a group
+        ngroups = hc[0]; maxg = hc[2];
+        memcpy(hpairs, hc + 22, sizeof(hpairs));
+    }
     c->rounds_tiled = c->rounds_global = c->rounds_quad = c->rounds_list = 0;
     if (ngroups != N) {
-        unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs[2] = {0, 0};
-        TRY(dev_zero(ex, counter + 2, sizeof(u32)));
-        TRY(dev_zero(ex, pairs, 2 * sizeof(*pairs)));
-        { MaxGroupArgs a{head, counter + 2, N, pairs}; launch_maxgroup(ex, N, a); }
-        TRY(read_u32(c, counter + 2, &maxg));
-        TRY(d2h(ex, hpairs, pairs, sizeof(hpairs)));
         c->ws_pairs = (double)hpairs[0];
         c->ws_sharing = (double)hpairs[1];
         if (getenv("CSA_GPU_TRACE")) fprintf(stderr, "[csa] groups %u of %u suffixes, largest %u, pairs %.0f (%.2f per suffix), sharing %.0f\n", ngroups, N, maxg, c->ws_pairs, c->ws_pairs / N, c->ws_sharing);
@@ -646,18 +682,17 @@ static int stage_emit_blocks(csa_gpu_ctx *c, const BatchView &v) {
     u32 *sa = P<u32>(c->sa);
     u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3), *bidx = P<u32>(c->t4);
     TRY((scan_u32<ScanSum, false>(ex, c->ps, isblock, bidx, N)));
-    u32 last_idx = 0, last_flag = 0;
-    TRY(read_u32(c, bidx + (N - 1), &last_idx));
-    TRY(read_u32(c, isblock + (N - 1), &last_flag));
-    c->B = last_idx + last_flag;
+    { SetCountArgs a{v, isblock, bidx, P<u32>(c->set_nblocks)}; launch_setcount(ex, nsets, a); }
+    c->h_set_nblocks.assign(nsets, 0);
+    TRY(d2h(ex, c->h_set_nblocks.data(), c->set_nblocks.p, sizeof(u32) * nsets)); // (the one wait of this stage)
+    u64 btot = 0;
+    for (u32 x : c->h_set_nblocks) btot += x;
+    c->B = (u32)btot;
     u32 B = c->B;
     TRY(dev_alloc(c->blk_lb, sizeof(u32) * (size_t)B)); TRY(dev_alloc(c->blk_depth, sizeof(u32) * (size_t)B));
     TRY(dev_alloc(c->blk_set, sizeof(u32) * (size_t)B));
-    TRY(dev_zero(ex, c->set_nblocks.p, sizeof(u32) * nsets));
     { BlockEmitArgs a{v, sa, isblock, bidx, depth, P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set), P<u32>(c->set_nblocks)};
       launch_blockemit(ex, N, a); }
-    c->h_set_nblocks.assign(nsets, 0);
-    TRY(d2h(ex, c->h_set_nblocks.data(), c->set_nblocks.p, sizeof(u32) * nsets));
     c->h_set_blk0.assign(nsets + 1, 0); c->h_set_pos0.assign(nsets + 1, 0);
     u64 e = 0;
     u32 b = 0;

@@ -689,9 +689,15 @@ HD void blockemit_body(long long i, const BlockEmitArgs &a) {
     a.blk_lb[b] = (u32)i;
     a.blk_depth[b] = a.depth[i];
     a.blk_set[b] = s;
-    ATOMIC_ADD(a.set_nblocks + s, 1u);
 }
 MAP_KERNEL(blockemit, BlockEmitArgs, 8)
+// blocks per set, from the running count (one thread per set): the one number the host waits for before the emit
+struct SetCountArgs { BatchView v; const u32 *isblock; const u32 *bidx; u32 *set_nblocks; };
+HD void setcount_body(long long s, const SetCountArgs &a) {
+    const u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
+    a.set_nblocks[s] = s1 > s0 ? a.bidx[s1 - 1] + a.isblock[s1 - 1] - a.bidx[s0] : 0u;
+}
+MAP_KERNEL(setcount, SetCountArgs, 12)
 
 // ---- stage 4: order of the block list ----------------------------------------------------------------
 // insertSortedItem (nodeslinkedlists.c:36) keeps the list by depth, descending, and puts a block
