@@ -114,10 +114,22 @@ extern "C" int csa_gpu_create(int device, csa_gpu_ctx **out) {
     if (!c) CSA_FAIL(CSA_GPU_ENOMEM, "out of host memory");
     c->device = device;
 #ifndef CSA_EMU
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    c->ex.stream = c->own_stream;
-    for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreate(&c->tm.ev[i]));
-    c->tm.ok = true;
+    {   // (a failure half way must not leak the context, its stream or the events made so far)
+        cudaError_t err = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+        int made = 0;
+        if (err == cudaSuccess) {
+            c->ex.stream = c->own_stream;
+            for (; made < 8 && err == cudaSuccess; made++) err = cudaEventCreate(&c->tm.ev[made]);
+            if (err != cudaSuccess) made--;
+        }
+        if (err != cudaSuccess) {
+            for (int i = 0; i < made; i++) cudaEventDestroy(c->tm.ev[i]);
+            if (c->ex.stream) cudaStreamDestroy(c->own_stream);
+            delete c;
+            CSA_FAIL(err == cudaErrorMemoryAllocation ? CSA_GPU_ENOMEM : CSA_GPU_ECUDA, "csa_gpu_create: %s", cudaGetErrorString(err));
+        }
+        c->tm.ok = true;
+    }
 #endif
     *out = c;
     return CSA_GPU_OK;
