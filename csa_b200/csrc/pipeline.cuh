@@ -660,23 +660,6 @@ static inline void launch_blockfind2(Exec &ex, long long n, BlockFind2Args a) {
 }
 #endif
 
-// a whole rotation of the shortest sequence occurs in every sequence: the reference walks off its
-// tree (undefined behaviour).  Maximal runs of lcp >= nmin that hold every sequence.
-struct DegenArgs { BatchView v; const u32 *sa; const u32 *lcp; const u32 *R; u32 *set_flags; u32 batch_nmin; };
-HD void degen_body(long long i, const DegenArgs &a) {
-    u32 lb = (u32)i;
-    if (lb + 1 >= a.v.N || a.lcp[lb + 1] < a.batch_nmin) return; // (no set's shortest sequence is shorter: no search needed)
-    u32 s = set_of_pos(a.v, lb);
-    u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
-    u32 nmin = LDG(a.v.set_nmin + s);
-    if (lb + 1 >= s1 || a.lcp[lb + 1] < nmin) return;
-    if (lb != s0 && a.lcp[lb] >= nmin) return; // not the head of the run
-    u32 rb = lb + 1;
-    while (rb + 1 < s1 && a.lcp[rb + 1] >= nmin) rb++;
-    if (rb >= a.R[lb]) ATOMIC_OR(a.set_flags + s, 1u);
-}
-MAP_KERNEL(degen, DegenArgs, 12)
-
 // compaction of the block borders; blocks come out in SA order, i.e. grouped by set
 struct BlockEmitArgs {
     BatchView v; const u32 *sa; const u32 *isblock; const u32 *bidx; const u32 *depth;
@@ -798,13 +781,6 @@ HD void seq0take_body(long long t, const Seq0TakeArgs &a) {
     a.leaf_set[t] = LDG(a.v.seq_set + k);
 }
 MAP_KERNEL(seq0take, Seq0TakeArgs, 24)
-
-struct Seq0View {
-    u32 N0;
-    const u32 *z0;       // [nsets+1] first leaf of set s
-    const u32 *leaf_set; // [N0]
-    const u32 *lcp0;     // [N0] lcp of leaves t-1,t (undefined at the first leaf of a set)
-};
 
 struct Lcp0Args { const u32 *lcp; const u32 *saidx0; const u32 *leaf_set; const u32 *z0; u32 *lcp0; };
 HD void lcp0_body(long long t, const Lcp0Args &a) {
