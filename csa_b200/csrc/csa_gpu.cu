@@ -470,17 +470,17 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     } else if (phase != 2) {
     RsSeg seg{P<u32>(c->rs_start), P<u32>(c->rs_count), P<u32>(c->rs_cbase), P<u32>(c->rs_stride), c->rs_nblocks,
               P<u32>(c->set_base0), (u32)c->nsets};
-    { InitKeyArgs a{v, any_other ? P<u64>(c->keysA) : nullptr, any_other ? nullptr : P<u32>(c->keysA), P<u32>(c->valsA)};
+    { InitKeyArgs a{v, any_other ? P<u64>(c->keysA) : nullptr, any_other ? nullptr : P<u32>(c->keysA), nullptr};
       launch_initkey(ex, N, a); }
     if (any_other) {
         u64 *k = P<u64>(c->keysA), *ka = P<u64>(c->keysB);
         u32 *vv = P<u32>(c->valsA), *va = P<u32>(c->valsB);
-        TRY(radix_sort_pairs<u64>(ex, c->ps, k, vv, ka, va, N, 0, letters * lbits, &seg));
+        TRY(radix_sort_pairs<u64>(ex, c->ps, k, vv, ka, va, N, 0, letters * lbits, &seg, true));
         if (vv != P<u32>(c->valsA)) { std::swap(c->keysA, c->keysB); std::swap(c->valsA, c->valsB); }
     } else {
         u32 *k = P<u32>(c->keysA), *ka = P<u32>(c->keysB);
         u32 *vv = P<u32>(c->valsA), *va = P<u32>(c->valsB);
-        TRY(radix_sort_pairs<u32>(ex, c->ps, k, vv, ka, va, N, 0, letters * lbits, &seg));
+        TRY(radix_sort_pairs<u32>(ex, c->ps, k, vv, ka, va, N, 0, letters * lbits, &seg, true));
         if (vv != P<u32>(c->valsA)) { std::swap(c->keysA, c->keysB); std::swap(c->valsA, c->valsB); }
     }
     ngroups = 0;

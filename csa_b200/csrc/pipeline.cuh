@@ -159,6 +159,50 @@ HD void pack_body(long long w, const PackArgs &a) {
 }
 MAP_KERNEL(pack, PackArgs, 44)
 
+// ---- reading the packed, doubled text ------------------------------------------------------------
+HD u64 fetch2(const u64 *p2, u64 x) { // 32 bases starting at doubled base x
+    u64 j = x >> 5;
+    unsigned s = (unsigned)(x & 31) * 2;
+    u64 lo = LDG(p2 + j);
+    if (s == 0) return lo;
+    return (lo >> s) | (LDG(p2 + j + 1) << (64 - s));
+}
+HD u32 fetchm(const u32 *pm, u64 x) {
+    u64 j = x >> 5;
+    unsigned s = (unsigned)(x & 31);
+    u32 lo = LDG(pm + j);
+    if (s == 0) return lo;
+    return (lo >> s) | (LDG(pm + j + 1) << (32 - s));
+}
+HD int ctz64(u64 x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+HD int ctz32(u32 x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
+// 32 letters as a number that compares like the letters do: first letter in the top bits
+HD u64 lexkey2(u64 w) {
+#if defined(__CUDA_ARCH__)
+    u64 r = __brevll(w);
+#else
+    u64 r = w;
+    r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+    r = ((r >> 2) & 0x3333333333333333ull) | ((r & 0x3333333333333333ull) << 2);
+    r = ((r >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((r & 0x0F0F0F0F0F0F0F0Full) << 4);
+    r = __builtin_bswap64(r);
+#endif
+    return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1); // bit pairs back in order
+}
+
 // ---- stage 1: suffix array by prefix doubling --------------------------------------------------
 // The first sort key: the first letters of the rotation -- 13 letters of 3 bits in a u64, or, when the
 // batch holds nothing but A,C,G,T, 12 letters of 2 bits in a u32 (three radix passes of 8 B per element
@@ -169,13 +213,8 @@ HD void initkey_body(long long i, const InitKeyArgs &a) {
     u32 k = seq_of(a.v, g);
     u32 off = LDG(a.v.seq_off + k), n = LDG(a.v.seq_off + k + 1) - off;
     u32 p = g - off;
-    if (a.keys32) {
-        u32 key = 0;
-        for (int t = 0; t < 12; t++) {
-            key = (key << 2) | a.v.code[off + p];
-            if (++p == n) p = 0;
-        }
-        a.keys32[g] = key;
+    if (a.keys32) { // nothing but A,C,G,T in the batch: the 12 letters are the top 24 bits of one word of the packed text
+        a.keys32[g] = (u32)(lexkey2(fetch2(a.v.p2, LDG(a.v.dbl_off + k) + p)) >> 40);
     } else {
         u64 key = 0;
         for (int t = 0; t < CSA_K0; t++) {
@@ -184,7 +223,7 @@ HD void initkey_body(long long i, const InitKeyArgs &a) {
         }
         a.keys64[g] = key;
     }
-    a.vals[g] = g;
+    if (a.vals) a.vals[g] = g; // (the first pass of the first sort makes up the suffix numbers itself)
 }
 MAP_KERNEL(initkey, InitKeyArgs, 21)
 
@@ -265,34 +304,6 @@ MAP_KERNEL(key2, Key2Args, 24)
 
 // ---- stage 2: LCP of neighbouring suffixes, capped at the shorter rotation -------------------------
 // gencycsuffixtrees.c:500: a path of the tree ends after textsize letters.
-HD u64 fetch2(const u64 *p2, u64 x) { // 32 bases starting at doubled base x
-    u64 j = x >> 5;
-    unsigned s = (unsigned)(x & 31) * 2;
-    u64 lo = LDG(p2 + j);
-    if (s == 0) return lo;
-    return (lo >> s) | (LDG(p2 + j + 1) << (64 - s));
-}
-HD u32 fetchm(const u32 *pm, u64 x) {
-    u64 j = x >> 5;
-    unsigned s = (unsigned)(x & 31);
-    u32 lo = LDG(pm + j);
-    if (s == 0) return lo;
-    return (lo >> s) | (LDG(pm + j + 1) << (32 - s));
-}
-HD int ctz64(u64 x) {
-#if defined(__CUDA_ARCH__)
-    return __ffsll((long long)x) - 1;
-#else
-    return __builtin_ctzll(x);
-#endif
-}
-HD int ctz32(u32 x) {
-#if defined(__CUDA_ARCH__)
-    return __ffs((int)x) - 1;
-#else
-    return __builtin_ctz(x);
-#endif
-}
 
 // Text order (Kasai): if rotation p shares L letters with its SA predecessor, rotation p+1 shares at
 // least L-1 with its own, so a thread that walks LCP_CHUNK consecutive positions of a sequence
@@ -2561,19 +2572,6 @@ struct WSortArgs {
                // [4] unused, [5] entries of big
 };
 
-// 32 letters as a number that compares like the letters do: first letter in the top bits
-HD u64 lexkey2(u64 w) {
-#if defined(__CUDA_ARCH__)
-    u64 r = __brevll(w);
-#else
-    u64 r = w;
-    r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
-    r = ((r >> 2) & 0x3333333333333333ull) | ((r & 0x3333333333333333ull) << 2);
-    r = ((r >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((r & 0x0F0F0F0F0F0F0F0Full) << 4);
-    r = __builtin_bswap64(r);
-#endif
-    return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1); // bit pairs back in order
-}
 HD u32 lexmask(u32 w) {
 #if defined(__CUDA_ARCH__)
     return __brev(w);

@@ -47,7 +47,8 @@ static int scan_u32(Exec &, PrimScratch &, const u32 *in, u32 *out, long long n,
 
 template <class K>
 static int radix_sort_pairs(Exec &, PrimScratch &, K *&keys, u32 *&vals, K *&keys_alt, u32 *&vals_alt,
-                            long long n, int begin_bit, int end_bit, const RsSeg *seg = nullptr) {
+                            long long n, int begin_bit, int end_bit, const RsSeg *seg = nullptr, bool iota_vals = false) {
+    if (iota_vals) for (long long i = 0; i < n; i++) vals[i] = (u32)i; // (the values are the places themselves)
     if (n <= 1 || end_bit <= begin_bit) return 0;
     const int kb = (int)sizeof(K) * 8;
     K mask = (end_bit - begin_bit >= kb) ? (K)~(K)0 : (K)((((K)1 << (end_bit - begin_bit)) - 1) << begin_bit);
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_scatter(const K *__restric
         long long i = base + j * 32;
         bool ok = i < end;
         k[j] = ok ? keys[i] : (K)0;
-        v[j] = ok ? vals[i] : 0;
+        v[j] = ok ? (vals ? vals[i] : (u32)i) : 0; // (vals == nullptr: the values are the places themselves, first pass of a sort)
         dig[j] = ok ? ((unsigned)(k[j] >> shift) & (RS_BINS - 1)) : RS_BINS; // RS_BINS = "no key"
     }
 #pragma unroll
@@ -383,8 +384,11 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_scatter(const K *__restric
 // keys/vals and the _alt buffers are swapped as passes go; on return keys/vals point at the sorted data.
 template <class K>
 static int radix_sort_pairs(Exec &ex, PrimScratch &ps, K *&keys, u32 *&vals, K *&keys_alt, u32 *&vals_alt,
-                            long long n, int begin_bit, int end_bit, const RsSeg *segp = nullptr) {
-    if (n <= 1 || end_bit <= begin_bit) return 0;
+                            long long n, int begin_bit, int end_bit, const RsSeg *segp = nullptr, bool iota_vals = false) {
+    if (n <= 1 || end_bit <= begin_bit) {
+        if (iota_vals) CSA_FAIL(-2, "radix sort: nothing to sort, values not made");
+        return 0;
+    }
     if (n >= (1ll << 32)) CSA_FAIL(-2, "radix sort: more than 2^32 elements");
     RsSeg seg;
     if (segp) seg = *segp;
@@ -401,8 +405,9 @@ static int radix_sort_pairs(Exec &ex, PrimScratch &ps, K *&keys, u32 *&vals, K *
         ex.launches++;
         rc = scan_u32<ScanSum, false>(ex, ps, counts, counts, (long long)RS_BINS * nb);
         if (rc) return rc;
-        PROF_BEGIN(ex, "k_rs_scatter", 2.0 * (kbytes + 4.0) * n);
-        k_rs_scatter<K><<<nb, RS_THREADS, 0, ex.stream>>>(keys, vals, keys_alt, vals_alt, counts, n, shift, seg);
+        const bool iota = iota_vals && shift == begin_bit;
+        PROF_BEGIN(ex, "k_rs_scatter", (2.0 * (kbytes + 4.0) - (iota ? 4.0 : 0.0)) * n);
+        k_rs_scatter<K><<<nb, RS_THREADS, 0, ex.stream>>>(keys, iota ? nullptr : vals, keys_alt, vals_alt, counts, n, shift, seg);
         PROF_END(ex);
         ex.launches++;
         K *tk = keys; keys = keys_alt; keys_alt = tk;
