@@ -318,10 +318,15 @@ def main():
                 assert np.array_equal(rot, last[i])
         for c2 in ctxs[1:]:
             c2.close()
-        if buckets:  # the bucket-sharded run against the same set on this GPU alone
+        if buckets:  # the bucket-sharded run against the same set on this GPU alone: rotations and the whole block list
+            rf.upload(batch); rf_run()
+            sharded_blocks = rf.blocks()
             rf.upload(batch); rf.run()
             rot3, _ = rf.download()
             assert np.array_equal(rot, rot3), "bucket-sharded rotations differ from the single-GPU run"
+            alone = rf.blocks()
+            assert all(np.array_equal(x, y) for x, y in zip(sharded_blocks[0], alone[0])) and np.array_equal(sharded_blocks[1], alone[1]), \
+                "bucket-sharded blocks differ from the single-GPU run"
         h2d = batch.nbases + 4 * (2 * batch.nseqs + 4 * batch.nsets + 8) + 8 * (batch.nseqs + 1)
         d2h = 4 * batch.nseqs + 3 * 4 * batch.nsets
         e2e_value = total_bases / (e2e_ms / 1e3)
@@ -360,7 +365,8 @@ def main():
 
         res = {"value": value, "ms_per_step": dev_ms / steps, "e2e_value": e2e_value, "e2e_ms_per_step": e2e_ms / steps, "h2d": h2d, "d2h": d2h,
                "nctx": nctx, "launches": launches, "clk": clk, "roofline": roofline, "kernels": kernels, "ok_sets": ok_sets,
-               "stage_ms": [round(x / steps, 3) for x in stage_ms], "buckets": buckets, "batch": batch, "steps": steps}
+               "stage_ms": [round(x / steps, 3) for x in stage_ms], "buckets": buckets, "batch": batch, "steps": steps,
+               "shard_path": (sys.modules["csa_b200.shard"].last_path if buckets else None)}
         rf.close()
         return res
 
@@ -384,8 +390,8 @@ def main():
                             "gpu_launches": r["launches"], "stage_ms_per_step": r["stage_ms"],
                             "dominant_kernel": {k2: top.get(k2) for k2 in ("kernel", "frac", "achieved", "share_of_step", "avg_launch_ms")},
                             "kernels": r["kernels"][:6],
-                            "parallelism": (f"one set, suffix-array buckets sharded over {world} GPUs (csa_gpu_shard_*), rotations checked against "
-                                            f"the one-GPU run") if r["buckets"] else f"sets sharded over {world} GPU(s), no collective"}
+                            "parallelism": (f"one set, suffix-array buckets sharded over {world} GPUs (csa_gpu_shard_*; path taken after the bucket "
+                                            f"sort: {r['shard_path']}), rotations and blocks checked against the one-GPU run") if r["buckets"] else f"sets sharded over {world} GPU(s), no collective"}
             del r
 
     # ---- what ONE call of the drop-in costs: csa_gpu_find_rotations on one Mammals-shaped set, host buffers in, rotations out ----
@@ -423,8 +429,8 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": {"workload": what, "sets_per_gpu_per_step": nsets, "bases_per_gpu_per_step": batch.nbases,
                            "sequences_per_set": int(batch.set_start[1]),
-                           "parallelism": (f"one set, suffix-array buckets sharded over {world} GPUs: first sort on every rank, bucket sort + LCP "
-                                           f"per rank, buckets broadcast over NCCL, the rest on every rank") if buckets
+                           "parallelism": (f"one set, suffix-array buckets sharded over {world} GPUs (csa_gpu_shard_*; path taken after the bucket "
+                                           f"sort: {head['shard_path']}), rotations and blocks checked against the one-GPU run") if buckets
                                           else f"sets sharded over {world} GPU(s), no collective",
                            "l2": "per-step working set (~55 B/base) far above the 126 MB L2; no flush needed",
                            "sets_ok": head["ok_sets"], "stage_ms_per_step": head["stage_ms"],

@@ -91,6 +91,9 @@ def _load(path):
     lib.csa_gpu_shard_begin.argtypes = [vp, i, i]
     lib.csa_gpu_shard_view.argtypes = [vp, C.POINTER(ShardInfo)]
     lib.csa_gpu_shard_finish.argtypes = [vp, i, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+    lib.csa_gpu_shard_blocks_begin.argtypes = [vp, C.c_uint, C.c_void_p]
+    lib.csa_gpu_shard_blocks_buffers.argtypes = [vp, C.c_uint, C.c_uint, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.csa_gpu_shard_blocks_finish.argtypes = [vp, i, C.c_uint, C.c_uint, C.c_uint]
     lib.csa_gpu_profile_enable.argtypes = [vp, i]
     lib.csa_gpu_profile_count.argtypes = [vp]
     lib.csa_gpu_profile_get.argtypes = [vp, i, C.c_char_p, i, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
@@ -102,7 +105,14 @@ class ShardInfo(C.Structure):
     """csa_gpu_shard_info (include/csa_gpu.h)"""
     _fields_ = [("sa", C.c_void_p), ("head", C.c_void_p), ("lcp", C.c_void_p), ("left", C.c_void_p),
                 ("n", C.c_ulonglong), ("bounds", C.POINTER(C.c_uint)),
-                ("nleft", C.c_uint), ("left_suffixes", C.c_uint), ("min_depth", C.c_uint), ("max_group", C.c_uint)]
+                ("nleft", C.c_uint), ("left_suffixes", C.c_uint), ("min_depth", C.c_uint), ("max_group", C.c_uint),
+                ("own_sort", C.c_uint)]
+
+
+class ShardBlocks(C.Structure):
+    """csa_gpu_shard_blocks (include/csa_gpu.h)"""
+    _fields_ = [("blkrec", C.c_void_p), ("nblk", C.c_uint), ("m", C.c_uint), ("sa0", C.c_void_p), ("saidx0", C.c_void_p),
+                ("lcp0", C.c_void_p), ("n0", C.c_uint), ("head_min", C.c_uint), ("tail_min", C.c_uint), ("rare", C.c_uint)]
 
 
 def _ip(a):
@@ -194,6 +204,19 @@ class RotationFinder:
 
     def shard_finish(self, max_interval: int, flags: int, nleft: int, left_suffixes: int, min_depth: int, max_group: int):
         self._check(self.lib.csa_gpu_shard_finish(self.ctx, max_interval, flags, nleft, left_suffixes, min_depth, max_group))
+
+    def shard_blocks_begin(self, flags: int = 0) -> "ShardBlocks":
+        b = ShardBlocks()
+        self._check(self.lib.csa_gpu_shard_blocks_begin(self.ctx, flags, C.byref(b)))
+        return b
+
+    def shard_blocks_buffers(self, total_blocks: int, total_n0: int):
+        p = [C.c_void_p() for _ in range(4)]
+        self._check(self.lib.csa_gpu_shard_blocks_buffers(self.ctx, total_blocks, total_n0, *[C.byref(x) for x in p]))
+        return [x.value for x in p]
+
+    def shard_blocks_finish(self, max_interval: int, flags: int, total_blocks: int, total_n0: int):
+        self._check(self.lib.csa_gpu_shard_blocks_finish(self.ctx, max_interval, flags, total_blocks, total_n0))
 
     def download(self):
         b = self._batch

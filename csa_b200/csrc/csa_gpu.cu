@@ -74,6 +74,8 @@ struct csa_gpu_ctx {
     DevMem blk_lb, blk_depth, blk_set, order, o_depth, o_set, o_pos, elem_blk, seghead, succ_lo, succ_hi;
     DevMem next, gap, size, total, interval, inv, f_depth, f_size, f_total, f_interval, f_next, f_pos, rotations;
     DevMem blk_leaf, blk_tab, f_leaf, f_set, let_off, let_out; // block order; csa_gpu_batch_block_letters
+    DevMem sh_rec, sh_sa0, sh_saidx0, sh_lcp0, sh_allrec;      // csa_gpu_shard_blocks_*: this range's records, everybody's records
+    bool shard_sa_swapped = false;
     void *pinned = nullptr, *meta_pinned = nullptr;
     size_t pinned_bytes = 0, meta_bytes = 0;
     // per-kernel profile of the last run (csa_gpu_profile_*)
@@ -159,7 +161,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->set_neff, &c->seq_per, &c->rare_collected, &c->rare_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
                      &c->succ_lo, &c->succ_hi, &c->next, &c->gap, &c->size, &c->total, &c->interval, &c->inv, &c->f_depth,
-                     &c->f_size, &c->f_total, &c->f_interval, &c->f_next, &c->f_pos, &c->rotations, &c->blk_leaf, &c->blk_tab, &c->f_leaf, &c->f_set, &c->let_off, &c->let_out};
+                     &c->f_size, &c->f_total, &c->f_interval, &c->f_next, &c->f_pos, &c->rotations, &c->sh_rec, &c->sh_sa0, &c->sh_saidx0, &c->sh_lcp0, &c->sh_allrec, &c->blk_leaf, &c->blk_tab, &c->f_leaf, &c->f_set, &c->let_off, &c->let_out};
     for (DevMem *m : all) dev_free(*m);
     for (int i = 0; i < 4; i++) dev_free(c->ps.block_sums[i]);
     dev_free(c->ps.counts);
@@ -671,7 +673,7 @@ static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     u32 *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3);
     TRY(dev_alloc(c->saidx0, sizeof(u32) * (size_t)c->N0));
     if (!c->use_cover) {
-        { BlockFind2Args a{v, sa, lcp, isblock, depth, c->mmax}; launch_blockfind2(ex, N, a); }
+        { BlockFind2Args a{v, sa, lcp, isblock, depth, c->mmax, 0u}; launch_blockfind2(ex, N, a); }
         return 0;
     }
     TRY(dev_zero(ex, c->firstmax.p, sizeof(u32) * nsets));
@@ -785,14 +787,14 @@ static int stage_seq0(csa_gpu_ctx *c, const BatchView &v) {
     } else {            // the rotations of sequence 0 (a range check) picked out of the suffix array, in its order
 #ifdef CSA_EMU
         u32 *flag = P<u32>(c->t4), *idx = P<u32>(c->t1);
-        { Seq0FlagArgs a{v, sa, flag}; launch_seq0flag(ex, c->N, a); }
+        { Seq0FlagArgs a{v, sa, flag, 0u}; launch_seq0flag(ex, c->N, a); }
         TRY((scan_u32<ScanSum, false>(ex, c->ps, flag, idx, c->N)));
-        { Seq0EmitArgs a{v, sa, flag, idx, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set)}; launch_seq0emit(ex, c->N, a); }
+        { Seq0EmitArgs a{v, sa, flag, idx, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set), 0u, nullptr, c->N}; launch_seq0emit(ex, c->N, a); }
 #else
         const long long nt = ((long long)c->N + CS_TILE - 1) / CS_TILE;
         TRY(dev_alloc(c->ps.chain, sizeof(unsigned long long) * (size_t)(nt + 1)));
         CUDA_TRY(cudaMemsetAsync(c->ps.chain.p, 0, sizeof(unsigned long long) * (size_t)(nt + 1), ex.stream));
-        Seq0CompactArgs a{v, sa, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set), (unsigned long long *)c->ps.chain.p};
+        Seq0CompactArgs a{v, sa, P<u32>(c->sa0), P<u32>(c->saidx0), P<u32>(c->leaf_set), (unsigned long long *)c->ps.chain.p, 0u, nullptr};
         PROF_BEGIN(ex, "k_seq0compact", 4.0 * c->N + 12.0 * N0);
         k_seq0compact<<<(unsigned)nt, CS_THREADS, 0, ex.stream>>>((long long)c->N, a);
         PROF_END(ex);
@@ -977,7 +979,7 @@ static int run_phases(csa_gpu_ctx *c, int max_interval, unsigned flags, int phas
     mark(c, 2);
     TRY(dev_zero(ex, c->set_flags.p, sizeof(u32) * nsets));
     // sets whose tree is not their suffix array (rare.cuh): marked here, redone by one thread each further down
-    { LeafScanArgs a{v, P<u32>(c->t5), P<u32>(c->set_flags), c->batch_nmin}; launch_leafscan(ex, N, a); }
+    { LeafScanArgs a{v, P<u32>(c->t5), P<u32>(c->set_flags), c->batch_nmin, 0u}; launch_leafscan(ex, N, a); }
     { RareCollapseArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->set_flags), P<u32>(c->t2), P<u32>(c->set_neff), P<u32>(c->seq_per)};
       launch_rarecollapse(ex, nsets, a); }
     c->use_cover = (flags & CSA_GPU_FLAG_STATS) || c->mmax > 64 || c->force_cover;
@@ -1036,7 +1038,7 @@ extern "C" int csa_gpu_batch_run(csa_gpu_ctx *c, int max_interval, unsigned flag
 extern "C" int csa_gpu_shard_begin(csa_gpu_ctx *c, int rank, int nranks) {
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
     if (nranks < 1 || rank < 0 || rank >= nranks) CSA_FAIL(CSA_GPU_EINVAL, "bad rank %d of %d", rank, nranks);
-    c->shard_rank = rank; c->shard_nranks = nranks;
+    c->shard_rank = rank; c->shard_nranks = nranks; c->shard_sa_swapped = false;
     return run_phases(c, 0, 0, 1);
 }
 
@@ -1047,6 +1049,7 @@ extern "C" int csa_gpu_shard_view(csa_gpu_ctx *c, csa_gpu_shard_info *out) {
     out->n = c->N;
     out->bounds = c->h_shard_bounds.data();
     out->nleft = c->ws_left[0]; out->left_suffixes = c->ws_left[1]; out->min_depth = c->ws_left[2]; out->max_group = c->ws_left[3];
+    out->own_sort = c->shard_own_sort ? 1u : 0u;
     return CSA_GPU_OK;
 }
 
@@ -1055,7 +1058,159 @@ extern "C" int csa_gpu_shard_finish(csa_gpu_ctx *c, int max_interval, unsigned f
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
     if (c->shard_phase != 1) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_shard_finish before csa_gpu_shard_begin");
     c->ws_left[0] = nleft; c->ws_left[1] = left_suffixes; c->ws_left[2] = min_depth; c->ws_left[3] = max_group;
+    if (c->shard_sa_swapped) { std::swap(c->sa, c->valsA); c->shard_sa_swapped = false; } // (csa_gpu_shard_blocks_begin ran, then the caller fell back)
     return run_phases(c, max_interval, flags, 2);
+}
+
+// ---- ... and the block stages of a rank's own range (see include/csa_gpu.h) -------------------------------------------------
+extern "C" int csa_gpu_shard_blocks_begin(csa_gpu_ctx *c, unsigned flags, csa_gpu_shard_blocks *out) {
+    if (!c || !out) CSA_FAIL(CSA_GPU_EINVAL, "null argument");
+    if (c->shard_phase != 1) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_shard_blocks_begin before csa_gpu_shard_begin");
+    if (!c->shard_own_sort || c->nsets != 1 || c->mmax > 64 || (flags & CSA_GPU_FLAG_STATS) || c->ws_left[0])
+        CSA_FAIL(CSA_GPU_ESTATE, "the block stages shard for ONE set of up to 64 sequences whose buckets were sorted by their ranks, "
+                                 "without the counts of csamsa.c:332,338: take csa_gpu_shard_finish (own sort %d, sets %d, "
+                                 "sequences %d, flags %u, groups left %u)", (int)c->shard_own_sort, c->nsets, c->mmax, flags, c->ws_left[0]);
+#ifndef CSA_EMU
+    CUDA_TRY(cudaSetDevice(c->device));
+#endif
+    Exec &ex = c->ex;
+    BatchView v = view_of(c);
+    const u32 N = c->N, m = c->mmax, lo = c->h_shard_bounds[c->shard_rank], hi = c->h_shard_bounds[c->shard_rank + 1], n = hi - lo;
+    memset(out, 0, sizeof(*out));
+    out->m = m; out->head_min = out->tail_min = 0xFFFFFFFFu;
+    if (!c->shard_sa_swapped) { std::swap(c->sa, c->valsA); c->shard_sa_swapped = true; } // (as the end of the suffix-array stage does)
+    u32 *sa = P<u32>(c->sa), *lcp = P<u32>(c->t5), *isblock = P<u32>(c->t0), *depth = P<u32>(c->t3), *bidx = P<u32>(c->t4);
+    u32 *any_other = P<u32>(c->counter) + 8, *cnt = P<u32>(c->counter) + 14;
+    if (n == 0) return CSA_GPU_OK;
+    // the LCPs at the two borders of the range: no rank has seen both keys
+    if (lo > 0) { LcpAtArgs a{{v, sa, lcp, any_other, 1, nullptr}, lo}; launch_lcpat(ex, 1, a); }
+    if (hi < N) { LcpAtArgs a{{v, sa, lcp, any_other, 1, nullptr}, hi}; launch_lcpat(ex, 1, a); }
+    TRY(dev_zero(ex, c->set_flags.p, sizeof(u32) * c->nsets));
+    { LeafScanArgs a{v, lcp, P<u32>(c->set_flags), c->batch_nmin, lo}; launch_leafscan(ex, n, a); }
+    { BlockFind2Args a{v, sa, lcp, isblock, depth, m, lo}; launch_blockfind2(ex, n, a); }
+    TRY((scan_u32<ScanSum, false>(ex, c->ps, isblock + lo, bidx + lo, n)));
+    // the rotations of sequence 0 in the range, in suffix-array order
+    const u32 cap0 = std::min(n, c->N0);
+    TRY(dev_alloc(c->sh_sa0, sizeof(u32) * (size_t)cap0)); TRY(dev_alloc(c->sh_saidx0, sizeof(u32) * (size_t)cap0));
+    TRY(dev_alloc(c->sh_lcp0, sizeof(u32) * (size_t)cap0));
+    u32 *loc_set = P<u32>(c->t1); // (leaf_set of the range's rotations: all of set 0; scratch)
+    TRY(dev_zero(ex, cnt, 4 * sizeof(u32)));
+#ifdef CSA_EMU
+    {
+        u32 *flag = P<u32>(c->keysA), *idx = P<u32>(c->keysA) + N;
+        { Seq0FlagArgs a{v, sa, flag, lo}; launch_seq0flag(ex, n, a); }
+        TRY((scan_u32<ScanSum, false>(ex, c->ps, flag, idx, n)));
+        { Seq0EmitArgs a{v, sa, flag, idx, P<u32>(c->sh_sa0), P<u32>(c->sh_saidx0), loc_set, lo, cnt, n}; launch_seq0emit(ex, n, a); }
+    }
+#else
+    {
+        const long long nt = ((long long)n + CS_TILE - 1) / CS_TILE;
+        TRY(dev_alloc(c->ps.chain, sizeof(unsigned long long) * (size_t)(nt + 1)));
+        CUDA_TRY(cudaMemsetAsync(c->ps.chain.p, 0, sizeof(unsigned long long) * (size_t)(nt + 1), ex.stream));
+        Seq0CompactArgs a{v, sa, P<u32>(c->sh_sa0), P<u32>(c->sh_saidx0), loc_set, (unsigned long long *)c->ps.chain.p, lo, cnt};
+        PROF_BEGIN(ex, "k_seq0compact", 4.0 * n);
+        k_seq0compact<<<(unsigned)nt, CS_THREADS, 0, ex.stream>>>((long long)n, a);
+        PROF_END(ex);
+        ex.launches++;
+    }
+#endif
+    u32 hv[4] = {0, 0, 0, 0}; // [0] rotations of sequence 0, [1] running count at the last place, [2] is the last place a block, [3] flags
+    TRY(d2d(ex, cnt + 1, bidx + (hi - 1), sizeof(u32))); TRY(d2d(ex, cnt + 2, isblock + (hi - 1), sizeof(u32)));
+    TRY(d2d(ex, cnt + 3, c->set_flags.p, sizeof(u32)));
+    TRY(d2h(ex, hv, cnt, sizeof(hv)));
+    const u32 n0 = hv[0], nblk = hv[1] + hv[2];
+    out->n0 = n0; out->nblk = nblk; out->rare = (hv[3] & CSA_FLAG_RARE) ? 1u : 0u;
+    TRY(dev_alloc(c->sh_rec, sizeof(u32) * (size_t)std::max(nblk, 1u) * (2 + m)));
+    { BlkRecArgs a{sa, isblock, bidx + 0, depth, lo, m, P<u32>(c->sh_rec)}; launch_blkrecpack(ex, n, a); }
+    // their LCPs; what the first one lacks (the places before the range) and what lies behind the last one: two minima
+    u32 *mins = P<u32>(c->counter) + 18;
+    TRY(dev_fill_ff(ex, mins, 2 * sizeof(u32)));
+    if (n0) {
+        u32 ends[2] = {0, 0};
+        TRY(d2h(ex, ends, c->sh_saidx0.p, sizeof(u32)));
+        TRY(d2h(ex, ends + 1, P<u32>(c->sh_saidx0) + (n0 - 1), sizeof(u32)));
+        std::vector<u32> zz = {0u, n0};
+        TRY(h2d(ex, P<u32>(c->counter) + 30, zz.data(), 2 * sizeof(u32))); // (one "set" of n0 leaves for k_lcp0)
+        TRY(exec_sync(ex));
+        { Lcp0Args a{lcp, P<u32>(c->sh_saidx0), loc_set, P<u32>(c->counter) + 30, P<u32>(c->sh_lcp0)}; launch_lcp0(ex, n0, a); }
+        { RangeMinArgs a{lcp, lo, mins}; launch_rangemin(ex, (long long)ends[0] - lo + 1, a); }
+        if (ends[1] + 1 < hi) { RangeMinArgs a{lcp, ends[1] + 1, mins + 1}; launch_rangemin(ex, (long long)hi - ends[1] - 1, a); }
+    } else {
+        RangeMinArgs a{lcp, lo, mins}; launch_rangemin(ex, n, a);
+    }
+    u32 hm[2];
+    TRY(d2h(ex, hm, mins, sizeof(hm)));
+    out->head_min = hm[0]; out->tail_min = hm[1];
+    out->blkrec = c->sh_rec.p; out->sa0 = c->sh_sa0.p; out->saidx0 = c->sh_saidx0.p; out->lcp0 = c->sh_lcp0.p;
+    return CSA_GPU_OK;
+}
+
+extern "C" int csa_gpu_shard_blocks_buffers(csa_gpu_ctx *c, unsigned total_blocks, unsigned total_n0, void **blkrec, void **sa0,
+                                            void **saidx0, void **lcp0) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (c->shard_phase != 1) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_shard_blocks_buffers before csa_gpu_shard_begin");
+    if (total_n0 != c->N0) CSA_FAIL(CSA_GPU_EINVAL, "the ranks hold %u rotations of sequence 0, the set has %u", total_n0, c->N0);
+#ifndef CSA_EMU
+    CUDA_TRY(cudaSetDevice(c->device));
+#endif
+    TRY(dev_alloc(c->sh_allrec, sizeof(u32) * (size_t)std::max(total_blocks, 1u) * (2 + c->mmax)));
+    size_t n1 = sizeof(u32) * (size_t)c->N0;
+    DevMem *one[] = {&c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0};
+    for (DevMem *m : one) TRY(dev_alloc(*m, n1));
+    if (blkrec) *blkrec = c->sh_allrec.p;
+    if (sa0) *sa0 = c->sa0.p;
+    if (saidx0) *saidx0 = c->saidx0.p;
+    if (lcp0) *lcp0 = c->lcp0.p;
+    return CSA_GPU_OK;
+}
+
+extern "C" int csa_gpu_shard_blocks_finish(csa_gpu_ctx *c, int max_interval, unsigned flags, unsigned total_blocks, unsigned total_n0) {
+    if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
+    if (c->shard_phase != 1 || !c->shard_sa_swapped) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_shard_blocks_finish before csa_gpu_shard_blocks_begin");
+    if (total_n0 != c->N0 || (flags & CSA_GPU_FLAG_STATS)) CSA_FAIL(CSA_GPU_EINVAL, "bad argument");
+#ifndef CSA_EMU
+    CUDA_TRY(cudaSetDevice(c->device));
+#endif
+    Exec &ex = c->ex;
+    BatchView v = view_of(c);
+    const u32 B = total_blocks, m = c->mmax;
+    mark(c, 1); mark(c, 2);
+    c->B = B; c->E = B * m;
+    c->use_cover = false; c->have_stats = false;
+    TRY(dev_alloc(c->blk_lb, sizeof(u32) * (size_t)B)); TRY(dev_alloc(c->blk_depth, sizeof(u32) * (size_t)B));
+    TRY(dev_alloc(c->blk_set, sizeof(u32) * (size_t)B));
+    { BlkUnpackArgs a{P<u32>(c->sh_allrec), m, P<u32>(c->sa), P<u32>(c->blk_lb), P<u32>(c->blk_depth), P<u32>(c->blk_set)};
+      launch_blkrecunpack(ex, B, a); }
+    c->h_set_nblocks.assign(1, B);
+    c->h_set_blk0 = {0u, B}; c->h_set_pos0 = {0u, c->E};
+    TRY(h2d(ex, c->set_nblocks.p, c->h_set_nblocks.data(), sizeof(u32)));
+    TRY(h2d(ex, c->set_blk0.p, c->h_set_blk0.data(), 2 * sizeof(u32)));
+    TRY(h2d(ex, c->set_pos0.p, c->h_set_pos0.data(), 2 * sizeof(u32)));
+    TRY(dev_zero(ex, c->set_flags.p, sizeof(u32) * c->nsets));
+    TRY(dev_zero(ex, c->leaf_set.p, sizeof(u32) * (size_t)c->N0));
+    c->q0.N0 = c->N0; c->q0.z0 = P<u32>(c->z0); c->q0.leaf_set = P<u32>(c->leaf_set); c->q0.saidx0 = P<u32>(c->saidx0);
+    TRY(build_pyramid(c, c->pyr, P<u32>(c->lcp0), c->N0, c->q0.lcp));
+    TRY(build_pyramid(c, c->pyr2, P<u32>(c->sa0), c->N0, c->q0.pos));
+    mark(c, 3);
+    TRY(stage_block_order(c, v));
+    mark(c, 4);
+    TRY(stage_chain(c, v, max_interval));
+    { RotArgs a{v, P<u32>(c->set_blk0), P<u32>(c->set_pos0), P<int>(c->f_pos), P<int>(c->f_next), P<int>(c->rotations), P<u32>(c->set_cyclic)};
+      launch_rot(ex, c->nsets, a); }
+    mark(c, 5);
+    TRY(exec_sync(ex));
+#ifndef CSA_EMU
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) CSA_FAIL(CSA_GPU_ECUDA, "kernel failure: %s", cudaGetErrorString(e));
+        for (int i = 0; i < 5; i++) cudaEventElapsedTime(&c->tm.ms[i], c->tm.ev[i], c->tm.ev[i + 1]);
+        cudaEventElapsedTime(&c->tm.ms[5], c->tm.ev[0], c->tm.ev[5]);
+    }
+#endif
+    c->launches = ex.launches;
+    c->shard_phase = 0;
+    c->ran = true;
+    return CSA_GPU_OK;
 }
 
 // ---- the same from ONE process that drives several GPUs (the C host: no NCCL, no Python) -------------------------

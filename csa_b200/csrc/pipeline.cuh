@@ -552,7 +552,7 @@ static inline void launch_blockfind(Exec &ex, long long n, BlockFindArgs a) {
 // looked up.  This path skips k_colorkey, the colour sort, k_next, k_cover and the scan that builds R[] (3.4 ms of a
 // 15.8 ms step); R[] is still built when the counts of csamsa.c:332,338 are asked for (k_windepth, k_plateau work on it)
 // or a set holds more than 64 sequences.
-struct BlockFind2Args { BatchView v; const u32 *sa; const u32 *lcp; u32 *isblock; u32 *depth; u32 mmax; };
+struct BlockFind2Args { BatchView v; const u32 *sa; const u32 *lcp; u32 *isblock; u32 *depth; u32 mmax; u32 off; }; // off: first place of the launch (a rank's own range)
 HD bool blockfind2_screen(const BlockFind2Args &a, u32 lb, u32 *s0_out, u32 *s1_out, u32 *m_out) {
     const u32 s = set_of_pos(a.v, lb);
     const u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
@@ -567,7 +567,7 @@ HD bool blockfind2_screen(const BlockFind2Args &a, u32 lb, u32 *s0_out, u32 *s1_
 }
 #ifdef CSA_EMU
 HD void blockfind2_body(long long i, const BlockFind2Args &a) {
-    const u32 lb = (u32)i;
+    const u32 lb = (u32)i + a.off;
     a.isblock[lb] = 0;
     u32 s0, s1, m;
     if (!blockfind2_screen(a, lb, &s0, &s1, &m)) return;
@@ -596,8 +596,8 @@ HD void blockfind2_body(long long i, const BlockFind2Args &a) {
 MAP_KERNEL(blockfind2, BlockFind2Args, 12)
 #else
 // set of SA place i for the threads of one CTA: one search for the CTA's first place, then a step or two forward
-__device__ __forceinline__ u32 set_of_pos_cta(const BatchView &v, long long i, u32 *s_first) {
-    if (threadIdx.x == 0) *s_first = set_of_pos(v, (u32)((long long)blockIdx.x * blockDim.x));
+__device__ __forceinline__ u32 set_of_pos_cta(const BatchView &v, long long i, u32 off, u32 *s_first) {
+    if (threadIdx.x == 0) *s_first = set_of_pos(v, (u32)((long long)blockIdx.x * blockDim.x) + off);
     __syncthreads();
     u32 s = *s_first;
     while (s + 1 < (u32)v.nsets && (u32)i >= LDG(v.set_base0 + s + 1)) s++;
@@ -607,8 +607,8 @@ __global__ void __launch_bounds__(256) k_blockfind2(long long n, BlockFind2Args 
     __shared__ u32 s_first;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
-    const u32 lb = (u32)i;
-    const u32 s = set_of_pos_cta(a.v, i < n ? i : n - 1, &s_first);
+    const u32 lb = (u32)i + a.off;
+    const u32 s = set_of_pos_cta(a.v, (i < n ? i : n - 1) + a.off, a.off, &s_first);
     u32 m = 0, inner = 0;
     bool cand = false;
     if (i < n) {
@@ -693,6 +693,34 @@ HD void setcount_body(long long s, const SetCountArgs &a) {
 }
 MAP_KERNEL(setcount, SetCountArgs, 12)
 
+// ---- one set sharded over the ranks of a job: the block candidates of a rank's own range ------------------------------------
+// (csa_gpu_shard_blocks_begin / _finish)  A block is exchanged as a record: its place, its depth and the m suffixes of its
+// window -- all the later stages read of the suffix array.
+struct LcpAtArgs { LcpDirectArgs d; u32 pos; };
+HD void lcpat_body(long long, const LcpAtArgs &a) { lcpdirect_body((long long)a.pos, a.d); }
+MAP_KERNEL(lcpat, LcpAtArgs, 0)
+
+struct RangeMinArgs { const u32 *x; u32 lo; u32 *out; }; // *out = min(*out, x[lo .. lo+n))
+HD void rangemin_body(long long i, const RangeMinArgs &a) { ATOMIC_MIN(a.out, a.x[a.lo + (u32)i]); }
+MAP_KERNEL(rangemin, RangeMinArgs, 4)
+
+struct BlkRecArgs { const u32 *sa; const u32 *isblock; const u32 *bidx; const u32 *depth; u32 off; u32 m; u32 *rec; };
+HD void blkrecpack_body(long long i0, const BlkRecArgs &a) {
+    const u32 i = (u32)i0 + a.off;
+    if (!a.isblock[i]) return;
+    u32 *r = a.rec + (size_t)a.bidx[i] * (2u + a.m);
+    r[0] = i; r[1] = a.depth[i];
+    for (u32 j = 0; j < a.m; j++) r[2 + j] = a.sa[i + j];
+}
+MAP_KERNEL(blkrecpack, BlkRecArgs, 12)
+struct BlkUnpackArgs { const u32 *rec; u32 m; u32 *sa; u32 *blk_lb; u32 *blk_depth; u32 *blk_set; };
+HD void blkrecunpack_body(long long b, const BlkUnpackArgs &a) {
+    const u32 *r = a.rec + (size_t)b * (2u + a.m);
+    a.blk_lb[b] = r[0]; a.blk_depth[b] = r[1]; a.blk_set[b] = 0;
+    for (u32 j = 0; j < a.m; j++) a.sa[r[0] + j] = r[2 + j];
+}
+MAP_KERNEL(blkrecunpack, BlkUnpackArgs, 12)
+
 // ---- stage 4: order of the block list ----------------------------------------------------------------
 // insertSortedItem (nodeslinkedlists.c:36) keeps the list by depth, descending, and puts a block
 // BEFORE the blocks of equal depth met earlier; blocks are met in the DFS order of the tree,
@@ -701,27 +729,28 @@ MAP_KERNEL(setcount, SetCountArgs, 12)
 // rotation of sequence 0 is computed on the LCP-interval tree of sequence 0 alone:
 //   dfs(leaf) = sum over the nodes v on the path leaf..root of before(v),
 //   before(v) = leaves under the siblings of v whose first occurrence precedes v's.
-struct Seq0FlagArgs { BatchView v; const u32 *sa; u32 *flag; };
+struct Seq0FlagArgs { BatchView v; const u32 *sa; u32 *flag; u32 off; };
 HD void seq0flag_body(long long i, const Seq0FlagArgs &a) { // (a rotation of sequence 0 of its set: a range check, no gather)
-    const u32 s = set_of_pos(a.v, (u32)i), k0 = LDG(a.v.set_seq0 + s);
-    const u32 g = a.sa[i];
+    const u32 s = set_of_pos(a.v, (u32)i + a.off), k0 = LDG(a.v.set_seq0 + s);
+    const u32 g = a.sa[i + a.off];
     a.flag[i] = (g >= LDG(a.v.seq_off + k0) && g < LDG(a.v.seq_off + k0 + 1)) ? 1u : 0u;
 }
 MAP_KERNEL(seq0flag, Seq0FlagArgs, 12)
 
-struct Seq0EmitArgs { BatchView v; const u32 *sa; const u32 *flag; const u32 *idx0; u32 *sa0; u32 *saidx0; u32 *leaf_set; };
-HD void seq0emit_body(long long i, const Seq0EmitArgs &a) {
+struct Seq0EmitArgs { BatchView v; const u32 *sa; const u32 *flag; const u32 *idx0; u32 *sa0; u32 *saidx0; u32 *leaf_set; u32 off; u32 *count; u32 n; };
+HD void seq0emit_body(long long i, const Seq0EmitArgs &a) { // (flag, idx0: for the places [off, off+n) of the launch)
+    if (a.count && (u32)i + 1 == a.n) *a.count = a.idx0[i] + a.flag[i];
     if (!a.flag[i]) return;
-    const u32 t = a.idx0[i], s = set_of_pos(a.v, (u32)i);
-    a.sa0[t] = a.sa[i] - LDG(a.v.seq_off + LDG(a.v.set_seq0 + s)); // (sequence 0 of the set: no look-up of the suffix's sequence)
-    a.saidx0[t] = (u32)i;
+    const u32 t = a.idx0[i], s = set_of_pos(a.v, (u32)i + a.off);
+    a.sa0[t] = a.sa[i + a.off] - LDG(a.v.seq_off + LDG(a.v.set_seq0 + s)); // (sequence 0 of the set: no look-up of the suffix's sequence)
+    a.saidx0[t] = (u32)i + a.off;
     a.leaf_set[t] = s;
 }
 MAP_KERNEL(seq0emit, Seq0EmitArgs, 8)
 #ifndef CSA_EMU
 // the three kernels above in ONE pass over the suffix array (flag, running count by decoupled look-back as in k_scan_chain,
 // write-out): 4 B read per place instead of 28 B moved
-struct Seq0CompactArgs { BatchView v; const u32 *sa; u32 *sa0; u32 *saidx0; u32 *leaf_set; unsigned long long *state; };
+struct Seq0CompactArgs { BatchView v; const u32 *sa; u32 *sa0; u32 *saidx0; u32 *leaf_set; unsigned long long *state; u32 off; u32 *count; }; // places [off, off+n); count: how many came out
 __global__ void __launch_bounds__(CS_THREADS) k_seq0compact(long long n, Seq0CompactArgs a) {
     __shared__ u32 sm[33];
     __shared__ u32 s_tile, s_prefix, s_set;
@@ -730,7 +759,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_seq0compact(long long n, Seq0Com
     const u32 tile = s_tile;
     volatile unsigned long long *st = a.state + 1;
     const long long tile0 = (long long)tile * CS_TILE, base = tile0 + (long long)threadIdx.x * CS_ITEMS;
-    if (threadIdx.x == 0) s_set = set_of_pos(a.v, (u32)tile0);
+    if (threadIdx.x == 0) s_set = set_of_pos(a.v, (u32)tile0 + a.off);
     __syncthreads();
     u32 s = s_set;
     u32 g[CS_ITEMS], sset[CS_ITEMS];
@@ -740,9 +769,9 @@ __global__ void __launch_bounds__(CS_THREADS) k_seq0compact(long long n, Seq0Com
         const long long i = base + j;
         g[j] = 0; sset[j] = 0;
         if (i < n) {
-            while (s + 1 < (u32)a.v.nsets && (u32)i >= LDG(a.v.set_base0 + s + 1)) s++;
+            while (s + 1 < (u32)a.v.nsets && (u32)i + a.off >= LDG(a.v.set_base0 + s + 1)) s++;
             const u32 k0 = LDG(a.v.set_seq0 + s), off = LDG(a.v.seq_off + k0);
-            const u32 x = a.sa[i];
+            const u32 x = a.sa[i + a.off];
             if (x >= off && x < LDG(a.v.seq_off + k0 + 1)) { flags |= 1u << j; cnt++; g[j] = x - off; sset[j] = s; }
         }
     }
@@ -773,9 +802,10 @@ __global__ void __launch_bounds__(CS_THREADS) k_seq0compact(long long n, Seq0Com
     }
     __syncthreads();
     u32 t = s_prefix + excl;
+    if (a.count && threadIdx.x == 0 && tile0 + CS_TILE >= n) *a.count = s_prefix + total; // (the last tile knows the sum)
 #pragma unroll
     for (int j = 0; j < CS_ITEMS; j++)
-        if (flags >> j & 1u) { a.sa0[t] = g[j]; a.saidx0[t] = (u32)(base + j); a.leaf_set[t] = sset[j]; t++; }
+        if (flags >> j & 1u) { a.sa0[t] = g[j]; a.saidx0[t] = (u32)(base + j) + a.off; a.leaf_set[t] = sset[j]; t++; }
 }
 #endif
 

@@ -22,8 +22,9 @@
 #define CSA_FLAG_RARE 4u        // a full-length match somewhere in the set: the kernels of this file run
 #define CSA_FLAG_UNDEFINED 8u   // removeSuffixNodes frees the list item it stands on
 
-struct LeafScanArgs { BatchView v; const u32 *lcp; u32 *set_flags; u32 batch_nmin; };
-HD void leafscan_body(long long i, const LeafScanArgs &a) {
+struct LeafScanArgs { BatchView v; const u32 *lcp; u32 *set_flags; u32 batch_nmin; u32 off; };
+HD void leafscan_body(long long i0, const LeafScanArgs &a) {
+    const u32 i = (u32)i0 + a.off;
     u32 l = a.lcp[i];
     if (l < a.batch_nmin || l == 0xFFFFFFFFu) return; // (no set's shortest sequence is shorter: no search for the set)
     u32 s = set_of_pos(a.v, (u32)i);

@@ -80,8 +80,84 @@ def _alias(ptr: int, count: int, itemsize: int, cuda: bool):
     return torch.from_numpy(arr)
 
 
+def _gather_var(dist, t, counts, width, dev):
+    """all-gather of pieces of different lengths (counts[r] rows of `width`): padded to the longest, cut on arrival"""
+    import torch
+    mx = max(max(counts), 1)
+    mine = torch.zeros(mx * width, dtype=torch.int32, device=dev)
+    mine[:t.numel()].copy_(t)
+    allb = torch.empty(len(counts) * mx * width, dtype=torch.int32, device=dev)
+    if dev == "cuda":
+        dist.all_gather_into_tensor(allb, mine)
+    else:
+        parts = [torch.empty_like(mine) for _ in counts]
+        dist.all_gather(parts, mine)
+        allb = torch.cat(parts)
+    return torch.cat([allb[r * mx * width:r * mx * width + counts[r] * width] for r in range(len(counts))])
+
+
+last_path = None  # of the last run_bucket_sharded: "blocks" (block stages on every rank's own range) | "exchange"
+
+
+def _run_blocks_sharded(finder, rank, world, dist, max_interval, flags, v, bounds, n, m, cuda):
+    """the block stages on every rank's own range (see include/csa_gpu.h, csa_gpu_shard_blocks_*).  False: some range holds
+    a full-length match (rare.cuh's sets) -- the caller falls back on the full exchange."""
+    import torch
+    dev = "cuda" if cuda else "cpu"
+    sa, lcp = _alias(v.sa, n, 4, cuda), _alias(v.lcp, n, 4, cuda)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    # halos: the first m places of every range (suffixes and LCPs) and its last suffix, to its neighbours
+    mine = torch.cat([sa[lo:lo + m], lcp[lo:lo + m], sa[hi - 1:hi]])
+    if cuda:
+        allh = torch.empty(world * (2 * m + 1), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allh, mine.contiguous())
+        allh = allh.view(world, 2 * m + 1)
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.contiguous())
+        allh = torch.stack(parts)
+    if rank + 1 < world:
+        sa[hi:hi + m].copy_(allh[rank + 1, :m])
+        lcp[hi:hi + m].copy_(allh[rank + 1, m:2 * m])
+    if rank > 0:
+        sa[lo - 1:lo].copy_(allh[rank - 1, 2 * m:])
+    if cuda:
+        torch.cuda.synchronize()
+    b = finder.shard_blocks_begin(flags)
+    info = torch.tensor([b.nblk, b.n0, b.head_min, b.tail_min, b.rare], dtype=torch.int64, device=dev)
+    alli = [torch.zeros_like(info) for _ in range(world)]
+    dist.all_gather(alli, info)
+    alli = [x.tolist() for x in alli]
+    if any(x[4] for x in alli):
+        return False
+    nblk, n0 = [x[0] for x in alli], [x[1] for x in alli]
+    tb, t0 = sum(nblk), sum(n0)
+    p_rec, p_sa0, p_saidx0, p_lcp0 = finder.shard_blocks_buffers(tb, t0)
+    w = 2 + m
+    rec = _gather_var(dist, _alias(b.blkrec, b.nblk * w, 4, cuda), nblk, w, dev)
+    if tb:
+        _alias(p_rec, tb * w, 4, cuda).copy_(rec)
+    for src, dst in ((b.sa0, p_sa0), (b.saidx0, p_saidx0), (b.lcp0, p_lcp0)):
+        _alias(dst, t0, 4, cuda).copy_(_gather_var(dist, _alias(src, b.n0, 4, cuda), n0, 1, dev))
+    # the LCP of a range's first rotation of sequence 0 with the one before it: the smallest lcp between them
+    lcp0 = _alias(p_lcp0, t0, 4, cuda)
+    carry, at, seen = 0xFFFFFFFF, 0, False
+    for r in range(world):
+        if n0[r]:
+            val = 0 if not seen else min(carry, alli[r][2])
+            lcp0[at:at + 1].fill_(val if val < 2**31 else val - 2**32)
+            carry, seen = alli[r][3], True
+            at += n0[r]
+        else:
+            carry = min(carry, alli[r][2])
+    if cuda:
+        torch.cuda.synchronize()
+    finder.shard_blocks_finish(max_interval, flags, tb, t0)
+    return True
+
+
 def run_bucket_sharded(finder: RotationFinder, rank: int, world: int, dist=None, max_interval: int = 2**31 - 1,
-                       flags: int = 0, cuda: bool = True):
+                       flags: int = 0, cuda: bool = True, shard_blocks: bool = True):
     """The batch uploaded to `finder` on EVERY rank (the same batch), its suffix array built bucket by bucket:
     rank r orders the groups of bucket r (csa_gpu_shard_begin), the buckets -- suffix array, group heads, LCP --
     are broadcast from their owners over the job's process group (NCCL over NVLink on the GPU box, gloo in the
@@ -89,6 +165,8 @@ def run_bucket_sharded(finder: RotationFinder, rank: int, world: int, dist=None,
     path (csa_gpu_shard_finish).  Afterwards finder.download() / finder.blocks() give the same results on every
     rank as a single-GPU run.  Returns the bucket borders."""
     import torch
+    global last_path
+    last_path = "exchange"
     finder.shard_begin(rank, world)
     v = finder.shard_view()
     bounds = [int(v.bounds[r]) for r in range(world + 1)]
@@ -104,6 +182,16 @@ def run_bucket_sharded(finder: RotationFinder, rank: int, world: int, dist=None,
     allc = [c.tolist() for c in allc]
     nl = [c[0] for c in allc]
     total = sum(nl)
+    batch = finder._batch
+    m = int(batch.set_start[1] - batch.set_start[0])
+    # ONE set of up to 64 sequences, every bucket finished by its rank, no counts asked for: the block stages run on every
+    # rank's own range too and only the blocks and sequence 0's arrays travel (csa_gpu_shard_blocks_*)
+    if (shard_blocks and int(v.own_sort) and batch.nsets == 1 and m <= 64 and not (flags & 1) and total == 0
+            and min(bounds[r + 1] - bounds[r] for r in range(world)) >= m + 1
+            and os.environ.get("CSA_SHARD_BLOCKS", "1") != "0"):
+        if _run_blocks_sharded(finder, rank, world, dist, max_interval, flags, v, bounds, n, m, cuda):
+            last_path = "blocks"
+            return bounds
     # suffix array and LCP of every bucket to every rank; the group heads only when some bucket sort left groups
     # for the doubling rounds (which work on the heads)
     arrays = [_alias(ptr, n, 4, cuda) for ptr in (v.sa, v.lcp) + ((v.head,) if total else ())]

@@ -157,11 +157,40 @@ typedef struct csa_gpu_shard_info {
     unsigned long long n;
     const unsigned *bounds;       /* host, nranks + 1 entries, valid until the next call on ctx */
     unsigned nleft, left_suffixes, min_depth, max_group;
+    unsigned own_sort;            /* 1: this rank sorted only its own bucket (one set); 0: the first sort ran on every rank */
 } csa_gpu_shard_info;
 int csa_gpu_shard_begin(csa_gpu_ctx *ctx, int rank, int nranks);
 int csa_gpu_shard_view(csa_gpu_ctx *ctx, csa_gpu_shard_info *out);
 int csa_gpu_shard_finish(csa_gpu_ctx *ctx, int max_interval, unsigned flags, unsigned nleft, unsigned left_suffixes,
                          unsigned min_depth, unsigned max_group);
+/* ---- ... and the block stages too (one set, every bucket finished by its rank: nleft == 0 everywhere) ----------------------
+ * Instead of copying every bucket of the suffix array and the LCP array to every rank (2 x 4 N bytes) and finding the
+ * blocks on every rank, each rank finds the blocks that START in its own range and picks out its rotations of sequence 0;
+ * what travels is a record per block (place, depth, the m suffixes of its window) and sequence 0's three arrays:
+ *   caller:  copy sa and lcp [bounds[r+1] .. bounds[r+1]+m) from rank r+1 and sa[bounds[r]-1] from rank r-1 into rank r's
+ *            arrays (csa_gpu_shard_view: the same global places); needs every bucket to hold at least m places
+ *   csa_gpu_shard_blocks_begin(ctx, flags, &b)   this range's block records and rotations of sequence 0
+ *   caller:  all-gather the counts; if some rank reports b.rare (a full-length match: csa_b200/csrc/rare.cuh redoes such
+ *            sets one thread per set) fall back on the full exchange + csa_gpu_shard_finish; else
+ *            csa_gpu_shard_blocks_buffers(ctx, total blocks, total n0, ...) and gather the ranks' records / arrays into
+ *            them in rank order; lcp0 of the first rotation of a rank's range = min(its head_min, the tail_min of the
+ *            ranks before it back to the last one that holds a rotation of sequence 0) (0 for the very first)
+ *   csa_gpu_shard_blocks_finish(ctx, ...)        block order, chaining, rotations on every rank (results as csa_gpu_batch_run;
+ *            csa_gpu_batch_suffix_array is then valid for the rank's own range and the blocks' windows only) */
+typedef struct csa_gpu_shard_blocks {
+    void *blkrec;                 /* device, unsigned[nblk][2 + m] */
+    unsigned nblk, m;
+    void *sa0, *saidx0, *lcp0;    /* device, unsigned[n0]: position in sequence 0, SA place, LCP with the rotation before */
+    unsigned n0;
+    unsigned head_min, tail_min;  /* smallest lcp from the range's start to its first rotation of sequence 0 / behind its last
+                                     one to the range's end (0xFFFFFFFF: none); n0 == 0: head_min = the whole range */
+    unsigned rare;
+} csa_gpu_shard_blocks;
+int csa_gpu_shard_blocks_begin(csa_gpu_ctx *ctx, unsigned flags, csa_gpu_shard_blocks *out);
+int csa_gpu_shard_blocks_buffers(csa_gpu_ctx *ctx, unsigned total_blocks, unsigned total_n0, void **blkrec, void **sa0,
+                                 void **saidx0, void **lcp0);
+int csa_gpu_shard_blocks_finish(csa_gpu_ctx *ctx, int max_interval, unsigned flags, unsigned total_blocks, unsigned total_n0);
+
 /* The same from ONE process that drives several GPUs (what the C host does: no NCCL, no Python).  One host thread
  * per GPU for the compute phases, the bucket exchange by peer copies.  Results are read from context 0
  * (csa_gpu_multi_ctx(m, 0)) with the csa_gpu_batch_* calls above. */

@@ -37,22 +37,24 @@ import os, sys, random
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
 import numpy as np
 import torch.distributed as dist
-from common import EMU_LIB, build_emu, gen_case, oracle_run, oracle_gsa, compare_with_oracle
+from common import EMU_LIB, KINDS, build_emu, gen_case, oracle_run, oracle_gsa, compare_with_oracle
 from csa_b200.api import RotationFinder, Batch
 from csa_b200.shard import run_bucket_sharded
+import csa_b200.shard as shard
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 rng = random.Random(77)
 rf = RotationFinder(lib_path=EMU_LIB)
-for trial in range(8):
+taken = {"blocks": 0, "exchange": 0}
+for trial in range(20):
     # trials 0-3: ONE set (every rank sorts only its own bucket of key prefixes; trial 3: the whole set on every rank);
     # later trials: batches of sets (first sort on every rank, buckets cut at group borders)
-    sets = [gen_case(rng, max_n=1500)[1] for _ in range(1 if trial < 4 else rng.randint(2, 4))]
-    mode = 8 if trial == 3 else (4 if trial % 2 else 0)   # 4: the bucket sorts stop early and leave groups to the doubling rounds
+    sets = [gen_case(rng, max_n=1500, kinds=KINDS if trial != 2 else ["contained", "periodic"])[1] for _ in range(1 if trial < 4 or trial >= 8 else rng.randint(2, 4))]
+    mode = 8 if trial == 3 else (4 if trial % 2 and trial < 8 else 0)   # 4: the bucket sorts stop early and leave groups to the doubling rounds
     rf.debug_rounds(mode)
     batch = Batch(sets)
     rf.upload(batch)
-    bounds = run_bucket_sharded(rf, rank, world, dist, cuda=False)
+    bounds = run_bucket_sharded(rf, rank, world, dist, cuda=False, shard_blocks=False)  # (buckets exchanged in full)
     assert bounds[0] == 0 and bounds[-1] == batch.nbases and bounds == sorted(bounds)
     sa, lcp = rf.suffix_array()
     off = 0
@@ -66,16 +68,27 @@ for trial in range(8):
     ref = rf.find_rotations_batch(batch)          # the same batch on one rank alone
     rf.debug_rounds(mode)
     rf.upload(batch)
-    run_bucket_sharded(rf, rank, world, dist, cuda=False)
+    run_bucket_sharded(rf, rank, world, dist, cuda=False)  # ONE set: the block stages on every rank's own range too
+    taken[shard.last_path] += 1
     rot, info = rf.download()
+    (depth, size, total, interval, nxt), pos = rf.blocks()
     for k, (s, r) in enumerate(zip(sets, ref)):
         o = oracle_run(s)
-        assert info[k].status == o["status"] == r.status
+        assert info[k].status == o["status"] == r.status, (trial, info[k].status, o["status"], r.status)
         if o["status"] == 0:
             q0, q1 = int(batch.set_start[k]), int(batch.set_start[k + 1])
             assert list(rot[q0:q1]) == list(o["rotations"])
+            b0, nb = info[k].block_offset, info[k].nblocks
+            assert info[k].count_chains == o["count_chains"] and nb == o["nblocks"]
+            for got, name in ((depth, "depth"), (size, "size"), (total, "totalsize"), (interval, "interval"), (nxt, "next")):
+                assert np.array_equal(got[b0:b0 + nb], o[name]), (trial, name)
+            if len(sets) == 1:
+                assert np.array_equal(pos.reshape(nb, len(s)), o["positions"]), (trial, "positions")
+                letters = rf.block_letters()
+                assert [bytes(x) for x in letters] == [bytes(x) for x in o["letters"]], (trial, "letters")
 rf.debug_rounds(0)
-sys.stdout.write("BUCKET_OK_%d_of_%d\n" % (rank, world)); sys.stdout.flush()
+assert taken["blocks"] >= 6 and taken["exchange"] >= 5, taken
+sys.stdout.write("BUCKET_OK_%d_of_%d %r\n" % (rank, world, taken)); sys.stdout.flush()
 dist.destroy_process_group()
 '''
 
