@@ -64,6 +64,7 @@ struct csa_gpu_ctx {
     double lcp_mean_sample = 0;
     int force_kasai = 0;
     int rounds_list = 0, round_mode = 0;
+    int carry_mode = 0; bool ws_carried = false; // carried word sort: 0 for sets of whole genomes, 1 always, 2 never
     int rounds_tiled = 0, rounds_global = 0, rounds_quad = 0, force_global_rounds = 0, no_quad_rounds = 0;
     DevMem pyr, pyr2, sa0, saidx0, leaf_set, lcp0;
     Seq0Q q0{};                 // sequence 0 of every set (stage_seq0)
@@ -412,7 +413,11 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     u32 any_other = c->sa_any_other;
     if (phase != 2) TRY(read_u32(c, counter + 8, &any_other)); // set by k_encode: a letter outside ACGT somewhere in the batch
     c->sa_any_other = any_other;
-    const int letters = any_other ? CSA_K0 : 12, lbits = any_other ? CSA_LETTER_BITS : 2;
+    // 12 letters tell the places of a 16 kb mitogenome apart; in a 5 Mb chromosome every fourth 12-letter word turns up again
+    // somewhere else (4^12 = 16.7 M) and drags a whole unrelated column into the group: 16 letters there (one more radix pass)
+    static const int env_letters = getenv("CSA_GPU_KEY_LETTERS") ? atoi(getenv("CSA_GPU_KEY_LETTERS")) : 0;
+    const int letters32 = env_letters == 12 || env_letters == 16 ? env_letters : (c->max_set_bases > (1u << 20) ? 16 : 12);
+    const int letters = any_other ? CSA_K0 : letters32, lbits = any_other ? CSA_LETTER_BITS : 2;
     int nbits = bits_for((u64)N - 1);
     u64 sorted_len = (u64)letters;
     u32 ngroups = c->sa_ngroups, maxg = 0;
@@ -423,7 +428,7 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     if (phase == 1) c->shard_own_sort = own_sort;
     if (own_sort) {
         const int R = c->shard_nranks, kbits = letters * lbits, shift = kbits - BK_BITS;
-        { InitKeyArgs a{v, any_other ? P<u64>(c->keysB) : nullptr, any_other ? nullptr : P<u32>(c->keysB), P<u32>(c->valsB)};
+        { InitKeyArgs a{v, any_other ? P<u64>(c->keysB) : nullptr, any_other ? nullptr : P<u32>(c->keysB), P<u32>(c->valsB), letters32};
           launch_initkey(ex, N, a); }
         TRY(dev_alloc(c->bk_hist, sizeof(u32) * BK_BINS));
         TRY(dev_zero(ex, c->bk_hist.p, sizeof(u32) * BK_BINS));
@@ -472,7 +477,7 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     } else if (phase != 2) {
     RsSeg seg{P<u32>(c->rs_start), P<u32>(c->rs_count), P<u32>(c->rs_cbase), P<u32>(c->rs_stride), c->rs_nblocks,
               P<u32>(c->set_base0), (u32)c->nsets};
-    { InitKeyArgs a{v, any_other ? P<u64>(c->keysA) : nullptr, any_other ? nullptr : P<u32>(c->keysA), nullptr};
+    { InitKeyArgs a{v, any_other ? P<u64>(c->keysA) : nullptr, any_other ? nullptr : P<u32>(c->keysA), nullptr, letters32};
       launch_initkey(ex, N, a); }
     if (any_other) {
         u64 *k = P<u64>(c->keysA), *ka = P<u64>(c->keysB);
@@ -556,7 +561,37 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
             const u32 init[6] = {0u, 0u, 0xFFFFFFFFu, 0u, 0u, 0u};
             TRY(h2d(ex, res, init, sizeof(init)));
             const u32 lo = phase == 1 ? c->h_shard_bounds[c->shard_rank] : 0u, hi = phase == 1 ? c->h_shard_bounds[c->shard_rank + 1] : N;
-            WSortArgs a{v, P<u32>(c->valsA), head, lcp, N, lo, hi, (u32)letters, c->ws_depth_cap, (int)any_other, glist[0], glist[1], 0u, res};
+            WSortArgs a{v, P<u32>(c->valsA), head, lcp, N, lo, hi, (u32)letters, c->ws_depth_cap, (int)any_other, glist[0], glist[1], 0u, res,
+                        nullptr, nullptr, 0u, nullptr, nullptr};
+            // sets of whole genomes (millions of letters a sequence): what near-identical genomes share runs for hundreds of
+            // letters, and a column's order carries over to the next (pipeline.cuh "carried word sort")
+            const bool carry = c->carry_mode == 1 || (c->carry_mode == 0 && c->max_set_bases > WS_LARGE_SET);
+            c->ws_carried = carry;
+            if (carry) {
+                u32 *grp = rank, *head2 = rank2, *roots = P<u32>(c->keysA), *nroots = counter + 32;
+                unsigned char *flag = P<unsigned char>(c->keysB);
+                if (phase == 1) TRY(dev_fill_ff(ex, grp, sizeof(u32) * (size_t)N)); // (suffixes of other ranks' buckets: in no group)
+                TRY(dev_zero(ex, nroots, 2 * sizeof(u32)));
+                CarryArgs ca{v, P<u32>(c->valsA), head, head2, grp, flag, lo, hi};
+                launch_cygrp(ex, (long long)hi - lo, ca);
+                launch_cyroots(ex, (long long)hi - lo, ca);
+                a.head_in = head2; a.flag = flag; a.want = 1u; a.roots = roots; a.nroots = nroots;
+                launch_wsort(ex, a);
+                CyWalkArgs w{v, P<u32>(c->valsA), head, lcp, head2, grp, flag, lo, hi, (u32)letters, roots, nroots, nroots + 1};
+                launch_cywalk(ex, w);
+                a.want = 0u; a.roots = nullptr; a.nroots = nullptr;
+                if (getenv("CSA_GPU_TRACE")) {
+                    std::vector<unsigned char> f((size_t)hi - lo);
+                    std::vector<u32> h2((size_t)hi - lo);
+                    u32 nr = 0;
+                    TRY(d2h(ex, f.data(), flag + lo, f.size())); TRY(d2h(ex, h2.data(), head2 + lo, sizeof(u32) * h2.size()));
+                    TRY(d2h(ex, &nr, nroots, sizeof(u32)));
+                    size_t cnt[3] = {0, 0, 0};
+                    for (size_t x = 0; x + 1 < f.size(); x++) if (h2[x] == lo + x && h2[x + 1] == lo + x) cnt[f[x] < 3 ? f[x] : 0]++;
+                    fprintf(stderr, "[csa] carried word sort: %zu groups ordered by letters (%u walks started), %zu written by the walks, %zu left to the sweep\n",
+                            cnt[1], nr, cnt[2], cnt[0]);
+                }
+            }
             launch_wsort(ex, a);
             TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
             if (c->ws_left[5]) { // groups that did not fit a warp's window: one CTA each
@@ -1350,6 +1385,8 @@ extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds
         c->no_chain_big = force_global == 7; // 7: free choice, but long block lists walked by one thread (k_chain) as short ones are
         c->shard_full_sort = force_global == 8; // 8: sharded runs of one set sort the whole set on every rank (as batches of sets do)
         c->force_cover = force_global == 9;     // 9: free choice, blocks always through the cover array R[]
+        c->carry_mode = force_global == 10 ? 1 : force_global == 11 ? 2 : 0; // 10: word sort, carried, whatever the sets look like; 11: free choice, never carried
+        if (force_global == 10) c->ws_force = true;
         if (force_global >= 6) c->round_mode = 0;
         c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; c->force_kasai = force_global == 2;
     }

@@ -207,14 +207,14 @@ HD u64 lexkey2(u64 w) {
 // The first sort key: the first letters of the rotation -- 13 letters of 3 bits in a u64, or, when the
 // batch holds nothing but A,C,G,T, 12 letters of 2 bits in a u32 (three radix passes of 8 B per element
 // instead of five of 12 B).  The set number is not in the key: the first sort is segmented by set.
-struct InitKeyArgs { BatchView v; u64 *keys64; u32 *keys32; u32 *vals; };
+struct InitKeyArgs { BatchView v; u64 *keys64; u32 *keys32; u32 *vals; int letters32; }; // letters32: 12 or 16 letters in a u32 key
 HD void initkey_body(long long i, const InitKeyArgs &a) {
     u32 g = (u32)i;
     u32 k = seq_of(a.v, g);
     u32 off = LDG(a.v.seq_off + k), n = LDG(a.v.seq_off + k + 1) - off;
     u32 p = g - off;
-    if (a.keys32) { // nothing but A,C,G,T in the batch: the 12 letters are the top 24 bits of one word of the packed text
-        a.keys32[g] = (u32)(lexkey2(fetch2(a.v.p2, LDG(a.v.dbl_off + k) + p)) >> 40);
+    if (a.keys32) { // nothing but A,C,G,T in the batch: the 12 (16) letters are the top 24 (32) bits of one word of the packed text
+        a.keys32[g] = (u32)(lexkey2(fetch2(a.v.p2, LDG(a.v.dbl_off + k) + p)) >> (64 - 2 * a.letters32));
     } else {
         u64 key = 0;
         for (int t = 0; t < CSA_K0; t++) {
@@ -2600,7 +2600,15 @@ struct WSortArgs {
     u32 nbig;  // (k_wsort_big) entries of big
     u32 *res;  // [0] groups left, [1] suffixes in them, [2] fewest letters a left group shares, [3] largest left group,
                // [4] unused, [5] entries of big
+    // the carried word sort (see "carry" below): groups as they stood after the first sort, which of them to take, and the
+    // list of the groups sorted here whose order carries over to the groups one letter on
+    const u32 *head_in;        // group borders are read here (nullptr: head)
+    const unsigned char *flag; // by first place of a group (nullptr: every group is taken)
+    u32 want;                  // ... the groups with flag[start] == want
+    u32 *roots, *nroots;       // first places of the groups of <= CY_MAXG suffixes ordered here without a tie (nullptr: no list)
 };
+HD const u32 *ws_head_in(const WSortArgs &a) { return a.head_in ? a.head_in : a.head; }
+HD bool ws_taken(const WSortArgs &a, u32 start) { return !a.flag || a.flag[start] == a.want; }
 
 HD u32 lexmask(u32 w) {
 #if defined(__CUDA_ARCH__)
@@ -2696,9 +2704,158 @@ HD void bounds_map_body(long long r, const BoundsArgs &a) {
 MAP_KERNEL(bounds_map, BoundsArgs, 4)
 static inline void launch_bounds(Exec &ex, const BoundsArgs &a) { launch_bounds_map(ex, (long long)a.nranks + 1, a); }
 
+// ---- the carried word sort: one compare per column of near-identical genomes, not one per place ----------------
+// Two rotations that share l > L0 letters still share l - 1 one place on, in the same order.  So when every suffix of
+// a group G' has its predecessor in the text (one letter back round its sequence) in ONE group G of the first sort,
+// G' is G's order, moved one place, restricted to the suffixes whose L0 letters still agree -- and the LCPs are G's
+// less one (Kasai's carry-over, applied to whole groups).  Only the groups that are NOT of that kind ("roots": a
+// predecessor differs, i.e. the column follows a place where the genomes differ) are ordered by comparing letters
+// (k_wsort on the flagged groups); one warp per root then walks the text, a lane per suffix, and writes the groups
+// that follow from it, step by step, until every lane's run has ended:
+//   k_cygrp    grp[suffix] = first place of its group (unset: alone in its group, or the group holds more than a
+//              warp); snapshot of the heads (the walk reads borders while other warps rewrite heads)
+//   k_cyroots  flag[first place] = 1 for the groups that must be ordered afresh: a predecessor in another group or
+//              in none, or a suffix at a multiple of CY_CUT letters from its sequence's start (cuts the walks, so
+//              that ten thousand of them run side by side whatever the genomes share)
+//   k_wsort    (want = 1) orders the roots, lists those a walk can start from (<= 32 suffixes, no two still equal)
+//   k_cywalk   the walks; flag = 2 on every group written
+//   k_wsort    (want = 0) whatever no walk reached (descendants of roots with ties): as before, by letters
+// Results are those of the word sort alone, place by place (tests: forced on every golden set; full-size agreement).
+#define CY_MAXG 32u
+#define CY_CUT 1024u
+#define CY_UNSET 0xFFFFFFFFu
+struct CarryArgs {
+    BatchView v; const u32 *sa; const u32 *head; u32 *head2; u32 *grp; unsigned char *flag; u32 lo, hi;
+};
+HD bool cy_single(const u32 *h, u32 x, u32 hs, u32 hi) { return hs == x && (x + 1 >= hi || (h[x + 1] & 0x7FFFFFFFu) != hs); }
+HD bool cy_big(const u32 *h, u32 hs, u32 hi) { return (u64)hs + CY_MAXG < hi && (h[hs + CY_MAXG] & 0x7FFFFFFFu) == hs; }
+HD void cygrp_body(long long i, const CarryArgs &a) {
+    const u32 x = a.lo + (u32)i, hs = a.head[x] & 0x7FFFFFFFu;
+    a.head2[x] = hs;
+    const bool big = cy_big(a.head, hs, a.hi);
+    a.grp[a.sa[x]] = (big || cy_single(a.head, x, hs, a.hi)) ? CY_UNSET : hs;
+    a.flag[x] = (big && hs == x) ? 1 : 0;
+}
+MAP_KERNEL(cygrp, CarryArgs, 17)
+// the group (first place) of the suffix one letter back round its sequence; *cut: the suffix stands at a multiple of CY_CUT
+HD u32 cy_parent(const CarryArgs &a, u32 s, bool *cut) {
+    const u32 k = seq_of_few(a.v, s), st = LDG(a.v.seq_off + k), off = s - st;
+    *cut = (off & (CY_CUT - 1u)) == 0u;
+    return a.grp[off ? s - 1u : LDG(a.v.seq_off + k + 1) - 1u];
+}
+HD void cyroots_body(long long i, const CarryArgs &a) {
+    const u32 x = a.lo + (u32)i, hs = a.head2[x];
+    if (cy_single(a.head2, x, hs, a.hi) || cy_big(a.head2, hs, a.hi)) return;
+    bool cut, cut0;
+    const u32 par = cy_parent(a, a.sa[x], &cut);
+    bool root = cut || par == CY_UNSET;
+    if (!root && x != hs) root = par != cy_parent(a, a.sa[hs], &cut0);
+    if (root) a.flag[hs] = 1;
+}
+MAP_KERNEL(cyroots, CarryArgs, 20)
+
+struct CyWalkArgs {
+    BatchView v; u32 *sa; u32 *head; u32 *lcp; const u32 *head2; const u32 *grp; unsigned char *flag;
+    u32 lo, hi, L0; const u32 *roots; const u32 *nroots; u32 *next; // next: the walks' work counter (zeroed)
+};
+#ifdef CSA_EMU
+// one root, lane by lane as the warp does it
+static inline void emu_cywalk_root(const CyWalkArgs &a, u32 hs) {
+    u32 g = 1;
+    while (hs + g < a.hi && a.head2[hs + g] == hs) g++;
+    struct Lane { u32 st, len, off, lcp; bool on; };
+    std::vector<Lane> ln(g);
+    for (u32 r = 0; r < g; r++) {
+        const u32 s = a.sa[hs + r], k = seq_of(a.v, s), st = a.v.seq_off[k];
+        ln[r] = Lane{st, a.v.seq_off[k + 1] - st, s - st, r ? a.lcp[hs + r] : 0u, true};
+    }
+    for (u32 j = 1;; j++) {
+        bool any = false;
+        for (u32 r = 0; r < g; r++)
+            if (ln[r].on) { ln[r].off = ln[r].off + 1 == ln[r].len ? 0 : ln[r].off + 1; any = true; }
+        if (!any) return;
+        for (u32 rs = 0; rs < g;) {
+            if (!ln[rs].on) { rs++; continue; }
+            u32 re = rs + 1;
+            while (re < g && ln[re].on && ln[re].lcp >= a.L0 + j) re++;
+            const u32 G = a.grp[ln[rs].st + ln[rs].off], n = re - rs;
+            bool ok = G != CY_UNSET && n >= 2;
+            if (ok) ok = (u64)G + n >= a.hi || a.head2[G + n] != G;
+            for (u32 r = rs; r < re && ok; r++) if ((ln[r].off & (CY_CUT - 1u)) == 0u) ok = false;
+            if (ok) {
+                for (u32 r = rs; r < re; r++) {
+                    const u32 place = G + (r - rs);
+                    a.sa[place] = ln[r].st + ln[r].off;
+                    a.head[place] = place;
+                    if (r > rs) a.lcp[place] = ln[r].lcp - j;
+                }
+                a.flag[G] = 2;
+            } else for (u32 r = rs; r < re; r++) ln[r].on = false;
+            rs = re;
+        }
+    }
+}
+static inline void launch_cywalk(Exec &, const CyWalkArgs &a) {
+    for (u32 i = 0; i < *a.nroots; i++) emu_cywalk_root(a, a.roots[i]);
+}
+#else
+#define CY_WARPS 8
+__global__ void __launch_bounds__(CY_WARPS * 32) k_cywalk(CyWalkArgs a) {
+    const u32 lane = threadIdx.x & 31u, nroots = *a.nroots;
+    for (;;) {
+        u32 i = 0;
+        if (lane == 0) i = atomicAdd(a.next, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= nroots) return;
+        const u32 hs = a.roots[i];
+        const bool mine = (u64)hs + lane < a.hi && a.head2[hs + lane] == hs; // (a root holds at most 32 suffixes)
+        u32 st = 0, len = 1, off = 0, l = 0;
+        if (mine) {
+            const u32 s = a.sa[hs + lane], k = seq_of_few(a.v, s);
+            st = LDG(a.v.seq_off + k); len = LDG(a.v.seq_off + k + 1) - st; off = s - st;
+            l = lane ? a.lcp[hs + lane] : 0u;
+        }
+        bool on = mine;
+        for (u32 j = 1;; j++) {
+            const u32 onmask = __ballot_sync(0xffffffffu, on);
+            if (!onmask) break;
+            off = off + 1u == len ? 0u : off + 1u;
+            const u32 G = on ? LDG(a.grp + st + off) : CY_UNSET;
+            // runs: lane r goes on with lane r - 1 when both are in the walk and still share L0 letters after j steps
+            const bool cont = on && lane && ((onmask >> (lane - 1u)) & 1u) && l >= a.L0 + j;
+            const u32 startmask = __ballot_sync(0xffffffffu, on && !cont);
+            const u32 cutmask = __ballot_sync(0xffffffffu, on && (off & (CY_CUT - 1u)) == 0u);
+            bool ok = false;
+            u32 rs = 0;
+            if (on) {
+                rs = 31u - (u32)__clz((int)(startmask & (0xFFFFFFFFu >> (31u - lane))));
+                const u32 ends = (startmask | ~onmask) & (lane < 31u ? 0xFFFFFFFFu << (lane + 1u) : 0u);
+                const u32 re = ends ? (u32)__ffs((int)ends) - 1u : 32u, n = re - rs;
+                const u32 runmask = (re < 32u ? (1u << re) - 1u : 0xFFFFFFFFu) & (0xFFFFFFFFu << rs);
+                ok = G != CY_UNSET && n >= 2u && !(cutmask & runmask);
+                if (ok) ok = (u64)G + n >= a.hi || LDG(a.head2 + G + n) != G; // the group holds nobody else
+            }
+            if (ok) {
+                const u32 place = G + (lane - rs);
+                a.sa[place] = st + off;
+                a.head[place] = place;
+                if (lane > rs) a.lcp[place] = l - j; else a.flag[G] = 2;
+            }
+            on = ok;
+        }
+    }
+}
+static inline void launch_cywalk(Exec &ex, const CyWalkArgs &a) {
+    PROF_BEGIN(ex, "k_cywalk", 0.0);
+    k_cywalk<<<148 * 8, CY_WARPS * 32, 0, ex.stream>>>(a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
+
 #ifdef CSA_EMU
 // one group [p, e) by the letters [L0, Lend): stable; what is still together goes to the list
-static inline void emu_wsort_group(const WSortArgs &a, u32 p, u32 e, u32 Lend) {
+static inline void emu_wsort_group(const WSortArgs &a, u32 p, u32 e, u32 Lend, bool with_root = false) {
     const BatchView &v = a.v;
     struct It { u32 g; std::vector<unsigned char> s; };
     std::vector<It> items;
@@ -2709,10 +2866,12 @@ static inline void emu_wsort_group(const WSortArgs &a, u32 p, u32 e, u32 Lend) {
     }
     std::stable_sort(items.begin(), items.end(), [](const It &x, const It &y) { return x.s < y.s; });
     u32 hd = p;
+    bool ties = false;
     for (u32 x = p; x <= e; x++) {
         const bool brk = x == e || (x > p && items[x - p - 1].s != items[x - p].s);
         if (brk) {
             if (x - hd >= 2) { // still together after Lend letters
+                ties = true;
                 a.left[a.res[0]++] = ((u64)hd << 32) | (x - hd);
                 a.res[1] += x - hd;
                 if (Lend < a.res[2]) a.res[2] = Lend;
@@ -2728,6 +2887,7 @@ static inline void emu_wsort_group(const WSortArgs &a, u32 p, u32 e, u32 Lend) {
         }
         if (x < e) { a.sa[x] = items[x - p].g; a.head[x] = hd; }
     }
+    if (with_root && a.roots && !ties && e - p <= CY_MAXG) a.roots[(*a.nroots)++] = p;
 }
 static inline void emu_wsort_leave(const WSortArgs &a, u32 p, u32 e) {
     a.left[a.res[0]++] = ((u64)p << 32) | (e - p);
@@ -2745,7 +2905,8 @@ static inline void launch_wsort(Exec &, const WSortArgs &a) {
     const BatchView &v = a.v;
     const u32 N = a.N;
     (void)N; // (heads beyond hi may belong to another rank's bucket and not be there yet: hi itself is a border)
-    auto border = [&](u64 p) { return p < a.hi ? (a.head[p] & 0x7FFFFFFFu) == (u32)p : p == a.hi; };
+    const u32 *hin = ws_head_in(a);
+    auto border = [&](u64 p) { return p < a.hi ? (hin[p] & 0x7FFFFFFFu) == (u32)p : p == a.hi; };
     for (u64 r0 = a.lo & ~31u; r0 < a.hi; r0 += WS_NOM) {
         // groups that start in [r0, r0+WS_NOM) and end at or before place r0 + WS_CAP - 1
         std::vector<std::pair<u32, u32>> groups;
@@ -2755,10 +2916,10 @@ static inline void launch_wsort(Exec &, const WSortArgs &a) {
             u64 e = p + 1;
             while (!border(e)) e++;
             if (e - r0 > WS_CAP - 1) { // runs past the warp's window
-                if (e - p >= 2) a.big[a.res[5]++] = ((u64)p << 32) | (u32)(e - p);
+                if (e - p >= 2 && ws_taken(a, (u32)p)) a.big[a.res[5]++] = ((u64)p << 32) | (u32)(e - p);
                 break;
             }
-            if (e - p >= 2) {
+            if (e - p >= 2 && ws_taken(a, (u32)p)) {
                 groups.push_back({(u32)p, (u32)e});
                 for (u64 x = p; x < e; x++) {
                     u32 nm = v.set_nmin[v.seq_set[v.seqof[a.sa[x]]]];
@@ -2766,7 +2927,7 @@ static inline void launch_wsort(Exec &, const WSortArgs &a) {
                 }
             }
         }
-        for (auto &gr : groups) emu_wsort_group(a, gr.first, gr.second, emu_wsort_lend(a, nmin));
+        for (auto &gr : groups) emu_wsort_group(a, gr.first, gr.second, emu_wsort_lend(a, nmin), true);
     }
 }
 static inline void launch_wsort_big(Exec &, const WSortArgs &a) {
@@ -2945,6 +3106,11 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
             const u32 t = tid + TT * j;
             a.sa[base + np[j]] = s.g[t];
             a.head[base + np[j]] = base + nh[j];
+            if (WARPS == 1 && a.roots && t == s.seg[t] && (u32)s.end[t] - t <= CY_MAXG) { // a walk can start here unless two are still equal
+                bool ties = false;
+                for (u32 q = t; q < (u32)s.end[t]; q++) ties |= s.clsz[q] != 0u;
+                if (!ties) a.roots[atomicAdd(a.nroots, 1u)] = base + t;
+            }
             if (np[j] == nh[j]) {
                 if (nh[j] != s.seg[t]) a.lcp[base + np[j]] = s.best[t]; // (the first of the old group keeps its border LCP)
                 const u32 size = s.clsz[nh[j]];
@@ -2968,12 +3134,13 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
     if (r0_64 >= a.hi) return;
     const u32 r0 = (u32)r0_64, N = a.hi; // (heads beyond hi may be another rank's and not there yet: hi itself is a border)
     WsSmem<1> &s = s_all[warp];
+    const u32 *hin = ws_head_in(a);
     // ---- the window: heads of WS_CAP places, borders as a bit set ----
     u32 hv[WS_T], bw[WS_T];
 #pragma unroll
     for (int j = 0; j < WS_T; j++) {
         const u64 p = (u64)r0 + lane + 32u * j;
-        hv[j] = p < N ? (a.head[p] & 0x7FFFFFFFu) : 0u;
+        hv[j] = p < N ? (hin[p] & 0x7FFFFFFFu) : 0u;
         bw[j] = __ballot_sync(0xffffffffu, p < N ? hv[j] == (u32)p : p == N);
     }
     // starts that are this launch's: places in [lo, hi)
@@ -2993,13 +3160,13 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
         // its length: gallop, then bisect (head[p] == its start for every place inside it)
         const u32 hs = r0 + te;
         u64 lo = (u64)r0 + WS_CAP - 1, step = WS_CAP; // lo is inside the group
-        while (lo + step < N && (a.head[lo + step] & 0x7FFFFFFFu) == hs) { lo += step; step *= 2; }
+        while (lo + step < N && (hin[lo + step] & 0x7FFFFFFFu) == hs) { lo += step; step *= 2; }
         u64 hi = lo + step < N ? lo + step : N; // first place known to be outside (or N)
         while (hi - lo > 1) {
             const u64 mid = (lo + hi) >> 1;
-            if ((a.head[mid] & 0x7FFFFFFFu) == hs) lo = mid; else hi = mid;
+            if ((hin[mid] & 0x7FFFFFFFu) == hs) lo = mid; else hi = mid;
         }
-        if (lane == 0) a.big[atomicAdd(a.res + 5, 1u)] = ((u64)hs << 32) | (u32)(hi - hs);
+        if (lane == 0 && ws_taken(a, hs)) a.big[atomicAdd(a.res + 5, 1u)] = ((u64)hs << 32) | (u32)(hi - hs);
     }
     const u64 b0 = (u64)bw[0] | ((u64)bw[1] << 32), b1 = (u64)bw[2] | ((u64)bw[3] << 32);
     // ---- the suffixes of every group of two or more ----
@@ -3011,7 +3178,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
         act[j] = false;
         if (t >= tb && t < te) {
             const u32 hs = hv[j] - r0, he = ws_next_border(b0, b1, t);
-            act[j] = he - hs >= 2u;
+            act[j] = he - hs >= 2u && ws_taken(a, r0 + hs);
             s.seg[t] = (unsigned short)hs;
             s.end[t] = (unsigned short)he;
         }
@@ -3075,7 +3242,7 @@ __global__ void __launch_bounds__(WS_BIG_WARPS * 32) k_wsort_big(WSortArgs a) {
 static inline void launch_wsort(Exec &ex, const WSortArgs &a) {
     if (a.hi <= a.lo) return;
     const u32 nwarps = (a.hi - (a.lo & ~31u) + WS_NOM - 1) / WS_NOM;
-    PROF_BEGIN(ex, "k_wsort", 4.0 * a.N);
+    PROF_BEGIN(ex, a.flag ? (a.want ? "k_wsort(roots)" : "k_wsort(rest)") : "k_wsort", 4.0 * a.N);
     if (a.masks) k_wsort<true><<<(nwarps + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, ex.stream>>>(a);
     else k_wsort<false><<<(nwarps + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, ex.stream>>>(a);
     PROF_END(ex);

@@ -209,7 +209,9 @@ int csa_gpu_multi_batch_rotations(csa_gpu_multi *m, int nsets, const int *set_st
  * 3 tile rounds, quadrupling allowed; 4 word sort stopped after two words, the rest by doubling rounds; 5 free choice
  * among the doubling rounds (no word sort); 6 word sort whatever the groups look like; 7 free choice, long block
  * lists chained by the literal one-thread walk; 8 free choice, sharded runs of one set sort the whole set on every
- * rank; 9 free choice, blocks always found through the cover array (as when the counts are asked for).  rounds[0..1] = rounds of the last run on the tile/list/word-sort paths and on the device-wide path */
+ * rank; 9 free choice, blocks always found through the cover array (as when the counts are asked for); 10 word sort
+ * with the order of a column carried over to the next (what sets of whole genomes take) whatever the sets look like;
+ * 11 free choice, but the word sort never carried.  rounds[0..1] = rounds of the last run on the tile/list/word-sort paths and on the device-wide path */
 int csa_gpu_debug_rounds(csa_gpu_ctx *ctx, int mode, int rounds[2]);
 /* per-kernel profile: with it enabled every launch of the next runs is bracketed by CUDA events on
  * the run's stream; after a run row i gives the kernel's name, its launches, their summed device

@@ -71,13 +71,16 @@ def test_emu_both_round_paths(emu_finder):
         emu_finder.debug_rounds(6)
         res_w = emu_finder.find_rotations_batch(sets)
         assert emu_finder.debug_rounds()[0] > 0
+        emu_finder.debug_rounds(10)   # the word sort, a column's order carried over to the next
+        res_c = emu_finder.find_rotations_batch(sets)
         emu_finder.debug_rounds(0)
         res_0 = emu_finder.find_rotations_batch(sets)
     finally:
         emu_finder.debug_rounds(0)
-    for i, (a, b, d, q, w, w4, r0, s) in enumerate(zip(res_t, res_g, res_d, res_q, res_w, res_w4, res_0, sets)):
+    for i, (a, b, d, q, w, w4, r0, cw, s) in enumerate(zip(res_t, res_g, res_d, res_q, res_w, res_w4, res_0, res_c, sets)):
         o = oracle_run(s)
         compare_with_oracle(r0, o, s, f"free choice set {i}")
+        compare_with_oracle(cw, o, s, f"carried word sort set {i}")
         compare_with_oracle(w, o, s, f"word sort set {i}")
         compare_with_oracle(w4, o, s, f"word sort stopped early, then group lists set {i}")
         compare_with_oracle(a, o, s, f"group-list path set {i}")

@@ -183,8 +183,9 @@ def test_gpu_tile_rounds_equal_device_wide_rounds(gpu_finder):
             # 0 free choice (word sort first), 5 free choice among the doubling rounds (group lists while groups are
             # small), 4 word sort stopped after two words + doubling, 3 tile rounds with quadrupling, 2 tile rounds
             # with doubling only (+ text-order LCP), 1 device-wide rounds only
-            # 6 word sort whatever the groups look like (0 picks it only for small groups)
-            for mode in (0, 6, 5, 4, 3, 2, 1):
+            # 6 word sort whatever the groups look like (0 picks it only for small groups); 10 the same, a column's order
+            # carried over to the next (what sets of whole genomes take)
+            for mode in (0, 6, 5, 4, 3, 2, 1, 10):
                 gpu_finder.debug_rounds(mode)
                 res = gpu_finder.find_rotations_batch(batch)
                 sa, lcp = gpu_finder.suffix_array()
@@ -196,7 +197,7 @@ def test_gpu_tile_rounds_equal_device_wide_rounds(gpu_finder):
         assert rounds0[0] > 0
         assert out[(name, 1)][3][0] == 0 and out[(name, 1)][3][1] > 0
         assert out[(name, 2)][3][0] >= out[(name, 3)][3][0]  # doubling needs at least as many rounds as quadrupling
-        for mode in (1, 2, 3, 4, 5, 6):
+        for mode in (1, 2, 3, 4, 5, 6, 10):
             r, sa, lcp, _ = out[(name, mode)]
             assert np.array_equal(sa0, sa) and np.array_equal(lcp0, lcp), (name, mode)
             for a, b in zip(r0, r):
@@ -331,7 +332,7 @@ def test_gpu_randomized_sweep_all_paths(gpu_finder, seed0):
             rng = random.Random(1000 + seed)
             cases = [gen_case(rng, max_n=rng.choice([500, 1500, 6000]))[1] for _ in range(150)]
             oras = [oracle_run(s) for s in cases]
-            for mode in (0, 6, 4, 5):
+            for mode in (0, 6, 4, 5, 10):
                 gpu_finder.debug_rounds(mode)
                 res = gpu_finder.find_rotations_batch(cases, flags=1 if mode == 0 else 0)
                 for i, (r, o, s) in enumerate(zip(res, oras, cases)):
@@ -375,11 +376,12 @@ def test_gpu_one_process_several_gpus():
 def test_gpu_full_size_paths_agree(gpu_finder, name, nsets):
     """BASELINE.json's full sizes (80-100 M suffixes per batch), where the oracle is out of reach: the two independent
     ways to the suffix array -- rank doubling + LCP kernels, word sort with its own LCPs -- must give the same
-    rotations, suffix array, LCP array and block lists (they share only the first sort)"""
+    rotations, suffix array, LCP array and block lists (they share only the first sort); so must the word sort with a
+    column's order carried over to the next (10; what the free choice takes on the bacterial set) and without (11)"""
     batch = workload_batch(name, nsets, seed=1000)
     out = {}
     try:
-        for mode in (5, 6):
+        for mode in (5, 6, 10, 11):
             gpu_finder.debug_rounds(mode)
             gpu_finder.upload(batch)
             gpu_finder.run()
@@ -390,8 +392,9 @@ def test_gpu_full_size_paths_agree(gpu_finder, name, nsets):
     finally:
         gpu_finder.debug_rounds(0)
     assert (out[5][9] == 0).all()
-    for x, y in zip(out[5], out[6]):
-        assert np.array_equal(x, y)
+    for mode in (6, 10, 11):
+        for x, y in zip(out[5], out[mode]):
+            assert np.array_equal(x, y), mode
 
 
 @pytest.mark.parametrize("name", ["variants256", "bacterial"])
