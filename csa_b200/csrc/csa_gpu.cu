@@ -64,7 +64,7 @@ struct csa_gpu_ctx {
     double lcp_mean_sample = 0;
     int force_kasai = 0;
     int rounds_list = 0, round_mode = 0;
-    int carry_mode = 0; bool ws_carried = false; // carried word sort: 0 for sets of whole genomes, 1 always, 2 never
+    int carry_mode = 0; bool ws_carried = false, carry_pick = false; // carried word sort: 0 for sets of whole genomes, 1 always, 2 never
     int rounds_tiled = 0, rounds_global = 0, rounds_quad = 0, force_global_rounds = 0, no_quad_rounds = 0;
     DevMem pyr, pyr2, sa0, saidx0, leaf_set, lcp0;
     Seq0Q q0{};                 // sequence 0 of every set (stage_seq0)
@@ -501,17 +501,18 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     if (words) TRY(dev_fill_ff(ex, lcp, sizeof(u32) * (size_t)N));
     // group borders, heads, and what decides between the word sort and the doubling rounds -- the number of groups, the
     // largest one, the pairs they hold -- all queued, then ONE wait for the four numbers
-    unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs[2] = {0, 0};
+    unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs[3] = {0, 0, 0};
+    c->carry_pick = false;
     TRY(dev_zero(ex, counter, 4 * sizeof(u32)));
-    TRY(dev_zero(ex, pairs, 2 * sizeof(*pairs)));
+    TRY(dev_zero(ex, pairs, 3 * sizeof(*pairs)));
     { FlagArgs a{P<u64>(c->keysA), !any_other ? P<u32>(c->keysA) : nullptr, head, counter, words ? lcp : nullptr, letters, lbits,
                  P<u32>(c->valsA), P<u32>(c->seqof), P<u32>(c->seq_off), c->batch_nmin < (u32)letters ? 1 : 0, 0u}; launch_flag(ex, N, a); }
     { SetStartArgs a{view_of(c), head, counter, words ? lcp : nullptr}; launch_setstart(ex, c->nsets, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, head, head, N)));
     { MaxGroupArgs a{head, counter + 2, N, pairs}; launch_maxgroup(ex, N, a); }
     {
-        u32 hc[26];
-        TRY(d2h(ex, hc, counter, sizeof(hc))); // [0] groups, [2] largest group, [22..25] pairs, suffixes that share a group
+        u32 hc[28];
+        TRY(d2h(ex, hc, counter, sizeof(hc))); // [0] groups, [2] largest group, [22..27] pairs, suffixes that share a group, ... of no more than 32
         ngroups = hc[0]; maxg = hc[2];
         memcpy(hpairs, hc + 22, sizeof(hpairs));
     }
@@ -523,7 +524,12 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
         // measured: ~0.05 ns per pair; rank doubling + LCP ~0.2 ns per suffix while a set's ranks live in L2, ~0.55 ns when
         // they do not (one set of tens of millions of suffixes: every gather a trip to HBM)
         const double per_suffix = c->max_set_bases > WS_LARGE_SET ? WS_PAIRS_PER_SUFFIX_LARGE : WS_PAIRS_PER_SUFFIX;
-        if (phase == 0 && c->round_mode == 0 && !c->ws_force && (double)hpairs[0] > per_suffix * (double)N) words = false;
+        if (phase == 0 && c->round_mode == 0 && !c->ws_force && (double)hpairs[0] > per_suffix * (double)N) {
+            // many pairs = many near-identical sequences: every pair compared is too much, but when the groups fit a warp
+            // (dozens of sequences, not hundreds) a column's order carries over to the next and few pairs are compared at all
+            if (c->carry_mode == 0 && (double)hpairs[2] >= 0.9 * (double)hpairs[1]) c->carry_pick = true;
+            else words = false;
+        }
     }
     if (!words) { SetRankArgs r{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, r); }
     c->sa_ngroups = ngroups;
@@ -565,21 +571,36 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
                         nullptr, nullptr, 0u, nullptr, nullptr};
             // sets of whole genomes (millions of letters a sequence): what near-identical genomes share runs for hundreds of
             // letters, and a column's order carries over to the next (pipeline.cuh "carried word sort")
-            const bool carry = c->carry_mode == 1 || (c->carry_mode == 0 && c->max_set_bases > WS_LARGE_SET);
+            const bool carry = c->carry_mode == 1 || (c->carry_mode == 0 && (c->max_set_bases > WS_LARGE_SET || c->carry_pick));
             c->ws_carried = carry;
             if (carry) {
                 u32 *grp = rank, *head2 = rank2, *roots = P<u32>(c->keysA), *nroots = counter + 32;
                 unsigned char *flag = P<unsigned char>(c->keysB);
                 if (phase == 1) TRY(dev_fill_ff(ex, grp, sizeof(u32) * (size_t)N)); // (suffixes of other ranks' buckets: in no group)
                 TRY(dev_zero(ex, nroots, 2 * sizeof(u32)));
-                CarryArgs ca{v, P<u32>(c->valsA), head, head2, grp, flag, lo, hi};
+                static const bool direct = getenv("CSA_GPU_CYGRP_DIRECT") != nullptr; // (experiments)
+                const bool dealt = !direct && (c->carry_mode == 1 || c->max_set_bases > WS_LARGE_SET) && hi - lo > 1; // (sets of a few MB: their stretch of grp sits in L2 anyway)
+                CarryArgs ca{v, P<u32>(c->valsA), head, head2, grp, flag, lo, hi, dealt ? P<u32>(c->valsB) : nullptr};
                 launch_cygrp(ex, (long long)hi - lo, ca);
+                if (dealt) {
+                    u32 *k = P<u32>(c->valsA) + lo, *ka = P<u32>(c->sa), *vv = P<u32>(c->valsB), *va = P<u32>(c->t2);
+                    TRY(radix_sort_pairs<u32>(ex, c->ps, k, vv, ka, va, (long long)hi - lo, nbits > 8 ? nbits - 8 : 0, nbits));
+                    CyScatterArgs sc{k, vv, grp};
+                    launch_cyscatter(ex, (long long)hi - lo, sc);
+                    ca.gval = nullptr;
+                }
                 launch_cyroots(ex, (long long)hi - lo, ca);
+                u64 *list = P<u64>(c->keysA) + ((size_t)N + 1) / 2; // (behind the roots; at most N / 2 groups of two or more)
+                u32 *nlistA = counter + 34, *nlistB = counter + 36; // (each followed by its work counter)
+                TRY(dev_zero(ex, nlistA, 4 * sizeof(u32)));
+                { CyListArgs l{head2, flag, 1u, lo, hi, list, nlistA}; launch_cylist(ex, (long long)hi - lo, l); }
                 a.head_in = head2; a.flag = flag; a.want = 1u; a.roots = roots; a.nroots = nroots;
-                launch_wsort(ex, a);
+                launch_wsort_list(ex, a, list, nlistA);
                 CyWalkArgs w{v, P<u32>(c->valsA), head, lcp, head2, grp, flag, lo, hi, (u32)letters, roots, nroots, nroots + 1};
                 launch_cywalk(ex, w);
                 a.want = 0u; a.roots = nullptr; a.nroots = nullptr;
+                { CyListArgs l{head2, flag, 0u, lo, hi, list, nlistB}; launch_cylist(ex, (long long)hi - lo, l); }
+                launch_wsort_list(ex, a, list, nlistB);
                 if (getenv("CSA_GPU_TRACE")) {
                     std::vector<unsigned char> f((size_t)hi - lo);
                     std::vector<u32> h2((size_t)hi - lo);
@@ -591,8 +612,7 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
                     fprintf(stderr, "[csa] carried word sort: %zu groups ordered by letters (%u walks started), %zu written by the walks, %zu left to the sweep\n",
                             cnt[1], nr, cnt[2], cnt[0]);
                 }
-            }
-            launch_wsort(ex, a);
+            } else launch_wsort(ex, a);
             TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
             if (c->ws_left[5]) { // groups that did not fit a warp's window: one CTA each
                 a.nbig = c->ws_left[5];

@@ -1642,43 +1642,44 @@ MAP_KERNEL(tile, TileArgs, 8)
 
 // largest group of equal h-prefixes: the last suffix of a group is as far from its head as the group is long
 // (pairs != nullptr: also pairs[0] = the number of pairs of suffixes that share a group -- what the word sort would
-// compare -- and pairs[1] = the number of suffixes that share a group)
+// compare --, pairs[1] = the number of suffixes that share a group and pairs[2] = those of them whose group holds no more
+// than a warp has lanes, which the carried word sort can walk)
 struct MaxGroupArgs { const u32 *head; u32 *maxgroup; u32 N; unsigned long long *pairs; };
 #ifdef CSA_EMU
 HD void maxgroup_body(long long i, const MaxGroupArgs &a) {
     if ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1) {
         u32 sz = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
         if (sz > *a.maxgroup) *a.maxgroup = sz;
-        if (a.pairs) { a.pairs[0] += (unsigned long long)sz * (sz - 1) / 2; if (sz > 1) a.pairs[1] += sz; }
+        if (a.pairs) { a.pairs[0] += (unsigned long long)sz * (sz - 1) / 2; if (sz > 1) a.pairs[1] += sz; if (sz > 1 && sz <= 32) a.pairs[2] += sz; }
     }
 }
 MAP_KERNEL(maxgroup, MaxGroupArgs, 4)
 #else
 __global__ void __launch_bounds__(256) k_maxgroup(long long n, MaxGroupArgs a) {
     __shared__ u32 s_max;
-    __shared__ unsigned long long s_pairs, s_shared;
-    if (threadIdx.x == 0) { s_max = 0; s_pairs = 0; s_shared = 0; }
+    __shared__ unsigned long long s_pairs, s_shared, s_walk;
+    if (threadIdx.x == 0) { s_max = 0; s_pairs = 0; s_shared = 0; s_walk = 0; }
     __syncthreads();
     // a persistent grid: every thread folds many places (neighbouring lanes read neighbouring words)
-    u32 sz = 0, sh = 0;
+    u32 sz = 0, sh = 0, wk = 0;
     unsigned long long pr = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         if ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1) {
             const u32 z = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
             sz = z > sz ? z : sz;
-            if (z > 1) { pr += (unsigned long long)z * (z - 1) / 2; sh += z; }
+            if (z > 1) { pr += (unsigned long long)z * (z - 1) / 2; sh += z; if (z <= 32u) wk += z; }
         }
     }
     if (a.pairs) { // one atomic per CTA: same-address atomics serialise in L2
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { pr += __shfl_xor_sync(0xffffffffu, pr, d); sh += __shfl_xor_sync(0xffffffffu, sh, d); }
-        if ((threadIdx.x & 31) == 0 && pr) { atomicAdd(&s_pairs, pr); atomicAdd(&s_shared, (unsigned long long)sh); }
+        for (int d = 16; d > 0; d >>= 1) { pr += __shfl_xor_sync(0xffffffffu, pr, d); sh += __shfl_xor_sync(0xffffffffu, sh, d); wk += __shfl_xor_sync(0xffffffffu, wk, d); }
+        if ((threadIdx.x & 31) == 0 && pr) { atomicAdd(&s_pairs, pr); atomicAdd(&s_shared, (unsigned long long)sh); atomicAdd(&s_walk, (unsigned long long)wk); }
     }
     sz = __reduce_max_sync(0xffffffffu, sz);
     if ((threadIdx.x & 31) == 0 && sz) atomicMax(&s_max, sz);
     __syncthreads();
     if (threadIdx.x == 0 && s_max) atomicMax(a.maxgroup, s_max);
-    if (threadIdx.x == 0 && a.pairs && s_pairs) { atomicAdd(a.pairs, s_pairs); atomicAdd(a.pairs + 1, s_shared); }
+    if (threadIdx.x == 0 && a.pairs && s_pairs) { atomicAdd(a.pairs, s_pairs); atomicAdd(a.pairs + 1, s_shared); atomicAdd(a.pairs + 2, s_walk); }
 }
 static inline void launch_maxgroup(Exec &ex, long long n, MaxGroupArgs a) {
     if (n <= 0) return;
@@ -2726,6 +2727,9 @@ static inline void launch_bounds(Exec &ex, const BoundsArgs &a) { launch_bounds_
 #define CY_UNSET 0xFFFFFFFFu
 struct CarryArgs {
     BatchView v; const u32 *sa; const u32 *head; u32 *head2; u32 *grp; unsigned char *flag; u32 lo, hi;
+    u32 *gval; // nullptr: grp[suffix] written at once; else the value by place -- one set of tens of millions of suffixes:
+               // 4-byte stores all over a 320 MB array cost 2.9 ms, dealt by the top 8 bits of the suffix first (one
+               // radix pass) and stored then (k_cyscatter), every stretch of the array is filled while it sits in L2
 };
 HD bool cy_single(const u32 *h, u32 x, u32 hs, u32 hi) { return hs == x && (x + 1 >= hi || (h[x + 1] & 0x7FFFFFFFu) != hs); }
 HD bool cy_big(const u32 *h, u32 hs, u32 hi) { return (u64)hs + CY_MAXG < hi && (h[hs + CY_MAXG] & 0x7FFFFFFFu) == hs; }
@@ -2733,10 +2737,14 @@ HD void cygrp_body(long long i, const CarryArgs &a) {
     const u32 x = a.lo + (u32)i, hs = a.head[x] & 0x7FFFFFFFu;
     a.head2[x] = hs;
     const bool big = cy_big(a.head, hs, a.hi);
-    a.grp[a.sa[x]] = (big || cy_single(a.head, x, hs, a.hi)) ? CY_UNSET : hs;
+    const u32 val = (big || cy_single(a.head, x, hs, a.hi)) ? CY_UNSET : hs;
+    if (a.gval) a.gval[i] = val; else a.grp[a.sa[x]] = val;
     a.flag[x] = (big && hs == x) ? 1 : 0;
 }
 MAP_KERNEL(cygrp, CarryArgs, 17)
+struct CyScatterArgs { const u32 *suffix; const u32 *val; u32 *grp; };
+HD void cyscatter_body(long long i, const CyScatterArgs &a) { a.grp[a.suffix[i]] = a.val[i]; }
+MAP_KERNEL(cyscatter, CyScatterArgs, 12)
 // the group (first place) of the suffix one letter back round its sequence; *cut: the suffix stands at a multiple of CY_CUT
 HD u32 cy_parent(const CarryArgs &a, u32 s, bool *cut) {
     const u32 k = seq_of_few(a.v, s), st = LDG(a.v.seq_off + k), off = s - st;
@@ -2753,6 +2761,23 @@ HD void cyroots_body(long long i, const CarryArgs &a) {
     if (root) a.flag[hs] = 1;
 }
 MAP_KERNEL(cyroots, CarryArgs, 20)
+// the groups of two or more with flag == want, as a list (first place : size) -- the few that are ordered by letters
+struct CyListArgs { const u32 *head2; const unsigned char *flag; u32 want; u32 lo, hi; u64 *list; u32 *count; };
+HD void cylist_body(long long i, const CyListArgs &a) {
+    const u32 x = a.lo + (u32)i;
+    if (a.head2[x] != x || a.flag[x] != a.want || cy_single(a.head2, x, x, a.hi)) return;
+    u64 e = (u64)x + 2;
+    while (e < a.hi && e < (u64)x + CY_MAXG && a.head2[e] == x) e++;
+    if (e < a.hi && a.head2[e] == x) { // longer than a warp: gallop, then bisect
+        u64 lo = e, step = CY_MAXG;
+        while (lo + step < a.hi && a.head2[lo + step] == x) { lo += step; step *= 2; }
+        u64 hi = lo + step < a.hi ? lo + step : a.hi;
+        while (hi - lo > 1) { const u64 mid = (lo + hi) >> 1; if (a.head2[mid] == x) lo = mid; else hi = mid; }
+        e = hi;
+    }
+    a.list[ATOMIC_ADD(a.count, 1u)] = ((u64)x << 32) | (u32)(e - x);
+}
+MAP_KERNEL(cylist, CyListArgs, 5)
 
 struct CyWalkArgs {
     BatchView v; u32 *sa; u32 *head; u32 *lcp; const u32 *head2; const u32 *grp; unsigned char *flag;
@@ -2928,6 +2953,16 @@ static inline void launch_wsort(Exec &, const WSortArgs &a) {
             }
         }
         for (auto &gr : groups) emu_wsort_group(a, gr.first, gr.second, emu_wsort_lend(a, nmin), true);
+    }
+}
+// the groups of a list (k_cylist) instead of every group of [lo, hi)
+static inline void launch_wsort_list(Exec &, const WSortArgs &a, const u64 *list, const u32 *count) {
+    for (u32 i = 0; i < *count; i++) {
+        const u32 p = (u32)(list[i] >> 32), e = p + (u32)list[i];
+        if (e - p > WS_CAP) { a.big[a.res[5]++] = list[i]; continue; }
+        u32 nmin = 0xFFFFFFFFu;
+        for (u32 x = p; x < e; x++) { const u32 nm = a.v.set_nmin[a.v.seq_set[a.v.seqof[a.sa[x]]]]; if (nm < nmin) nmin = nm; }
+        emu_wsort_group(a, p, e, emu_wsort_lend(a, nmin), true);
     }
 }
 static inline void launch_wsort_big(Exec &, const WSortArgs &a) {
@@ -3239,6 +3274,51 @@ __global__ void __launch_bounds__(WS_BIG_WARPS * 32) k_wsort_big(WSortArgs a) {
     ws_pairs<MASKS, WS_BIG_WARPS>(a, s, tid, start, act, nmin < a.depth_cap ? nmin : a.depth_cap);
 }
 
+// the groups of a list (k_cylist), one warp a group, the warps fetching entries until the list is done
+template <bool MASKS>
+__global__ void __launch_bounds__(WS_WARPS * 32) k_wsort_list(WSortArgs a, const u64 *list, const u32 *count, u32 *next) {
+    __shared__ WsSmem<1> s_all[WS_WARPS];
+    const u32 lane = threadIdx.x & 31u;
+    WsSmem<1> &s = s_all[threadIdx.x >> 5];
+    const u32 n = *count;
+    for (;;) {
+        u32 i = 0;
+        if (lane == 0) i = atomicAdd(next, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) return;
+        const u64 desc = list[i];
+        const u32 start = (u32)(desc >> 32), size = (u32)desc;
+        if (size > (u32)WS_CAP) { if (lane == 0) a.big[atomicAdd(a.res + 5, 1u)] = desc; continue; }
+        bool act[WS_T];
+        u32 nmin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < WS_T; j++) {
+            const u32 t = lane + 32u * j;
+            act[j] = t < size;
+            if (act[j]) {
+                const u32 g = a.sa[start + t];
+                const u32 k = seq_of_few(a.v, g);
+                s.x[t] = LDG(a.v.dbl_off + k) + (g - LDG(a.v.seq_off + k));
+                s.g[t] = g;
+                s.seg[t] = 0;
+                s.end[t] = (unsigned short)size;
+                s.ct[t] = 0; s.best[t] = 0; s.clsz[t] = 0;
+                if (t == 0) nmin = LDG(a.v.set_nmin + LDG(a.v.seq_set + k)); // a group never leaves its set
+            }
+        }
+        nmin = __shfl_sync(0xffffffffu, nmin, 0);
+        __syncwarp();
+        ws_pairs<MASKS, 1>(a, s, lane, start, act, nmin < a.depth_cap ? nmin : a.depth_cap);
+        __syncwarp();
+    }
+}
+static inline void launch_wsort_list(Exec &ex, const WSortArgs &a, const u64 *list, const u32 *count) {
+    PROF_BEGIN(ex, a.roots ? "k_wsort_list(roots)" : "k_wsort_list(rest)", 0.0);
+    if (a.masks) k_wsort_list<true><<<148 * 4, WS_WARPS * 32, 0, ex.stream>>>(a, list, count, const_cast<u32 *>(count) + 1);
+    else k_wsort_list<false><<<148 * 4, WS_WARPS * 32, 0, ex.stream>>>(a, list, count, const_cast<u32 *>(count) + 1);
+    PROF_END(ex);
+    ex.launches++;
+}
 static inline void launch_wsort(Exec &ex, const WSortArgs &a) {
     if (a.hi <= a.lo) return;
     const u32 nwarps = (a.hi - (a.lo & ~31u) + WS_NOM - 1) / WS_NOM;
