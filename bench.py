@@ -234,6 +234,8 @@ def main():
         buckets = workload == "bacterial" and world > 1
         batch = workload_batch(workload, nsets, seed=1000 + (0 if buckets else rank))  # every rank its own sets
         rf = RotationFinder(device=local)
+        if os.environ.get("CSA_BENCH_MODE"):  # (experiments: csa_gpu_debug_rounds, one of the equivalent suffix-array paths forced)
+            rf.debug_rounds(int(os.environ["CSA_BENCH_MODE"]))
         stream = torch.cuda.current_stream()
         rf.set_stream(stream.cuda_stream)
         if buckets:

@@ -89,6 +89,7 @@ def _load(path):
     lib.csa_gpu_multi_ctx.restype = vp
     lib.csa_gpu_multi_batch_rotations.argtypes = [vp, i, ip, C.POINTER(C.c_char_p), ip, i, C.c_uint, ip, C.POINTER(SetInfo)]
     lib.csa_gpu_shard_begin.argtypes = [vp, i, i]
+    lib.csa_gpu_shard_advice.argtypes = [vp, i]
     lib.csa_gpu_shard_view.argtypes = [vp, C.POINTER(ShardInfo)]
     lib.csa_gpu_shard_finish.argtypes = [vp, i, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
     lib.csa_gpu_shard_blocks_begin.argtypes = [vp, C.c_uint, C.c_void_p]
@@ -196,6 +197,10 @@ class RotationFinder:
     # ---- one batch, the suffix-array stage sharded over the ranks of a job (csa_b200/shard.py drives it) ----
     def shard_begin(self, rank: int, nranks: int):
         self._check(self.lib.csa_gpu_shard_begin(self.ctx, rank, nranks))
+
+    def shard_advice(self, nranks: int) -> bool:
+        """does sharding the uploaded batch by buckets over nranks ranks pay (include/csa_gpu.h)?"""
+        return bool(self.lib.csa_gpu_shard_advice(self.ctx, nranks))
 
     def shard_view(self) -> ShardInfo:
         v = ShardInfo()

@@ -625,7 +625,12 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
 #ifndef CSA_EMU
             // every suffix's head in; per suffix of a group: sa in, sa + head + lcp out
             // (suffixes of a group: counted by k_maxgroup; a bucket's share of them when the stage is sharded)
-            if (ex.prof) for (auto &r : ex.prof->recs) if (!strcmp(r.name, "k_wsort")) r.bytes = (4.0 * N + 16.0 * c->ws_sharing) * ((double)(hi - lo) / N);
+            if (ex.prof) for (auto &r : ex.prof->recs) {
+                if (!strcmp(r.name, "k_wsort")) r.bytes = (4.0 * N + 16.0 * c->ws_sharing) * ((double)(hi - lo) / N);
+                // the walks: per suffix of a group its place in the group table in, sa + head + lcp out (the few groups ordered by
+                // letters are not told apart here: no count of them comes back to the host)
+                if (!strcmp(r.name, "k_cywalk")) r.bytes = 16.0 * (phase == 1 ? (double)(hi - lo) : c->ws_sharing);
+            }
 #endif
             c->ws_runs = 1;
         }
@@ -975,6 +980,25 @@ static int stage_chain(csa_gpu_ctx *c, const BatchView &v, int max_interval) {
 }
 
 // phase 0: the whole path; 1: up to this rank's bucket of the suffix array (csa_gpu_shard_begin); 2: the rest
+static void fold_profile(csa_gpu_ctx *c) { // the event pairs of this run into per-kernel sums
+#ifndef CSA_EMU
+    if (!c->ex.prof) return;
+    c->prof_sum.clear();
+    for (ProfRec &r : c->prof.recs) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        size_t j = 0;
+        while (j < c->prof_sum.size() && c->prof_sum[j].name != r.name) j++;
+        if (j == c->prof_sum.size()) c->prof_sum.push_back({r.name, 0, 0.0, 0.0});
+        c->prof_sum[j].launches++; c->prof_sum[j].ms += ms; c->prof_sum[j].bytes += r.bytes;
+    }
+    c->prof.recs.clear();
+    c->prof.pool_used = 0;
+#else
+    (void)c;
+#endif
+}
+
 static int run_phases(csa_gpu_ctx *c, int max_interval, unsigned flags, int phase) {
     if (!c) CSA_FAIL(CSA_GPU_EINVAL, "null context");
     if (!c->uploaded) CSA_FAIL(CSA_GPU_ESTATE, "csa_gpu_batch_run before csa_gpu_batch_upload");
@@ -1066,21 +1090,7 @@ static int run_phases(csa_gpu_ctx *c, int max_interval, unsigned flags, int phas
 #endif
     c->launches = ex.launches;
     c->ran = true;
-#ifndef CSA_EMU
-    if (ex.prof) { // fold the event pairs of this run into per-kernel sums
-        c->prof_sum.clear();
-        for (ProfRec &r : c->prof.recs) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, r.a, r.b);
-            size_t j = 0;
-            while (j < c->prof_sum.size() && c->prof_sum[j].name != r.name) j++;
-            if (j == c->prof_sum.size()) c->prof_sum.push_back({r.name, 0, 0.0, 0.0});
-            c->prof_sum[j].launches++; c->prof_sum[j].ms += ms; c->prof_sum[j].bytes += r.bytes;
-        }
-        c->prof.recs.clear();
-        c->prof.pool_used = 0;
-    }
-#endif
+    fold_profile(c);
     return CSA_GPU_OK;
 }
 
@@ -1095,6 +1105,12 @@ extern "C" int csa_gpu_shard_begin(csa_gpu_ctx *c, int rank, int nranks) {
     if (nranks < 1 || rank < 0 || rank >= nranks) CSA_FAIL(CSA_GPU_EINVAL, "bad rank %d of %d", rank, nranks);
     c->shard_rank = rank; c->shard_nranks = nranks; c->shard_sa_swapped = false;
     return run_phases(c, 0, 0, 1);
+}
+
+extern "C" int csa_gpu_shard_advice(csa_gpu_ctx *c, int nranks) {
+    if (!c || !c->uploaded) return 1;
+    const bool carried = c->nsets == 1 && c->carry_mode != 2 && c->max_set_bases > WS_LARGE_SET && !c->shard_full_sort;
+    return (!carried || nranks >= CSA_GPU_SHARD_MIN_RANKS) ? 1 : 0;
 }
 
 extern "C" int csa_gpu_shard_view(csa_gpu_ctx *c, csa_gpu_shard_info *out) {
@@ -1265,6 +1281,7 @@ extern "C" int csa_gpu_shard_blocks_finish(csa_gpu_ctx *c, int max_interval, uns
     c->launches = ex.launches;
     c->shard_phase = 0;
     c->ran = true;
+    fold_profile(c);
     return CSA_GPU_OK;
 }
 
@@ -1341,8 +1358,13 @@ extern "C" int csa_gpu_multi_batch_rotations(csa_gpu_multi *m, int nsets, const 
     const int R = (int)m->ctx.size();
     if (R == 1) return csa_gpu_batch_rotations(m->ctx[0], nsets, set_start, texts, textsizes, max_interval, flags, rotations, info);
     // every GPU: the whole batch, then its own bucket of the suffix array
+    TRY(csa_gpu_batch_upload(m->ctx[0], nsets, set_start, texts, textsizes));
+    if (!csa_gpu_shard_advice(m->ctx[0], R)) { // one set of whole genomes on few GPUs: one GPU's carried sort is the fastest way
+        TRY(csa_gpu_batch_run(m->ctx[0], max_interval, flags));
+        return csa_gpu_batch_download(m->ctx[0], rotations, info);
+    }
     TRY(multi_parallel(m, [&](int r) {
-        int rc = csa_gpu_batch_upload(m->ctx[r], nsets, set_start, texts, textsizes);
+        int rc = r ? csa_gpu_batch_upload(m->ctx[r], nsets, set_start, texts, textsizes) : 0;
         return rc ? rc : csa_gpu_shard_begin(m->ctx[r], r, R);
     }));
     std::vector<csa_gpu_shard_info> v(R);

@@ -2716,8 +2716,8 @@ static inline void launch_bounds(Exec &ex, const BoundsArgs &a) { launch_bounds_
 //   k_cygrp    grp[suffix] = first place of its group (unset: alone in its group, or the group holds more than a
 //              warp); snapshot of the heads (the walk reads borders while other warps rewrite heads)
 //   k_cyroots  flag[first place] = 1 for the groups that must be ordered afresh: a predecessor in another group or
-//              in none, or a suffix at a multiple of CY_CUT letters from its sequence's start (cuts the walks, so
-//              that ten thousand of them run side by side whatever the genomes share)
+//              in none, or its first suffix at a multiple of CY_CUT letters from its sequence's start (cuts the walks,
+//              so that ten thousand of them run side by side whatever the genomes share)
 //   k_wsort    (want = 1) orders the roots, lists those a walk can start from (<= 32 suffixes, no two still equal)
 //   k_cywalk   the walks; flag = 2 on every group written
 //   k_wsort    (want = 0) whatever no walk reached (descendants of roots with ties): as before, by letters
@@ -2756,7 +2756,7 @@ HD void cyroots_body(long long i, const CarryArgs &a) {
     if (cy_single(a.head2, x, hs, a.hi) || cy_big(a.head2, hs, a.hi)) return;
     bool cut, cut0;
     const u32 par = cy_parent(a, a.sa[x], &cut);
-    bool root = cut || par == CY_UNSET;
+    bool root = (cut && x == hs) || par == CY_UNSET; // (the cut: by the group's first suffix -- the smallest, the first sort is stable)
     if (!root && x != hs) root = par != cy_parent(a, a.sa[hs], &cut0);
     if (root) a.flag[hs] = 1;
 }
@@ -2806,7 +2806,11 @@ static inline void emu_cywalk_root(const CyWalkArgs &a, u32 hs) {
             const u32 G = a.grp[ln[rs].st + ln[rs].off], n = re - rs;
             bool ok = G != CY_UNSET && n >= 2;
             if (ok) ok = (u64)G + n >= a.hi || a.head2[G + n] != G;
-            for (u32 r = rs; r < re && ok; r++) if ((ln[r].off & (CY_CUT - 1u)) == 0u) ok = false;
+            if (ok) { // the cut: by the smallest suffix of the group
+                u32 first = rs;
+                for (u32 r = rs + 1; r < re; r++) if (ln[r].st + ln[r].off < ln[first].st + ln[first].off) first = r;
+                if ((ln[first].off & (CY_CUT - 1u)) == 0u) ok = false;
+            }
             if (ok) {
                 for (u32 r = rs; r < re; r++) {
                     const u32 place = G + (r - rs);
@@ -2849,14 +2853,20 @@ __global__ void __launch_bounds__(CY_WARPS * 32) k_cywalk(CyWalkArgs a) {
             // runs: lane r goes on with lane r - 1 when both are in the walk and still share L0 letters after j steps
             const bool cont = on && lane && ((onmask >> (lane - 1u)) & 1u) && l >= a.L0 + j;
             const u32 startmask = __ballot_sync(0xffffffffu, on && !cont);
-            const u32 cutmask = __ballot_sync(0xffffffffu, on && (off & (CY_CUT - 1u)) == 0u);
             bool ok = false;
-            u32 rs = 0;
+            u32 rs = 0, n = 0, runmask = 0;
+            bool cutme = false;
             if (on) {
                 rs = 31u - (u32)__clz((int)(startmask & (0xFFFFFFFFu >> (31u - lane))));
                 const u32 ends = (startmask | ~onmask) & (lane < 31u ? 0xFFFFFFFFu << (lane + 1u) : 0u);
-                const u32 re = ends ? (u32)__ffs((int)ends) - 1u : 32u, n = re - rs;
-                const u32 runmask = (re < 32u ? (1u << re) - 1u : 0xFFFFFFFFu) & (0xFFFFFFFFu << rs);
+                const u32 re = ends ? (u32)__ffs((int)ends) - 1u : 32u;
+                n = re - rs;
+                runmask = (re < 32u ? (1u << re) - 1u : 0xFFFFFFFFu) & (0xFFFFFFFFu << rs);
+                // the cut: by the smallest suffix of the run (the lanes of a run hold the same mask)
+                cutme = __reduce_min_sync(runmask, st + off) == st + off && (off & (CY_CUT - 1u)) == 0u;
+            }
+            const u32 cutmask = __ballot_sync(0xffffffffu, cutme);
+            if (on) {
                 ok = G != CY_UNSET && n >= 2u && !(cutmask & runmask);
                 if (ok) ok = (u64)G + n >= a.hi || LDG(a.head2 + G + n) != G; // the group holds nobody else
             }
@@ -3010,7 +3020,7 @@ template <int WARPS> struct WsSmem {
 // share bound the larger one's LCP from below (its predecessor is the smaller suffix it shares most
 // with).  Pairs that agree up to the depth limit count as equal (place by old order; the doubling rounds
 // finish them).  On entry: x, g, seg, end set and ct = best = clsz = 0 for every place with act[j].
-template <bool MASKS, int WARPS>
+template <bool MASKS, int WARPS, bool ROOTS = false>
 __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, const u32 tid, const u32 base,
                                          const bool (&act)[WS_T], const u32 Lmax) {
     typedef WsTeam<WARPS> Team;
@@ -3141,7 +3151,7 @@ __device__ __forceinline__ void ws_pairs(const WSortArgs &a, WsSmem<WARPS> &s, c
             const u32 t = tid + TT * j;
             a.sa[base + np[j]] = s.g[t];
             a.head[base + np[j]] = base + nh[j];
-            if (WARPS == 1 && a.roots && t == s.seg[t] && (u32)s.end[t] - t <= CY_MAXG) { // a walk can start here unless two are still equal
+            if (ROOTS && a.roots && t == s.seg[t] && (u32)s.end[t] - t <= CY_MAXG) { // a walk can start here unless two are still equal
                 bool ties = false;
                 for (u32 q = t; q < (u32)s.end[t]; q++) ties |= s.clsz[q] != 0u;
                 if (!ties) a.roots[atomicAdd(a.nroots, 1u)] = base + t;
@@ -3169,7 +3179,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
     if (r0_64 >= a.hi) return;
     const u32 r0 = (u32)r0_64, N = a.hi; // (heads beyond hi may be another rank's and not there yet: hi itself is a border)
     WsSmem<1> &s = s_all[warp];
-    const u32 *hin = ws_head_in(a);
+    const u32 *hin = a.head; // (the carried word sort takes its groups from a list: k_wsort_list)
     // ---- the window: heads of WS_CAP places, borders as a bit set ----
     u32 hv[WS_T], bw[WS_T];
 #pragma unroll
@@ -3201,7 +3211,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
             const u64 mid = (lo + hi) >> 1;
             if ((hin[mid] & 0x7FFFFFFFu) == hs) lo = mid; else hi = mid;
         }
-        if (lane == 0 && ws_taken(a, hs)) a.big[atomicAdd(a.res + 5, 1u)] = ((u64)hs << 32) | (u32)(hi - hs);
+        if (lane == 0) a.big[atomicAdd(a.res + 5, 1u)] = ((u64)hs << 32) | (u32)(hi - hs);
     }
     const u64 b0 = (u64)bw[0] | ((u64)bw[1] << 32), b1 = (u64)bw[2] | ((u64)bw[3] << 32);
     // ---- the suffixes of every group of two or more ----
@@ -3213,7 +3223,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
         act[j] = false;
         if (t >= tb && t < te) {
             const u32 hs = hv[j] - r0, he = ws_next_border(b0, b1, t);
-            act[j] = he - hs >= 2u && ws_taken(a, r0 + hs);
+            act[j] = he - hs >= 2u;
             s.seg[t] = (unsigned short)hs;
             s.end[t] = (unsigned short)he;
         }
@@ -3308,7 +3318,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort_list(WSortArgs a, const
         }
         nmin = __shfl_sync(0xffffffffu, nmin, 0);
         __syncwarp();
-        ws_pairs<MASKS, 1>(a, s, lane, start, act, nmin < a.depth_cap ? nmin : a.depth_cap);
+        ws_pairs<MASKS, 1, true>(a, s, lane, start, act, nmin < a.depth_cap ? nmin : a.depth_cap);
         __syncwarp();
     }
 }
@@ -3322,7 +3332,7 @@ static inline void launch_wsort_list(Exec &ex, const WSortArgs &a, const u64 *li
 static inline void launch_wsort(Exec &ex, const WSortArgs &a) {
     if (a.hi <= a.lo) return;
     const u32 nwarps = (a.hi - (a.lo & ~31u) + WS_NOM - 1) / WS_NOM;
-    PROF_BEGIN(ex, a.flag ? (a.want ? "k_wsort(roots)" : "k_wsort(rest)") : "k_wsort", 4.0 * a.N);
+    PROF_BEGIN(ex, "k_wsort", 4.0 * a.N);
     if (a.masks) k_wsort<true><<<(nwarps + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, ex.stream>>>(a);
     else k_wsort<false><<<(nwarps + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, ex.stream>>>(a);
     PROF_END(ex);

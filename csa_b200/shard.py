@@ -96,7 +96,7 @@ def _gather_var(dist, t, counts, width, dev):
     return torch.cat([allb[r * mx * width:r * mx * width + counts[r] * width] for r in range(len(counts))])
 
 
-last_path = None  # of the last run_bucket_sharded: "blocks" (block stages on every rank's own range) | "exchange"
+last_path = None  # of the last run_bucket_sharded: "blocks" (block stages on every rank's own range) | "exchange" | "replicas"
 
 
 def _run_blocks_sharded(finder, rank, world, dist, max_interval, flags, v, bounds, n, m, cuda):
@@ -157,7 +157,7 @@ def _run_blocks_sharded(finder, rank, world, dist, max_interval, flags, v, bound
 
 
 def run_bucket_sharded(finder: RotationFinder, rank: int, world: int, dist=None, max_interval: int = 2**31 - 1,
-                       flags: int = 0, cuda: bool = True, shard_blocks: bool = True):
+                       flags: int = 0, cuda: bool = True, shard_blocks: bool = True, respect_advice: bool = True):
     """The batch uploaded to `finder` on EVERY rank (the same batch), its suffix array built bucket by bucket:
     rank r orders the groups of bucket r (csa_gpu_shard_begin), the buckets -- suffix array, group heads, LCP --
     are broadcast from their owners over the job's process group (NCCL over NVLink on the GPU box, gloo in the
@@ -166,6 +166,13 @@ def run_bucket_sharded(finder: RotationFinder, rank: int, world: int, dist=None,
     rank as a single-GPU run.  Returns the bucket borders."""
     import torch
     global last_path
+    if world > 1 and respect_advice and os.environ.get("CSA_SHARD_ALWAYS") != "1" and not finder.shard_advice(world):
+        # one set of whole genomes on few ranks: every rank runs the whole set (the carried word sort on one GPU beats
+        # the bucket sorts of up to CSA_GPU_SHARD_MIN_RANKS - 1 ranks; include/csa_gpu.h csa_gpu_shard_advice)
+        last_path = "replicas"
+        finder.run(max_interval, flags)
+        n = finder._batch.nbases
+        return [0] + [n] * world
     last_path = "exchange"
     finder.shard_begin(rank, world)
     v = finder.shard_view()

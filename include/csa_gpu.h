@@ -160,6 +160,13 @@ typedef struct csa_gpu_shard_info {
     unsigned own_sort;            /* 1: this rank sorted only its own bucket (one set); 0: the first sort ran on every rank */
 } csa_gpu_shard_info;
 int csa_gpu_shard_begin(csa_gpu_ctx *ctx, int rank, int nranks);
+/* Does sharding the uploaded batch over nranks ranks by buckets pay?  1 yes, 0 no: ONE set of whole genomes is ordered
+ * on one GPU by carrying a column's order over to the next along the text (pipeline.cuh "carried word sort"), and the
+ * walks cross the buckets at every step -- a bucket's rank must order most of its groups letter by letter again.  That
+ * beats the one-GPU run only from CSA_GPU_SHARD_MIN_RANKS ranks on; below, every rank had better run the whole set
+ * (csa_gpu_batch_run; "replicas").  Batches of several sets always shard (no walk leaves its set's stretch). */
+#define CSA_GPU_SHARD_MIN_RANKS 6
+int csa_gpu_shard_advice(csa_gpu_ctx *ctx, int nranks);
 int csa_gpu_shard_view(csa_gpu_ctx *ctx, csa_gpu_shard_info *out);
 int csa_gpu_shard_finish(csa_gpu_ctx *ctx, int max_interval, unsigned flags, unsigned nleft, unsigned left_suffixes,
                          unsigned min_depth, unsigned max_group);
