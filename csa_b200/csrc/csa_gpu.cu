@@ -64,7 +64,7 @@ struct csa_gpu_ctx {
     double lcp_mean_sample = 0;
     int force_kasai = 0;
     int rounds_list = 0, round_mode = 0;
-    int carry_mode = 0; bool ws_carried = false, carry_pick = false; // carried word sort: 0 for sets of whole genomes, 1 always, 2 never
+    int carry_mode = 0; bool ws_carried = false, carry_pick = false, cy_nopack = false; // carried word sort: 0 for sets of whole genomes, 1 always, 2 never
     int rounds_tiled = 0, rounds_global = 0, rounds_quad = 0, force_global_rounds = 0, no_quad_rounds = 0;
     DevMem pyr, pyr2, sa0, saidx0, leaf_set, lcp0;
     Seq0Q q0{};                 // sequence 0 of every set (stage_seq0)
@@ -580,7 +580,8 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
                 TRY(dev_zero(ex, nroots, 2 * sizeof(u32)));
                 static const bool direct = getenv("CSA_GPU_CYGRP_DIRECT") != nullptr; // (experiments)
                 const bool dealt = !direct && (c->carry_mode == 1 || c->max_set_bases > WS_LARGE_SET) && hi - lo > 1; // (sets of a few MB: their stretch of grp sits in L2 anyway)
-                CarryArgs ca{v, P<u32>(c->valsA), head, head2, grp, flag, lo, hi, dealt ? P<u32>(c->valsB) : nullptr};
+                const int pack = (N < (1u << 27) && !c->cy_nopack) ? 1 : 0;
+                CarryArgs ca{v, P<u32>(c->valsA), head, head2, grp, flag, lo, hi, pack, dealt ? P<u32>(c->valsB) : nullptr};
                 launch_cygrp(ex, (long long)hi - lo, ca);
                 if (dealt) {
                     u32 *k = P<u32>(c->valsA) + lo, *ka = P<u32>(c->sa), *vv = P<u32>(c->valsB), *va = P<u32>(c->t2);
@@ -596,7 +597,7 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
                 { CyListArgs l{head2, flag, 1u, lo, hi, list, nlistA}; launch_cylist(ex, (long long)hi - lo, l); }
                 a.head_in = head2; a.flag = flag; a.want = 1u; a.roots = roots; a.nroots = nroots;
                 launch_wsort_list(ex, a, list, nlistA);
-                CyWalkArgs w{v, P<u32>(c->valsA), head, lcp, head2, grp, flag, lo, hi, (u32)letters, roots, nroots, nroots + 1};
+                CyWalkArgs w{v, P<u32>(c->valsA), head, lcp, head2, grp, pack, flag, lo, hi, (u32)letters, roots, nroots, nroots + 1};
                 launch_cywalk(ex, w);
                 a.want = 0u; a.roots = nullptr; a.nroots = nullptr;
                 { CyListArgs l{head2, flag, 0u, lo, hi, list, nlistB}; launch_cylist(ex, (long long)hi - lo, l); }
@@ -1427,8 +1428,9 @@ extern "C" int csa_gpu_debug_rounds(csa_gpu_ctx *c, int force_global, int rounds
         c->no_chain_big = force_global == 7; // 7: free choice, but long block lists walked by one thread (k_chain) as short ones are
         c->shard_full_sort = force_global == 8; // 8: sharded runs of one set sort the whole set on every rank (as batches of sets do)
         c->force_cover = force_global == 9;     // 9: free choice, blocks always through the cover array R[]
-        c->carry_mode = force_global == 10 ? 1 : force_global == 11 ? 2 : 0; // 10: word sort, carried, whatever the sets look like; 11: free choice, never carried
-        if (force_global == 10) c->ws_force = true;
+        c->carry_mode = force_global == 10 || force_global == 12 ? 1 : force_global == 11 ? 2 : 0; // 10: word sort, carried, whatever the sets look like; 11: free choice, never carried
+        c->cy_nopack = force_global == 12; // 12: as 10, with the group table laid out as for batches of 2^27 suffixes and more
+        if (force_global == 10 || force_global == 12) c->ws_force = true;
         if (force_global >= 6) c->round_mode = 0;
         c->force_global_rounds = force_global == 1; c->no_quad_rounds = force_global == 2; c->force_kasai = force_global == 2;
     }

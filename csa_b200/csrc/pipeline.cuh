@@ -2727,6 +2727,7 @@ static inline void launch_bounds(Exec &ex, const BoundsArgs &a) { launch_bounds_
 #define CY_UNSET 0xFFFFFFFFu
 struct CarryArgs {
     BatchView v; const u32 *sa; const u32 *head; u32 *head2; u32 *grp; unsigned char *flag; u32 lo, hi;
+    int pack;  // 1 (batches of < 2^27 suffixes): a grp entry = first place << 5 | size - 1, the walks need no second look at the heads
     u32 *gval; // nullptr: grp[suffix] written at once; else the value by place -- one set of tens of millions of suffixes:
                // 4-byte stores all over a 320 MB array cost 2.9 ms, dealt by the top 8 bits of the suffix first (one
                // radix pass) and stored then (k_cyscatter), every stretch of the array is filled while it sits in L2
@@ -2737,11 +2738,47 @@ HD void cygrp_body(long long i, const CarryArgs &a) {
     const u32 x = a.lo + (u32)i, hs = a.head[x] & 0x7FFFFFFFu;
     a.head2[x] = hs;
     const bool big = cy_big(a.head, hs, a.hi);
-    const u32 val = (big || cy_single(a.head, x, hs, a.hi)) ? CY_UNSET : hs;
+    u32 val = (big || cy_single(a.head, x, hs, a.hi)) ? CY_UNSET : hs;
+    if (a.pack && val != CY_UNSET) {
+        u32 e = x + 1;
+        while (e < a.hi && (a.head[e] & 0x7FFFFFFFu) == hs) e++; // (at most 31 steps: the group holds no more than 32)
+        val = (hs << 5) | (e - hs - 1u);
+    }
     if (a.gval) a.gval[i] = val; else a.grp[a.sa[x]] = val;
     a.flag[x] = (big && hs == x) ? 1 : 0;
 }
+#ifdef CSA_EMU
 MAP_KERNEL(cygrp, CarryArgs, 17)
+#else
+// the same; a group's end from the borders of the warp's 32 places and the 32 behind them (two ballots), no walk along the heads
+__global__ void __launch_bounds__(256) k_cygrp(long long n, CarryArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 lane = threadIdx.x & 31u;
+    const bool in = i < n;
+    const u64 x64 = (u64)a.lo + (u64)(in ? i : 0), y64 = x64 + 32u;
+    const u32 x = (u32)x64;
+    const u32 hs = in ? a.head[x] & 0x7FFFFFFFu : 0u;
+    const u32 hy = (in && y64 < a.hi) ? a.head[y64] & 0x7FFFFFFFu : 0u;
+    // border bits: place p starts a group (the end of the range counts as one)
+    const u64 b = (u64)__ballot_sync(0xffffffffu, !in || hs == x) | ((u64)__ballot_sync(0xffffffffu, !in || y64 >= a.hi || hy == (u32)y64) << 32);
+    if (!in) return;
+    a.head2[x] = hs;
+    const u64 above = b & (~0ull << (lane + 1u));
+    const u32 e = above ? x - lane + (u32)(__ffsll((long long)above) - 1) : x - lane + 64u; // first border behind x (at most 63 places on)
+    const bool big = e - hs > CY_MAXG, single = e - hs == 1u;
+    u32 val = (big || single) ? CY_UNSET : hs;
+    if (a.pack && val != CY_UNSET) val = (hs << 5) | (e - hs - 1u);
+    if (a.gval) a.gval[i] = val; else a.grp[a.sa[x]] = val;
+    a.flag[x] = (big && hs == x) ? 1 : 0;
+}
+static inline void launch_cygrp(Exec &ex, long long n, CarryArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_cygrp", 17.0 * n);
+    k_cygrp<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
 struct CyScatterArgs { const u32 *suffix; const u32 *val; u32 *grp; };
 HD void cyscatter_body(long long i, const CyScatterArgs &a) { a.grp[a.suffix[i]] = a.val[i]; }
 MAP_KERNEL(cyscatter, CyScatterArgs, 12)
@@ -2751,6 +2788,7 @@ HD u32 cy_parent(const CarryArgs &a, u32 s, bool *cut) {
     *cut = (off & (CY_CUT - 1u)) == 0u;
     return a.grp[off ? s - 1u : LDG(a.v.seq_off + k + 1) - 1u];
 }
+#ifdef CSA_EMU
 HD void cyroots_body(long long i, const CarryArgs &a) {
     const u32 x = a.lo + (u32)i, hs = a.head2[x];
     if (cy_single(a.head2, x, hs, a.hi) || cy_big(a.head2, hs, a.hi)) return;
@@ -2761,6 +2799,30 @@ HD void cyroots_body(long long i, const CarryArgs &a) {
     if (root) a.flag[hs] = 1;
 }
 MAP_KERNEL(cyroots, CarryArgs, 20)
+#else
+// the same; "all predecessors in one group" as "every suffix's predecessor in the group of its neighbour's": the neighbour's
+// comes by a shuffle, only a warp's first lane fetches it
+__global__ void __launch_bounds__(256) k_cyroots(long long n, CarryArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 lane = threadIdx.x & 31u;
+    const bool in = i < n;
+    const u32 x = a.lo + (u32)(in ? i : 0), hs = in ? a.head2[x] : 0xFFFFFFFEu;
+    const bool take = in && !cy_single(a.head2, x, hs, a.hi) && !cy_big(a.head2, hs, a.hi);
+    bool cut = false, cut0;
+    const u32 par = take ? cy_parent(a, a.sa[x], &cut) : CY_UNSET;
+    u32 prev = __shfl_up_sync(0xffffffffu, par, 1);
+    if (take && x != hs && lane == 0) prev = cy_parent(a, a.sa[x - 1], &cut0); // (x - 1 is of the same group: not alone, not big)
+    const bool root = take && ((cut && x == hs) || par == CY_UNSET || (x != hs && par != prev));
+    if (root) a.flag[hs] = 1;
+}
+static inline void launch_cyroots(Exec &ex, long long n, CarryArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_cyroots", 20.0 * n);
+    k_cyroots<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
 // the groups of two or more with flag == want, as a list (first place : size) -- the few that are ordered by letters
 struct CyListArgs { const u32 *head2; const unsigned char *flag; u32 want; u32 lo, hi; u64 *list; u32 *count; };
 HD void cylist_body(long long i, const CyListArgs &a) {
@@ -2780,7 +2842,7 @@ HD void cylist_body(long long i, const CyListArgs &a) {
 MAP_KERNEL(cylist, CyListArgs, 5)
 
 struct CyWalkArgs {
-    BatchView v; u32 *sa; u32 *head; u32 *lcp; const u32 *head2; const u32 *grp; unsigned char *flag;
+    BatchView v; u32 *sa; u32 *head; u32 *lcp; const u32 *head2; const u32 *grp; int pack; unsigned char *flag;
     u32 lo, hi, L0; const u32 *roots; const u32 *nroots; u32 *next; // next: the walks' work counter (zeroed)
 };
 #ifdef CSA_EMU
@@ -2803,9 +2865,10 @@ static inline void emu_cywalk_root(const CyWalkArgs &a, u32 hs) {
             if (!ln[rs].on) { rs++; continue; }
             u32 re = rs + 1;
             while (re < g && ln[re].on && ln[re].lcp >= a.L0 + j) re++;
-            const u32 G = a.grp[ln[rs].st + ln[rs].off], n = re - rs;
-            bool ok = G != CY_UNSET && n >= 2;
-            if (ok) ok = (u64)G + n >= a.hi || a.head2[G + n] != G;
+            const u32 gv = a.grp[ln[rs].st + ln[rs].off], n = re - rs;
+            const u32 G = (a.pack && gv != CY_UNSET) ? gv >> 5 : gv;
+            bool ok = gv != CY_UNSET && n >= 2;
+            if (ok) ok = a.pack ? n == (gv & 31u) + 1u : ((u64)G + n >= a.hi || a.head2[G + n] != G);
             if (ok) { // the cut: by the smallest suffix of the group
                 u32 first = rs;
                 for (u32 r = rs + 1; r < re; r++) if (ln[r].st + ln[r].off < ln[first].st + ln[first].off) first = r;
@@ -2845,11 +2908,15 @@ __global__ void __launch_bounds__(CY_WARPS * 32) k_cywalk(CyWalkArgs a) {
             l = lane ? a.lcp[hs + lane] : 0u;
         }
         bool on = mine;
+        off = off + 1u == len ? 0u : off + 1u;
+        u32 gnext = on ? LDG(a.grp + st + off) : CY_UNSET; // (the entry of the next step is fetched a step ahead)
         for (u32 j = 1;; j++) {
             const u32 onmask = __ballot_sync(0xffffffffu, on);
             if (!onmask) break;
+            const u32 gv = gnext, pos = st + off;
             off = off + 1u == len ? 0u : off + 1u;
-            const u32 G = on ? LDG(a.grp + st + off) : CY_UNSET;
+            gnext = on ? LDG(a.grp + st + off) : CY_UNSET;
+            const u32 G = (a.pack && gv != CY_UNSET) ? gv >> 5 : gv;
             // runs: lane r goes on with lane r - 1 when both are in the walk and still share L0 letters after j steps
             const bool cont = on && lane && ((onmask >> (lane - 1u)) & 1u) && l >= a.L0 + j;
             const u32 startmask = __ballot_sync(0xffffffffu, on && !cont);
@@ -2863,16 +2930,16 @@ __global__ void __launch_bounds__(CY_WARPS * 32) k_cywalk(CyWalkArgs a) {
                 n = re - rs;
                 runmask = (re < 32u ? (1u << re) - 1u : 0xFFFFFFFFu) & (0xFFFFFFFFu << rs);
                 // the cut: by the smallest suffix of the run (the lanes of a run hold the same mask)
-                cutme = __reduce_min_sync(runmask, st + off) == st + off && (off & (CY_CUT - 1u)) == 0u;
+                cutme = __reduce_min_sync(runmask, pos) == pos && ((pos - st) & (CY_CUT - 1u)) == 0u;
             }
             const u32 cutmask = __ballot_sync(0xffffffffu, cutme);
             if (on) {
-                ok = G != CY_UNSET && n >= 2u && !(cutmask & runmask);
-                if (ok) ok = (u64)G + n >= a.hi || LDG(a.head2 + G + n) != G; // the group holds nobody else
+                ok = gv != CY_UNSET && n >= 2u && !(cutmask & runmask);
+                if (ok) ok = a.pack ? n == (gv & 31u) + 1u : ((u64)G + n >= a.hi || LDG(a.head2 + G + n) != G); // the group holds nobody else
             }
             if (ok) {
                 const u32 place = G + (lane - rs);
-                a.sa[place] = st + off;
+                a.sa[place] = pos;
                 a.head[place] = place;
                 if (lane > rs) a.lcp[place] = l - j; else a.flag[G] = 2;
             }

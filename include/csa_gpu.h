@@ -218,7 +218,8 @@ int csa_gpu_multi_batch_rotations(csa_gpu_multi *m, int nsets, const int *set_st
  * lists chained by the literal one-thread walk; 8 free choice, sharded runs of one set sort the whole set on every
  * rank; 9 free choice, blocks always found through the cover array (as when the counts are asked for); 10 word sort
  * with the order of a column carried over to the next (what sets of whole genomes take) whatever the sets look like;
- * 11 free choice, but the word sort never carried.  rounds[0..1] = rounds of the last run on the tile/list/word-sort paths and on the device-wide path */
+ * 11 free choice, but the word sort never carried; 12 as 10 with the group table laid out as for batches of 2^27
+ * suffixes and more.  rounds[0..1] = rounds of the last run on the tile/list/word-sort paths and on the device-wide path */
 int csa_gpu_debug_rounds(csa_gpu_ctx *ctx, int mode, int rounds[2]);
 /* per-kernel profile: with it enabled every launch of the next runs is bracketed by CUDA events on
  * the run's stream; after a run row i gives the kernel's name, its launches, their summed device

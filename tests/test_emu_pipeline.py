@@ -73,6 +73,8 @@ def test_emu_both_round_paths(emu_finder):
         assert emu_finder.debug_rounds()[0] > 0
         emu_finder.debug_rounds(10)   # the word sort, a column's order carried over to the next
         res_c = emu_finder.find_rotations_batch(sets)
+        emu_finder.debug_rounds(12)   # ... with the group table of very large batches
+        res_c2 = emu_finder.find_rotations_batch(sets)
         emu_finder.debug_rounds(0)
         res_0 = emu_finder.find_rotations_batch(sets)
     finally:
@@ -81,6 +83,7 @@ def test_emu_both_round_paths(emu_finder):
         o = oracle_run(s)
         compare_with_oracle(r0, o, s, f"free choice set {i}")
         compare_with_oracle(cw, o, s, f"carried word sort set {i}")
+        compare_with_oracle(res_c2[i], o, s, f"carried word sort, unpacked group table, set {i}")
         compare_with_oracle(w, o, s, f"word sort set {i}")
         compare_with_oracle(w4, o, s, f"word sort stopped early, then group lists set {i}")
         compare_with_oracle(a, o, s, f"group-list path set {i}")

@@ -185,7 +185,7 @@ def test_gpu_tile_rounds_equal_device_wide_rounds(gpu_finder):
             # with doubling only (+ text-order LCP), 1 device-wide rounds only
             # 6 word sort whatever the groups look like (0 picks it only for small groups); 10 the same, a column's order
             # carried over to the next (what sets of whole genomes take)
-            for mode in (0, 6, 5, 4, 3, 2, 1, 10):
+            for mode in (0, 6, 5, 4, 3, 2, 1, 10, 12):
                 gpu_finder.debug_rounds(mode)
                 res = gpu_finder.find_rotations_batch(batch)
                 sa, lcp = gpu_finder.suffix_array()
@@ -197,7 +197,7 @@ def test_gpu_tile_rounds_equal_device_wide_rounds(gpu_finder):
         assert rounds0[0] > 0
         assert out[(name, 1)][3][0] == 0 and out[(name, 1)][3][1] > 0
         assert out[(name, 2)][3][0] >= out[(name, 3)][3][0]  # doubling needs at least as many rounds as quadrupling
-        for mode in (1, 2, 3, 4, 5, 6, 10):
+        for mode in (1, 2, 3, 4, 5, 6, 10, 12):
             r, sa, lcp, _ = out[(name, mode)]
             assert np.array_equal(sa0, sa) and np.array_equal(lcp0, lcp), (name, mode)
             for a, b in zip(r0, r):
@@ -332,7 +332,7 @@ def test_gpu_randomized_sweep_all_paths(gpu_finder, seed0):
             rng = random.Random(1000 + seed)
             cases = [gen_case(rng, max_n=rng.choice([500, 1500, 6000]))[1] for _ in range(150)]
             oras = [oracle_run(s) for s in cases]
-            for mode in (0, 6, 4, 5, 10):
+            for mode in (0, 6, 4, 5, 10, 12):
                 gpu_finder.debug_rounds(mode)
                 res = gpu_finder.find_rotations_batch(cases, flags=1 if mode == 0 else 0)
                 for i, (r, o, s) in enumerate(zip(res, oras, cases)):
