@@ -46,11 +46,11 @@ rank, world = dist.get_rank(), dist.get_world_size()
 rng = random.Random(77)
 rf = RotationFinder(lib_path=EMU_LIB)
 taken = {"blocks": 0, "exchange": 0}
-for trial in range(20):
+for trial in range(24):
     # trials 0-3: ONE set (every rank sorts only its own bucket of key prefixes; trial 3: the whole set on every rank);
-    # later trials: batches of sets (first sort on every rank, buckets cut at group borders)
-    sets = [gen_case(rng, max_n=1500, kinds=KINDS if trial != 2 else ["contained", "periodic"])[1] for _ in range(1 if trial < 4 or trial >= 8 else rng.randint(2, 4))]
-    mode = 8 if trial == 3 else (4 if trial % 2 and trial < 8 else 10 if trial % 2 else 0)   # 10: the word sort carried from column to column   # 4: the bucket sorts stop early and leave groups to the doubling rounds
+    # trials 4-7 and 20-23: batches of sets (first sort on every rank, buckets cut at group borders; 20-23 with the carried word sort)
+    sets = [gen_case(rng, max_n=1500, kinds=KINDS if trial != 2 else ["contained", "periodic"])[1] for _ in range(1 if trial < 4 or 8 <= trial < 20 else rng.randint(2, 4))]
+    mode = 8 if trial == 3 else (4 if trial % 2 and trial < 8 else 10 if trial % 2 or trial >= 20 else 0)   # 10: the word sort carried from column to column   # 4: the bucket sorts stop early and leave groups to the doubling rounds
     rf.debug_rounds(mode)
     batch = Batch(sets)
     rf.upload(batch)
