@@ -40,14 +40,14 @@ struct csa_gpu_ctx {
     int nsets = 0;
     u32 M = 0, N = 0, N0 = 0, nmax = 0, n0max = 0, mmax = 0;
     u64 TW = 0; // words of the doubled text
-    std::vector<u32> h_seq_off, h_seq_set, h_set_seq0, h_set_base0, h_set_nmin, h_z0;
+    std::vector<u32> h_seq_off, h_seq_set, h_set_seq0, h_set_base0, h_set_nmin, h_seq_nmin, h_z0;
     std::vector<u64> h_dbl_off;
     // ---- results (host mirrors of the small arrays) ----
     std::vector<u32> h_set_nblocks, h_set_blk0, h_set_pos0, h_set_flags, h_set_nchains, h_set_cyclic;
     u32 B = 0, E = 0;
     long long launches = 0;
     // ---- device ----
-    DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, dbl_off, z0;
+    DevMem raw, code, seqof, p2, pm, seq_off, seq_set, set_seq0, set_base0, set_nmin, seq_nmin, dbl_off, z0;
     DevMem rs_start, rs_count, rs_cbase, rs_stride;
     u32 rs_nblocks = 0;
     DevMem keysA, keysB, valsA, valsB, sa, t0, t1, t2, t3, t4, t5, counter, tiles;
@@ -92,7 +92,7 @@ static BatchView view_of(csa_gpu_ctx *c) {
     v.nsets = c->nsets; v.M = c->M; v.N = c->N;
     v.seq_off = P<u32>(c->seq_off); v.seq_set = P<u32>(c->seq_set);
     v.set_seq0 = P<u32>(c->set_seq0); v.set_base0 = P<u32>(c->set_base0);
-    v.set_nmin = P<u32>(c->set_nmin); v.dbl_off = P<u64>(c->dbl_off);
+    v.set_nmin = P<u32>(c->set_nmin); v.seq_nmin = P<u32>(c->seq_nmin); v.dbl_off = P<u64>(c->dbl_off);
     v.seqof = P<u32>(c->seqof); v.code = P<unsigned char>(c->code);
     v.p2 = P<u64>(c->p2); v.pm = P<u32>(c->pm);
     return v;
@@ -157,7 +157,7 @@ extern "C" void csa_gpu_destroy(csa_gpu_ctx *c) {
     cudaStreamSynchronize(c->ex.stream);
 #endif
     DevMem *all[] = {&c->raw, &c->code, &c->seqof, &c->p2, &c->pm, &c->seq_off, &c->seq_set, &c->set_seq0, &c->set_base0,
-                     &c->set_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
+                     &c->set_nmin, &c->seq_nmin, &c->dbl_off, &c->z0, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sa, &c->t0, &c->t1,
                      &c->t2, &c->t3, &c->t4, &c->t5, &c->shard_bounds, &c->bk_hist, &c->chb_sets, &c->chb_evbase, &c->chb_events, &c->chb_work, &c->chb_redo, &c->counter, &c->tiles, &c->pyr, &c->pyr2, &c->rs_start, &c->rs_count, &c->rs_cbase, &c->rs_stride, &c->sa0, &c->saidx0, &c->leaf_set, &c->lcp0, &c->set_nblocks,
                      &c->set_blk0, &c->set_pos0, &c->set_flags, &c->set_nchains, &c->set_cyclic, &c->firstmax, &c->set_collected, &c->set_suffixfree, &c->set_neff, &c->seq_per, &c->rare_collected, &c->rare_suffixfree, &c->blk_lb,
                      &c->blk_depth, &c->blk_set, &c->order, &c->o_depth, &c->o_set, &c->o_pos, &c->elem_blk, &c->seghead,
@@ -253,6 +253,8 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     c->h_seq_off[M] = (u32)tot; c->h_dbl_off[M] = dbl;
     c->h_set_seq0[nsets] = (u32)M; c->h_set_base0[nsets] = (u32)tot; c->h_z0[nsets] = z;
     c->batch_nmin = *std::min_element(c->h_set_nmin.begin(), c->h_set_nmin.end());
+    c->h_seq_nmin.resize(M);
+    for (u32 k = 0; k < (u32)M; k++) c->h_seq_nmin[k] = c->h_set_nmin[c->h_seq_set[k]]; // (the same by sequence: one gather less in the word sort)
     c->max_set_bases = 0;
     for (int s = 0; s < nsets; s++) c->max_set_bases = std::max(c->max_set_bases, c->h_set_base0[s + 1] - c->h_set_base0[s]);
     c->N = (u32)tot; c->N0 = z; c->nmax = nmax; c->n0max = n0max; c->mmax = mmax; c->TW = dbl / 32 + 8; // (guard words: the word sort stages 5 words at a time and may read past the last sequence)
@@ -279,7 +281,7 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
     TRY(dev_alloc(c->p2, sizeof(u64) * c->TW)); TRY(dev_alloc(c->pm, sizeof(u32) * c->TW));
     TRY(dev_alloc(c->seq_off, sizeof(u32) * (M + 1))); TRY(dev_alloc(c->seq_set, sizeof(u32) * M));
     TRY(dev_alloc(c->set_seq0, sizeof(u32) * (nsets + 1))); TRY(dev_alloc(c->set_base0, sizeof(u32) * (nsets + 1)));
-    TRY(dev_alloc(c->set_nmin, sizeof(u32) * nsets)); TRY(dev_alloc(c->dbl_off, sizeof(u64) * (M + 1)));
+    TRY(dev_alloc(c->set_nmin, sizeof(u32) * nsets)); TRY(dev_alloc(c->seq_nmin, sizeof(u32) * M)); TRY(dev_alloc(c->dbl_off, sizeof(u64) * (M + 1)));
     TRY(dev_alloc(c->z0, sizeof(u32) * (nsets + 1)));
     TRY(h2d(ex, c->raw.p, src, N));
     std::vector<u32> bs, bc, bb, bt; // tile-blocks of the first (segmented) sort: none straddles a set
@@ -307,7 +309,8 @@ static int upload_common(csa_gpu_ctx *c, int nsets, const int *set_start, const 
         const Tab tabs[] = {
             {&c->seq_off, c->h_seq_off.data(), sizeof(u32) * (M + 1)}, {&c->seq_set, c->h_seq_set.data(), sizeof(u32) * M},
             {&c->set_seq0, c->h_set_seq0.data(), sizeof(u32) * (nsets + 1)}, {&c->set_base0, c->h_set_base0.data(), sizeof(u32) * (nsets + 1)},
-            {&c->set_nmin, c->h_set_nmin.data(), sizeof(u32) * nsets}, {&c->dbl_off, c->h_dbl_off.data(), sizeof(u64) * (M + 1)},
+            {&c->set_nmin, c->h_set_nmin.data(), sizeof(u32) * nsets}, {&c->seq_nmin, c->h_seq_nmin.data(), sizeof(u32) * M},
+            {&c->dbl_off, c->h_dbl_off.data(), sizeof(u64) * (M + 1)},
             {&c->z0, c->h_z0.data(), sizeof(u32) * (nsets + 1)},
             {&c->rs_start, bs.data(), sizeof(u32) * bs.size()}, {&c->rs_count, bc.data(), sizeof(u32) * bc.size()},
             {&c->rs_cbase, bb.data(), sizeof(u32) * bb.size()}, {&c->rs_stride, bt.data(), sizeof(u32) * bt.size()}};

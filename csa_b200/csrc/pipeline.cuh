@@ -29,6 +29,7 @@ struct BatchView {
     const u32 *set_seq0;       // [nsets+1] first sequence of set s
     const u32 *set_base0;      // [nsets+1] first base (== first SA index) of set s
     const u32 *set_nmin;       // [nsets] shortest sequence of set s
+    const u32 *seq_nmin;       // [M] the same by sequence: set_nmin[seq_set[k]]
     const u64 *dbl_off;        // [M+1] first base of sequence k in the doubled, packed text
     u32 *seqof;                // [N] sequence of base g
     unsigned char *code;       // [N] letter codes 0..4
@@ -69,14 +70,6 @@ HD u32 seq_of(const BatchView &v, u32 g) { return LDG(v.seqof + g); }
 HD u32 seq_of_few(const BatchView &v, u32 g) {
     if (v.M <= 64u) return upper_bound_u32(v.seq_off, v.M + 1, g) - 1;
     return LDG(v.seqof + g);
-}
-
-// The same for a suffix whose SA PLACE is known: the suffix array is laid out set by set, so the place gives the set (a
-// search in the sets' first places) and the set's own sequence starts give the sequence -- two short searches in tables
-// that sit in L1 instead of a 4-byte gather from an N-sized array
-HD u32 seq_of_in_set(const BatchView &v, u32 set, u32 g) {
-    const u32 q0 = LDG(v.set_seq0 + set), q1 = LDG(v.set_seq0 + set + 1);
-    return q0 + upper_bound_u32(v.seq_off + q0, q1 - q0 + 1u, g) - 1u;
 }
 
 // position h letters further round the circle
@@ -2791,8 +2784,8 @@ struct CyScatterArgs { const u32 *suffix; const u32 *val; u32 *grp; };
 HD void cyscatter_body(long long i, const CyScatterArgs &a) { a.grp[a.suffix[i]] = a.val[i]; }
 MAP_KERNEL(cyscatter, CyScatterArgs, 12)
 // the group (first place) of the suffix one letter back round its sequence; *cut: the suffix stands at a multiple of CY_CUT
-HD u32 cy_parent(const CarryArgs &a, u32 set, u32 s, bool *cut) {
-    const u32 k = seq_of_in_set(a.v, set, s), st = LDG(a.v.seq_off + k), off = s - st;
+HD u32 cy_parent(const CarryArgs &a, u32 s, bool *cut) {
+    const u32 k = seq_of_few(a.v, s), st = LDG(a.v.seq_off + k), off = s - st;
     *cut = (off & (CY_CUT - 1u)) == 0u;
     return a.grp[off ? s - 1u : LDG(a.v.seq_off + k + 1) - 1u];
 }
@@ -2801,10 +2794,9 @@ HD void cyroots_body(long long i, const CarryArgs &a) {
     const u32 x = a.lo + (u32)i, hs = a.head2[x];
     if (cy_single(a.head2, x, hs, a.hi) || cy_big(a.head2, hs, a.hi)) return;
     bool cut, cut0;
-    const u32 set = set_of_pos(a.v, x);
-    const u32 par = cy_parent(a, set, a.sa[x], &cut);
+    const u32 par = cy_parent(a, a.sa[x], &cut);
     bool root = (cut && x == hs) || par == CY_UNSET; // (the cut: by the group's first suffix -- the smallest, the first sort is stable)
-    if (!root && x != hs) root = par != cy_parent(a, set, a.sa[hs], &cut0);
+    if (!root && x != hs) root = par != cy_parent(a, a.sa[hs], &cut0);
     if (root) a.flag[hs] = 1;
 }
 MAP_KERNEL(cyroots, CarryArgs, 20)
@@ -2818,10 +2810,9 @@ __global__ void __launch_bounds__(256) k_cyroots(long long n, CarryArgs a) {
     const u32 x = a.lo + (u32)(in ? i : 0), hs = in ? a.head2[x] : 0xFFFFFFFEu;
     const bool take = in && !cy_single(a.head2, x, hs, a.hi) && !cy_big(a.head2, hs, a.hi);
     bool cut = false, cut0;
-    const u32 set = take ? set_of_pos(a.v, x) : 0u;
-    const u32 par = take ? cy_parent(a, set, a.sa[x], &cut) : CY_UNSET;
+    const u32 par = take ? cy_parent(a, a.sa[x], &cut) : CY_UNSET;
     u32 prev = __shfl_up_sync(0xffffffffu, par, 1);
-    if (take && x != hs && lane == 0) prev = cy_parent(a, set, a.sa[x - 1], &cut0); // (x - 1 is of the same group: not alone, not big)
+    if (take && x != hs && lane == 0) prev = cy_parent(a, a.sa[x - 1], &cut0); // (x - 1 is of the same group: not alone, not big)
     const bool root = take && ((cut && x == hs) || par == CY_UNSET || (x != hs && par != prev));
     if (root) a.flag[hs] = 1;
 }
@@ -2913,7 +2904,7 @@ __global__ void __launch_bounds__(CY_WARPS * 32) k_cywalk(CyWalkArgs a) {
         const bool mine = (u64)hs + lane < a.hi && a.head2[hs + lane] == hs; // (a root holds at most 32 suffixes)
         u32 st = 0, len = 1, off = 0, l = 0;
         if (mine) {
-            const u32 s = a.sa[hs + lane], k = seq_of_in_set(a.v, set_of_pos(a.v, hs), s);
+            const u32 s = a.sa[hs + lane], k = seq_of_few(a.v, s);
             st = LDG(a.v.seq_off + k); len = LDG(a.v.seq_off + k + 1) - st; off = s - st;
             l = lane ? a.lcp[hs + lane] : 0u;
         }
@@ -3312,26 +3303,23 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
         any |= act[j];
     }
     if (!__any_sync(0xffffffffu, any)) return;
-    // the suffixes, where they start in the packed text, the shortest sequence of their set.  The suffix array is laid out
-    // set by set: the set comes from the PLACE (one search in the sets' first places for the warp, the places behind the
-    // next set's first one search again) and the sequence from a search in that set's own sequence starts -- short tables that
-    // sit in L1 -- instead of suffix -> sequence -> set -> shortest, three dependent trips to L2/HBM per window
+    // the suffixes, where they start in the packed text, the shortest sequence of their set.  (Measured and dropped: the set
+    // from the PLACE and the sequence by a search in the set's own sequence starts instead of the gathers suffix -> sequence ->
+    // set -> shortest: the two searches' dependent L1 loads cost more than the gathers they save, 4.44 against 4.16 ms.)
     u32 gs[WS_T];
 #pragma unroll
     for (int j = 0; j < WS_T; j++) gs[j] = !act[j] ? 0u : j < 2 ? sv[j] : a.sa[r0 + lane + 32u * j];
-    const u32 set0 = set_of_pos(a.v, r0 + tb), next0 = LDG(a.v.set_base0 + set0 + 1);
     u32 nmin = 0xFFFFFFFFu;
 #pragma unroll
     for (int j = 0; j < WS_T; j++) {
         if (act[j]) {
             const u32 t = lane + 32u * j;
             const u32 g = gs[j];
-            const u32 set = r0 + t < next0 ? set0 : set_of_pos(a.v, r0 + t);
-            const u32 k = seq_of_in_set(a.v, set, g);
+            const u32 k = seq_of(a.v, g);
             s.x[t] = LDG(a.v.dbl_off + k) + (g - LDG(a.v.seq_off + k));
             s.g[t] = g;
             s.ct[t] = 0; s.best[t] = 0; s.clsz[t] = 0;
-            const u32 nm = LDG(a.v.set_nmin + set);
+            const u32 nm = LDG(a.v.seq_nmin + k);
             nmin = nm < nmin ? nm : nmin;
         }
     }
@@ -3370,7 +3358,7 @@ __global__ void __launch_bounds__(WS_BIG_WARPS * 32) k_wsort_big(WSortArgs a) {
             s.ct[t] = 0; s.best[t] = 0; s.clsz[t] = 0;
         }
     }
-    const u32 nmin = LDG(a.v.set_nmin + LDG(a.v.seq_set + seq_of(a.v, a.sa[start]))); // a group never leaves its set
+    const u32 nmin = LDG(a.v.seq_nmin + seq_of(a.v, a.sa[start])); // a group never leaves its set
     __syncthreads();
     ws_pairs<MASKS, WS_BIG_WARPS>(a, s, tid, start, act, nmin < a.depth_cap ? nmin : a.depth_cap);
 }
@@ -3390,7 +3378,6 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort_list(WSortArgs a, const
         const u64 desc = list[i];
         const u32 start = (u32)(desc >> 32), size = (u32)desc;
         if (size > (u32)WS_CAP) { if (lane == 0) a.big[atomicAdd(a.res + 5, 1u)] = desc; continue; }
-        const u32 set = set_of_pos(a.v, start);
         bool act[WS_T];
         u32 nmin = 0xFFFFFFFFu;
 #pragma unroll
@@ -3399,13 +3386,13 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort_list(WSortArgs a, const
             act[j] = t < size;
             if (act[j]) {
                 const u32 g = a.sa[start + t];
-                const u32 k = seq_of_in_set(a.v, set, g); // (a group never leaves its set)
+                const u32 k = seq_of_few(a.v, g);
                 s.x[t] = LDG(a.v.dbl_off + k) + (g - LDG(a.v.seq_off + k));
                 s.g[t] = g;
                 s.seg[t] = 0;
                 s.end[t] = (unsigned short)size;
                 s.ct[t] = 0; s.best[t] = 0; s.clsz[t] = 0;
-                if (t == 0) nmin = LDG(a.v.set_nmin + set);
+                if (t == 0) nmin = LDG(a.v.seq_nmin + k); // a group never leaves its set
             }
         }
         nmin = __shfl_sync(0xffffffffu, nmin, 0);
