@@ -604,7 +604,8 @@ __device__ __forceinline__ u32 set_of_pos_cta(const BatchView &v, long long i, u
     while (s + 1 < (u32)v.nsets && (u32)i >= LDG(v.set_base0 + s + 1)) s++;
     return s;
 }
-__global__ void __launch_bounds__(256) k_blockfind2(long long n, BlockFind2Args a) {
+#define BF2_THREADS 256 // (64-thread CTAs measured: 1.32 against 1.26 ms -- no tail to cut here)
+__global__ void __launch_bounds__(BF2_THREADS) k_blockfind2(long long n, BlockFind2Args a) {
     __shared__ u32 s_first;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(256) k_blockfind2(long long n, BlockFind2Args 
 static inline void launch_blockfind2(Exec &ex, long long n, BlockFind2Args a) {
     if (n <= 0) return;
     PROF_BEGIN(ex, "k_blockfind2", 12.0 * n);
-    k_blockfind2<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    k_blockfind2<<<(unsigned)((n + BF2_THREADS - 1) / BF2_THREADS), BF2_THREADS, 0, ex.stream>>>(n, a);
     PROF_END(ex);
     ex.launches++;
 }
@@ -2583,7 +2584,9 @@ static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
 #define WS_NOM 32    // SA places whose groups one warp takes
 #define WS_CAP 128   // suffixes a warp can hold
 #define WS_T 4
-#define WS_WARPS 8   // warps (= chunks) per CTA of k_wsort
+#define WS_WARPS 2   // warps (= chunks) per CTA of k_wsort: a CTA's registers and shared memory are free again only when its slowest
+                     // warp is done, and most warps find no group and leave at once -- 8 warps a CTA: 3.95 ms on the headline batch, 4: 3.64, 2: 3.42
+#define WSL_WARPS 8  // ... of k_wsort_list (every warp fetches groups until the list is done: no such tail)
 #define WS_BIG_WARPS 8
 #define WS_BIG_CAP (32 * WS_BIG_WARPS * WS_T)
 #define WS_STEP 4    // words (of 32 letters) a pair compares per round trip
@@ -3365,8 +3368,8 @@ __global__ void __launch_bounds__(WS_BIG_WARPS * 32) k_wsort_big(WSortArgs a) {
 
 // the groups of a list (k_cylist), one warp a group, the warps fetching entries until the list is done
 template <bool MASKS>
-__global__ void __launch_bounds__(WS_WARPS * 32) k_wsort_list(WSortArgs a, const u64 *list, const u32 *count, u32 *next) {
-    __shared__ WsSmem<1> s_all[WS_WARPS];
+__global__ void __launch_bounds__(WSL_WARPS * 32) k_wsort_list(WSortArgs a, const u64 *list, const u32 *count, u32 *next) {
+    __shared__ WsSmem<1> s_all[WSL_WARPS];
     const u32 lane = threadIdx.x & 31u;
     WsSmem<1> &s = s_all[threadIdx.x >> 5];
     const u32 n = *count;
@@ -3403,8 +3406,8 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort_list(WSortArgs a, const
 }
 static inline void launch_wsort_list(Exec &ex, const WSortArgs &a, const u64 *list, const u32 *count) {
     PROF_BEGIN(ex, a.roots ? "k_wsort_list(roots)" : "k_wsort_list(rest)", 0.0);
-    if (a.masks) k_wsort_list<true><<<148 * 4, WS_WARPS * 32, 0, ex.stream>>>(a, list, count, const_cast<u32 *>(count) + 1);
-    else k_wsort_list<false><<<148 * 4, WS_WARPS * 32, 0, ex.stream>>>(a, list, count, const_cast<u32 *>(count) + 1);
+    if (a.masks) k_wsort_list<true><<<148 * 4, WSL_WARPS * 32, 0, ex.stream>>>(a, list, count, const_cast<u32 *>(count) + 1);
+    else k_wsort_list<false><<<148 * 4, WSL_WARPS * 32, 0, ex.stream>>>(a, list, count, const_cast<u32 *>(count) + 1);
     PROF_END(ex);
     ex.launches++;
 }
