@@ -2581,7 +2581,7 @@ static inline void launch_refine_g(Exec &ex, const RefineGArgs &a) {
 // counting, then from ballots and popcounts): ~100 warp-synchronous passes per chunk with 2-3 % of the lanes
 // busy in the tail -- 18-25 ms on 64 sets of 32 sequences, 2.8-4.2 ms on 160 Mammals-shaped sets where this
 // takes 1.4.
-#define WS_NOM 32    // SA places whose groups one warp takes
+#define WS_NOM 64    // SA places whose groups one warp takes (32: a third of the lanes had no pair to compare on the headline batch)
 #define WS_CAP 128   // suffixes a warp can hold
 #define WS_T 4
 #define WS_WARPS 2   // warps (= chunks) per CTA of k_wsort: a CTA's registers and shared memory are free again only when its slowest
@@ -3264,20 +3264,19 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsort(WSortArgs a) {
         const u64 p = (u64)r0 + lane + 32u * j;
         bw[j] = __ballot_sync(0xffffffffu, p < N ? hv[j] == (u32)p : p == N);
     }
-    // starts that are this launch's: places in [lo, hi)
-    u32 mine = bw[0];
-    if (r0 < a.lo) mine &= ~0u << (a.lo - r0);
-    if (a.hi - r0 < 32u) mine &= (1u << (a.hi - r0)) - 1u;
+    // starts that are this launch's: places in [lo, hi) among the first WS_NOM = 64 of the window
+    static_assert(WS_NOM == 64, "a warp's own groups start in the first two border words");
+    u64 mine = (u64)bw[0] | ((u64)bw[1] << 32);
+    if (r0 < a.lo) mine &= ~0ull << (a.lo - r0);
+    if (a.hi - r0 < 64u) mine &= (1ull << (a.hi - r0)) - 1ull;
     if (mine == 0) return; // no group starts here
-    const u32 tb = (u32)__ffs((int)mine) - 1u;
+    const u32 tb = (u32)__ffsll((long long)mine) - 1u;
     u32 te;
-    if (a.hi - r0 < 32u) te = a.hi - r0; // hi is a border (or the end of the array)
-    else if (bw[1]) te = 32u + (u32)__ffs((int)bw[1]) - 1u;
+    if (a.hi - r0 < 64u) te = a.hi - r0; // hi is a border (or the end of the array)
     else if (bw[2]) te = 64u + (u32)__ffs((int)bw[2]) - 1u;
     else if (bw[3]) te = 96u + (u32)__ffs((int)bw[3]) - 1u;
-    else if (N - r0 < 32u) te = N - r0; // the array ends inside the first word: that end is the last border seen
     else { // the last group that starts here runs past the window: k_wsort_big's
-        te = 31u - (u32)__clz((int)bw[0]);
+        te = 63u - (u32)__clzll((long long)((u64)bw[0] | ((u64)bw[1] << 32)));
         // its length: gallop, then bisect (head[p] == its start for every place inside it)
         const u32 hs = r0 + te;
         u64 lo = (u64)r0 + WS_CAP - 1, step = WS_CAP; // lo is inside the group
