@@ -59,12 +59,12 @@ struct csa_gpu_ctx {
     DevMem bk_hist;
     DevMem shard_bounds; std::vector<u32> h_shard_bounds;
     DevMem chb_sets, chb_evbase, chb_events, chb_work, chb_redo;
-    bool use_cover = true; int force_cover = 0; // blocks through the cover array R[] (counts asked for, sets of > 64 sequences) or straight from the LCP array
+    bool use_cover = true; int force_cover = 0; // blocks through the cover array R[] (counts asked for, sets of > 256 sequences) or straight from the LCP array
     int no_chain_big = 0, chain_redone = 0; u32 ws_depth_cap = WS_DEPTH_CAP; u32 ws_left[6] = {0, 0, 0, 0, 0, 0};
     double lcp_mean_sample = 0;
     int force_kasai = 0;
     int rounds_list = 0, round_mode = 0;
-    int carry_mode = 0; bool ws_carried = false, carry_pick = false, cy_nopack = false; // carried word sort: 0 for sets of whole genomes, 1 always, 2 never
+    int carry_mode = 0; bool ws_carried = false, carry_pick = false, cy_nopack = false, carry_big = false; // carried word sort: 0 for sets of whole genomes, 1 always, 2 never
     int rounds_tiled = 0, rounds_global = 0, rounds_quad = 0, force_global_rounds = 0, no_quad_rounds = 0;
     DevMem pyr, pyr2, sa0, saidx0, leaf_set, lcp0;
     Seq0Q q0{};                 // sequence 0 of every set (stage_seq0)
@@ -504,18 +504,19 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
     if (words) TRY(dev_fill_ff(ex, lcp, sizeof(u32) * (size_t)N));
     // group borders, heads, and what decides between the word sort and the doubling rounds -- the number of groups, the
     // largest one, the pairs they hold -- all queued, then ONE wait for the four numbers
-    unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs[3] = {0, 0, 0};
+    unsigned long long *pairs = (unsigned long long *)(counter + 22), hpairs[4] = {0, 0, 0, 0};
     c->carry_pick = false;
+    c->carry_big = false;
     TRY(dev_zero(ex, counter, 4 * sizeof(u32)));
-    TRY(dev_zero(ex, pairs, 3 * sizeof(*pairs)));
+    TRY(dev_zero(ex, pairs, 4 * sizeof(*pairs)));
     { FlagArgs a{P<u64>(c->keysA), !any_other ? P<u32>(c->keysA) : nullptr, head, counter, words ? lcp : nullptr, letters, lbits,
                  P<u32>(c->valsA), P<u32>(c->seqof), P<u32>(c->seq_off), c->batch_nmin < (u32)letters ? 1 : 0, 0u}; launch_flag(ex, N, a); }
     { SetStartArgs a{view_of(c), head, counter, words ? lcp : nullptr}; launch_setstart(ex, c->nsets, a); }
     TRY((scan_u32<ScanMax, true>(ex, c->ps, head, head, N)));
     { MaxGroupArgs a{head, counter + 2, N, pairs}; launch_maxgroup(ex, N, a); }
     {
-        u32 hc[28];
-        TRY(d2h(ex, hc, counter, sizeof(hc))); // [0] groups, [2] largest group, [22..27] pairs, suffixes that share a group, ... of no more than 32
+        u32 hc[30];
+        TRY(d2h(ex, hc, counter, sizeof(hc))); // [0] groups, [2] largest group, [22..29] pairs, suffixes that share a group, ... of no more than 32, ... than 256
         ngroups = hc[0]; maxg = hc[2];
         memcpy(hpairs, hc + 22, sizeof(hpairs));
     }
@@ -530,9 +531,13 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
         if (phase == 0 && c->round_mode == 0 && !c->ws_force && (double)hpairs[0] > per_suffix * (double)N) {
             // many pairs = many near-identical sequences: every pair compared is too much, but when the groups fit a warp
             // (dozens of sequences, not hundreds) a column's order carries over to the next and few pairs are compared at all
+            // (hundreds: a CTA per group walks)
             if (c->carry_mode == 0 && (double)hpairs[2] >= 0.9 * (double)hpairs[1]) c->carry_pick = true;
+            else if (c->carry_mode == 0 && c->max_set_bases <= WS_LARGE_SET && (double)hpairs[3] >= 0.9 * (double)hpairs[1]) c->carry_pick = c->carry_big = true;
             else words = false;
         }
+        // (forced, tests: whatever the largest group asks for)
+        if (phase == 0 && c->carry_mode == 1 && c->max_set_bases <= WS_LARGE_SET && maxg > CY_MAXG) c->carry_big = true;
     }
     if (!words) { SetRankArgs r{P<u32>(c->valsA), head, rank}; launch_setrank(ex, N, r); }
     c->sa_ngroups = ngroups;
@@ -571,20 +576,23 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
             TRY(h2d(ex, res, init, sizeof(init)));
             const u32 lo = phase == 1 ? c->h_shard_bounds[c->shard_rank] : 0u, hi = phase == 1 ? c->h_shard_bounds[c->shard_rank + 1] : N;
             WSortArgs a{v, P<u32>(c->valsA), head, lcp, N, lo, hi, (u32)letters, c->ws_depth_cap, (int)any_other, glist[0], glist[1], 0u, res,
-                        nullptr, nullptr, 0u, nullptr, nullptr};
+                        nullptr, nullptr, 0u, nullptr, nullptr, CY_MAXG, nullptr, nullptr, 0u};
             // sets of whole genomes (millions of letters a sequence): what near-identical genomes share runs for hundreds of
             // letters, and a column's order carries over to the next (pipeline.cuh "carried word sort")
             const bool carry = c->carry_mode == 1 || (c->carry_mode == 0 && (c->max_set_bases > WS_LARGE_SET || c->carry_pick));
             c->ws_carried = carry;
             if (carry) {
                 u32 *grp = rank, *head2 = rank2, *roots = P<u32>(c->keysA), *nroots = counter + 32;
+                const bool cybig = carry && c->carry_big && phase == 0; // groups of up to CY_BIGG walked (a CTA each)
+                u32 *roots2 = roots + (size_t)N / 2 + 1, *nroots2 = counter + 38; // (at most N / 2 roots, N / 33 of them long ones)
                 unsigned char *flag = P<unsigned char>(c->keysB);
                 if (phase == 1) TRY(dev_fill_ff(ex, grp, sizeof(u32) * (size_t)N)); // (suffixes of other ranks' buckets: in no group)
                 TRY(dev_zero(ex, nroots, 2 * sizeof(u32)));
+                TRY(dev_zero(ex, nroots2, 2 * sizeof(u32)));
                 static const bool direct = getenv("CSA_GPU_CYGRP_DIRECT") != nullptr; // (experiments)
                 const bool dealt = !direct && (c->carry_mode == 1 || c->max_set_bases > WS_LARGE_SET) && hi - lo > 1; // (sets of a few MB: their stretch of grp sits in L2 anyway)
-                const int pack = (N < (1u << 27) && !c->cy_nopack) ? 1 : 0;
-                CarryArgs ca{v, P<u32>(c->valsA), head, head2, grp, flag, lo, hi, pack, dealt ? P<u32>(c->valsB) : nullptr};
+                const int pack = (N < (1u << 27) && !c->cy_nopack && !cybig) ? 1 : 0;
+                CarryArgs ca{v, P<u32>(c->valsA), head, head2, grp, flag, lo, hi, pack, dealt ? P<u32>(c->valsB) : nullptr, cybig ? CY_BIGG : CY_MAXG};
                 launch_cygrp(ex, (long long)hi - lo, ca);
                 if (dealt) {
                     u32 *k = P<u32>(c->valsA) + lo, *ka = P<u32>(c->sa), *vv = P<u32>(c->valsB), *va = P<u32>(c->t2);
@@ -599,22 +607,34 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
                 TRY(dev_zero(ex, nlistA, 4 * sizeof(u32)));
                 { CyListArgs l{head2, flag, 1u, lo, hi, list, nlistA}; launch_cylist(ex, (long long)hi - lo, l); }
                 a.head_in = head2; a.flag = flag; a.want = 1u; a.roots = roots; a.nroots = nroots;
+                a.maxg = ca.maxg; a.roots2 = roots2; a.nroots2 = nroots2;
                 launch_wsort_list(ex, a, list, nlistA);
-                CyWalkArgs w{v, P<u32>(c->valsA), head, lcp, head2, grp, pack, flag, lo, hi, (u32)letters, roots, nroots, nroots + 1};
+                if (cybig) { // roots longer than a warp's window: one CTA each, BEFORE the walks (they start from these too)
+                    TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
+                    if (c->ws_left[5]) {
+                        a.nbig = c->ws_left[5];
+                        launch_wsort_big(ex, a);
+                        a.nbig = 0;
+                        TRY(dev_zero(ex, res + 5, sizeof(u32)));
+                    }
+                }
+                CyWalkArgs w{v, P<u32>(c->valsA), head, lcp, head2, grp, pack, flag, lo, hi, (u32)letters, roots, nroots, nroots + 1,
+                             roots2, nroots2, nroots2 + 1};
                 launch_cywalk(ex, w);
+                if (cybig) launch_cywalk_cta(ex, w);
                 a.want = 0u; a.roots = nullptr; a.nroots = nullptr;
                 { CyListArgs l{head2, flag, 0u, lo, hi, list, nlistB}; launch_cylist(ex, (long long)hi - lo, l); }
                 launch_wsort_list(ex, a, list, nlistB);
                 if (getenv("CSA_GPU_TRACE")) {
                     std::vector<unsigned char> f((size_t)hi - lo);
                     std::vector<u32> h2((size_t)hi - lo);
-                    u32 nr = 0;
+                    u32 nr = 0, nr2 = 0;
                     TRY(d2h(ex, f.data(), flag + lo, f.size())); TRY(d2h(ex, h2.data(), head2 + lo, sizeof(u32) * h2.size()));
-                    TRY(d2h(ex, &nr, nroots, sizeof(u32)));
+                    TRY(d2h(ex, &nr, nroots, sizeof(u32))); TRY(d2h(ex, &nr2, nroots2, sizeof(u32)));
                     size_t cnt[3] = {0, 0, 0};
                     for (size_t x = 0; x + 1 < f.size(); x++) if (h2[x] == lo + x && h2[x + 1] == lo + x) cnt[f[x] < 3 ? f[x] : 0]++;
-                    fprintf(stderr, "[csa] carried word sort: %zu groups ordered by letters (%u walks started), %zu written by the walks, %zu left to the sweep\n",
-                            cnt[1], nr, cnt[2], cnt[0]);
+                    fprintf(stderr, "[csa] carried word sort: %zu groups ordered by letters (%u + %u walks started), %zu written by the walks, %zu left to the sweep\n",
+                            cnt[1], nr, nr2, cnt[2], cnt[0]);
                 }
             } else launch_wsort(ex, a);
             TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
@@ -633,7 +653,8 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
                 if (!strcmp(r.name, "k_wsort")) r.bytes = (4.0 * N + 16.0 * c->ws_sharing) * ((double)(hi - lo) / N);
                 // the walks: per suffix of a group its place in the group table in, sa + head + lcp out (the few groups ordered by
                 // letters are not told apart here: no count of them comes back to the host)
-                if (!strcmp(r.name, "k_cywalk")) r.bytes = 16.0 * (phase == 1 ? (double)(hi - lo) : c->ws_sharing);
+                if (!strcmp(r.name, "k_cywalk") && !c->carry_big) r.bytes = 16.0 * (phase == 1 ? (double)(hi - lo) : c->ws_sharing);
+                if (!strcmp(r.name, "k_cywalk_cta")) r.bytes = 16.0 * c->ws_sharing; // (the warps' walks' share is not told apart)
             }
 #endif
             c->ws_runs = 1;
@@ -728,7 +749,7 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
 }
 
 // block candidates (collectNodes / removeSuffixNodes / removeNonUniqueNodes on ordinary sets): through the cover array R[]
-// when the counts are asked for or a set holds more than 64 sequences, else straight from the LCP array (k_blockfind2)
+// when the counts are asked for or a set holds more than 256 sequences, else straight from the LCP array (k_blockfind2)
 static int stage_common_blocks(csa_gpu_ctx *c, const BatchView &v) {
     Exec &ex = c->ex;
     u32 N = c->N;
@@ -1065,7 +1086,7 @@ static int run_phases(csa_gpu_ctx *c, int max_interval, unsigned flags, int phas
     { LeafScanArgs a{v, P<u32>(c->t5), P<u32>(c->set_flags), c->batch_nmin, 0u}; launch_leafscan(ex, N, a); }
     { RareCollapseArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->set_flags), P<u32>(c->t2), P<u32>(c->set_neff), P<u32>(c->seq_per)};
       launch_rarecollapse(ex, nsets, a); }
-    c->use_cover = (flags & CSA_GPU_FLAG_STATS) || c->mmax > 64 || c->force_cover;
+    c->use_cover = (flags & CSA_GPU_FLAG_STATS) || c->mmax > BF2_MAXM || c->force_cover;
     TRY(stage_common_blocks(c, v));
     TRY(stage_seq0(c, v));
     { RareBlocksArgs a{v, P<u32>(c->sa), P<u32>(c->t5), P<u32>(c->t1), c->use_cover ? 1 : 0, P<u32>(c->set_flags), P<u32>(c->set_neff), P<u32>(c->seq_per), P<u32>(c->t2),

@@ -170,3 +170,25 @@ def test_emu_one_process_several_gpus(ngpus):
         mf.first.debug_rounds(0)
         mf.close()
 
+
+
+def test_emu_carried_word_sort_groups_of_hundreds(emu_finder):
+    """sets of more than 32 near-identical sequences: the carried word sort walks groups of up to 256 suffixes (a CTA a root,
+    k_cywalk_cta) and the blocks come straight from the LCP array for up to 256 sequences (k_blockfind2) -- the free choice
+    and the forced carried sort give the suffix array and LCP array of the doubling rounds, and the oracle's answer"""
+    import numpy as np
+    from csa_b200.workloads import batch_sets, make_batch
+    for m, n, nsets, seed in ((40, 1500, 2, 1), (100, 1200, 1, 2)):
+        b = make_batch(nsets=nsets, m=m, n=n, snp=0.04, indel=0.004, seed=seed, population=True)
+        out = {}
+        try:
+            for mode in (5, 0, 10):
+                emu_finder.debug_rounds(mode)
+                res = emu_finder.find_rotations_batch(b)
+                out[mode] = (res,) + tuple(emu_finder.suffix_array())
+        finally:
+            emu_finder.debug_rounds(0)
+        for mode in (0, 10):
+            assert np.array_equal(out[5][1], out[mode][1]) and np.array_equal(out[5][2], out[mode][2]), (m, mode)
+        for i, (r, seqs) in enumerate(zip(out[0][0], batch_sets(b))):
+            compare_with_oracle(r, oracle_run(seqs), seqs, f"m={m} set {i}")
