@@ -2624,6 +2624,7 @@ struct WSortArgs {
     u32 maxg;                  // CY_MAXG, or CY_BIGG: then the groups of CY_MAXG + 1 .. CY_BIGG suffixes go to a list of their own
     u32 *roots2, *nroots2;
     u32 big_min;               // (k_wsort_big) entries of big of up to big_min suffixes are k_wsort_words' (0: none)
+    u32 list_cap;              // (k_wsort_list) groups of more suffixes than this go to big (0: WS_CAP, what a warp holds)
 };
 HD const u32 *ws_head_in(const WSortArgs &a) { return a.head_in ? a.head_in : a.head; }
 HD bool ws_taken(const WSortArgs &a, u32 start) { return !a.flag || a.flag[start] == a.want; }
@@ -3144,7 +3145,7 @@ static inline void launch_wsort(Exec &, const WSortArgs &a) {
 static inline void launch_wsort_list(Exec &, const WSortArgs &a, const u64 *list, const u32 *count) {
     for (u32 i = 0; i < *count; i++) {
         const u32 p = (u32)(list[i] >> 32), e = p + (u32)list[i];
-        if (e - p > WS_CAP) { a.big[a.res[5]++] = list[i]; continue; }
+        if (e - p > (a.list_cap ? a.list_cap : (u32)WS_CAP)) { a.big[a.res[5]++] = list[i]; continue; }
         u32 nmin = 0xFFFFFFFFu;
         for (u32 x = p; x < e; x++) { const u32 nm = a.v.set_nmin[a.v.seq_set[a.v.seqof[a.sa[x]]]]; if (nm < nmin) nmin = nm; }
         emu_wsort_group(a, p, e, emu_wsort_lend(a, nmin), true);
@@ -3478,15 +3479,16 @@ __global__ void __launch_bounds__(WS_BIG_WARPS * 32) k_wsort_big(WSortArgs a) {
 // them (counting, stable) and split, the LCP at every new border read off the two words.  g loads a round where all pairs
 // walk g^2/2 pairs: the roots of the carried word sort on sets of hundreds of near-identical sequences (8.4 -> 0.x ms).
 // Same places, heads, LCPs, left-over list and roots as ws_pairs.
-#define WSW_THREADS 256u
-template <bool ROOTS>
+#define WSW_SMALL 256u  // a CTA of this many threads for the groups of up to as many suffixes,
+#define WSW_LARGE 1024u // ... of this many for the longer ones (the same 12 letters twice in a genome)
+template <bool ROOTS, u32 WSW_THREADS>
 __global__ void __launch_bounds__(WSW_THREADS) k_wsort_words(WSortArgs a) {
     __shared__ u64 s_key[WSW_THREADS];
     __shared__ u32 s_flag[WSW_THREADS], s_bits[WSW_THREADS / 32u];
     const u32 tid = threadIdx.x;
     const u64 desc = a.big[blockIdx.x];
     const u32 start = (u32)(desc >> 32), g = (u32)desc;
-    if (g > WSW_THREADS) return; // k_wsort_big's
+    if (g > WSW_THREADS || (WSW_THREADS == WSW_LARGE && g <= WSW_SMALL)) return; // the other launch's (or k_wsort_big's)
     const bool have = tid < g;
     u64 x = 0;
     u32 suf = 0;
@@ -3572,7 +3574,7 @@ __global__ void __launch_bounds__(WSL_WARPS * 32) k_wsort_list(WSortArgs a, cons
         if (i >= n) return;
         const u64 desc = list[i];
         const u32 start = (u32)(desc >> 32), size = (u32)desc;
-        if (size > (u32)WS_CAP) { if (lane == 0) a.big[atomicAdd(a.res + 5, 1u)] = desc; continue; }
+        if (size > (a.list_cap ? a.list_cap : (u32)WS_CAP)) { if (lane == 0) a.big[atomicAdd(a.res + 5, 1u)] = desc; continue; }
         bool act[WS_T];
         u32 nmin = 0xFFFFFFFFu;
 #pragma unroll
@@ -3615,13 +3617,13 @@ static inline void launch_wsort(Exec &ex, const WSortArgs &a) {
 static inline void launch_wsort_big(Exec &ex, const WSortArgs &a0) {
     if (a0.nbig == 0) return;
     WSortArgs a = a0;
-    if (!a.masks) { // ACGT only: the groups of up to 256 word by word
-        a.big_min = WSW_THREADS;
+    if (!a.masks) { // ACGT only: the groups of up to 1024 word by word
+        a.big_min = WSW_LARGE;
         PROF_BEGIN(ex, a.roots ? "k_wsort_words(roots)" : "k_wsort_words", 0.0);
-        if (a.roots) k_wsort_words<true><<<a.nbig, WSW_THREADS, 0, ex.stream>>>(a);
-        else k_wsort_words<false><<<a.nbig, WSW_THREADS, 0, ex.stream>>>(a);
+        if (a.roots) { k_wsort_words<true, WSW_SMALL><<<a.nbig, WSW_SMALL, 0, ex.stream>>>(a); k_wsort_words<true, WSW_LARGE><<<a.nbig, WSW_LARGE, 0, ex.stream>>>(a); }
+        else { k_wsort_words<false, WSW_SMALL><<<a.nbig, WSW_SMALL, 0, ex.stream>>>(a); k_wsort_words<false, WSW_LARGE><<<a.nbig, WSW_LARGE, 0, ex.stream>>>(a); }
         PROF_END(ex);
-        ex.launches++;
+        ex.launches += 2;
     }
     PROF_BEGIN(ex, a.roots ? "k_wsort_big(roots)" : "k_wsort_big", 0.0);
     if (a.roots) { // (the carried word sort's roots of more than a warp's window: the walks start from them too)
