@@ -606,18 +606,22 @@ __device__ __forceinline__ u32 set_of_pos_cta(const BatchView &v, long long i, u
     while (s + 1 < (u32)v.nsets && (u32)i >= LDG(v.set_base0 + s + 1)) s++;
     return s;
 }
+#define BF2_COOP_M 16u // sets of more sequences than this: a lane reads the first BF2_SCAN LCPs of its window, the warp the rest
+#define BF2_SCAN 8u
 #define BF2_THREADS 256 // (64-thread CTAs measured: 1.32 against 1.26 ms -- no tail to cut here)
-__global__ void __launch_bounds__(BF2_THREADS) k_blockfind2(long long n, BlockFind2Args a) {
+template <bool COOP> // COOP: the batch holds sets of more than BF2_COOP_M sequences (two kernels: the other one keeps its 32 registers)
+__global__ void __launch_bounds__(BF2_THREADS, 8) k_blockfind2(long long n, BlockFind2Args a) {
     __shared__ u32 s_first;
     __shared__ u32 s_seen[BF2_THREADS / 32][BF2_MAXM / 32]; // (sets of more than 64 sequences: the sequences seen, a bit each)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const u32 lb = (u32)i + a.off;
     const u32 s = set_of_pos_cta(a.v, (i < n ? i : n - 1) + a.off, a.off, &s_first);
-    u32 m = 0, inner = 0;
+    u32 m = 0, inner = 0, outer1 = 0; // outer1: the larger lcp at the window's two borders + 1 (0: the set's range ends on both sides)
     bool cand = false;
     if (i < n) {
-        // every lane screens its own window with the LCP array alone: borders first, then the smallest lcp inside
+        // every lane screens its own window with the LCP array alone: borders first, then the smallest lcp inside (of a set of
+        // more than BF2_COOP_M sequences: the first BF2_SCAN of them -- the warp reads the rest together, below)
         const u32 s0 = LDG(a.v.set_base0 + s), s1 = LDG(a.v.set_base0 + s + 1);
         m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
         if (m >= 2 && lb + m <= s1) {
@@ -626,8 +630,10 @@ __global__ void __launch_bounds__(BF2_THREADS) k_blockfind2(long long n, BlockFi
             const long long outer_r = (rb + 1 == s1) ? -1 : (long long)a.lcp[rb + 1];
             if (outer_l < (long long)a.lcp[lb + 1] && outer_r < (long long)a.lcp[rb]) {
                 const long long outer = outer_l > outer_r ? outer_l : outer_r;
+                outer1 = (u32)(outer + 1);
                 inner = 0xFFFFFFFFu;
-                for (u32 j = lb + 1; j <= rb && (long long)inner > outer; j++) { const u32 l = a.lcp[j]; inner = l < inner ? l : inner; }
+                const u32 je = (COOP && m > BF2_COOP_M) ? lb + BF2_SCAN : rb;
+                for (u32 j = lb + 1; j <= je && (long long)inner > outer; j++) { const u32 l = a.lcp[j]; inner = l < inner ? l : inner; }
                 cand = (long long)inner > outer;
             }
         }
@@ -638,19 +644,35 @@ __global__ void __launch_bounds__(BF2_THREADS) k_blockfind2(long long n, BlockFi
         const int src = __ffs((int)todo) - 1;
         todo &= todo - 1;
         const u32 clb = __shfl_sync(0xffffffffu, lb, src), cm = __shfl_sync(0xffffffffu, m, src);
-        const u32 cinner = __shfl_sync(0xffffffffu, inner, src), cs = __shfl_sync(0xffffffffu, s, src);
+        u32 cinner = __shfl_sync(0xffffffffu, inner, src);
+        const u32 cs = __shfl_sync(0xffffffffu, s, src);
         const u32 crb = clb + cm - 1, q0 = LDG(a.v.set_seq0 + cs);
+        if (COOP && cm > BF2_COOP_M) { // the rest of the window's LCPs, a lane each
+            const u32 couter1 = __shfl_sync(0xffffffffu, outer1, src);
+            u32 l = 0xFFFFFFFFu;
+            for (u32 j = clb + 1u + BF2_SCAN + lane; j <= crb; j += 32) { const u32 x = a.lcp[j]; l = x < l ? x : l; }
+            l = __reduce_min_sync(0xffffffffu, l);
+            cinner = l < cinner ? l : cinner;
+            if ((int)lane == src) inner = cinner;
+            if ((u64)cinner + 1u <= (u64)couter1) continue; // no LCP interval after all
+        }
         u32 seen_lo = 0, seen_hi = 0, c0 = 0xFFu;
         bool same = true, twice = false;
         const bool wide = cm > 64u;
         u32 *seen = s_seen[threadIdx.x >> 5];
         if (wide) { if (lane < BF2_MAXM / 32u) seen[lane] = 0u; __syncwarp(); }
+        // (the sequences of a set are about as long as one another: where a suffix's sequence should stand if they were
+        // equally long, then a step or two -- one round of loads where a search takes log2(m) dependent ones)
+        const u32 b0 = LDG(a.v.seq_off + q0);
+        const float per = (float)cm / (float)(LDG(a.v.seq_off + q0 + cm) - b0);
         for (u32 j = clb + lane; j <= crb; j += 32) {
-            // the suffix's sequence by a search in the set's own few sequence starts, the letter before it from the packed
+            // the suffix's sequence from the set's own few sequence starts, the letter before it from the packed
             // text: both sit in L1/L2, where the gathers seqof[g] and code[g-1] go to HBM for every suffix of a batch
             const u32 g = a.sa[j];
-            u32 lo = q0, hi = q0 + cm;
-            while (hi - lo > 1u) { const u32 mid = (lo + hi) >> 1; if (LDG(a.v.seq_off + mid) <= g) lo = mid; else hi = mid; }
+            u32 lo = q0 + (u32)((float)(g - b0) * per);
+            lo = lo < q0 + cm ? lo : q0 + cm - 1u;
+            while (LDG(a.v.seq_off + lo) > g) lo--;      // (g is a suffix of this set: seq_off[q0] <= g < seq_off[q0 + cm])
+            while (LDG(a.v.seq_off + lo + 1) <= g) lo++;
             const u32 col = lo - q0, off = LDG(a.v.seq_off + lo), nk = LDG(a.v.seq_off + lo + 1) - off;
             if (wide) twice |= (atomicOr(seen + (col >> 5), 1u << (col & 31u)) >> (col & 31u) & 1u) != 0u;
             else if (col < 32u) seen_lo |= 1u << col; else seen_hi |= 1u << (col - 32u);
@@ -676,7 +698,8 @@ __global__ void __launch_bounds__(BF2_THREADS) k_blockfind2(long long n, BlockFi
 static inline void launch_blockfind2(Exec &ex, long long n, BlockFind2Args a) {
     if (n <= 0) return;
     PROF_BEGIN(ex, "k_blockfind2", 12.0 * n);
-    k_blockfind2<<<(unsigned)((n + BF2_THREADS - 1) / BF2_THREADS), BF2_THREADS, 0, ex.stream>>>(n, a);
+    if (a.mmax > BF2_COOP_M) k_blockfind2<true><<<(unsigned)((n + BF2_THREADS - 1) / BF2_THREADS), BF2_THREADS, 0, ex.stream>>>(n, a);
+    else k_blockfind2<false><<<(unsigned)((n + BF2_THREADS - 1) / BF2_THREADS), BF2_THREADS, 0, ex.stream>>>(n, a);
     PROF_END(ex);
     ex.launches++;
 }

@@ -341,6 +341,34 @@ def test_gpu_randomized_sweep_all_paths(gpu_finder, seed0):
         gpu_finder.debug_rounds(0)
 
 
+@pytest.mark.parametrize("m,n,nsets,seed,snp", [
+    (100, 500, 2, 2, 0.01), (200, 400, 1, 3, 0.01), (150, 300, 3, 12, 0.02),   # short, nearly identical: ties left to the doubling rounds
+    (33, 3000, 3, 1, 0.04), (64, 4000, 2, 5, 0.02), (65, 4000, 2, 6, 0.02), (100, 2500, 2, 2, 0.04), (128, 3000, 1, 7, 0.03),
+    (200, 2000, 1, 3, 0.04), (256, 5000, 2, 8, 0.02), (257, 3000, 1, 9, 0.03), (300, 2000, 1, 10, 0.04), (256, 16500, 1, 11, 0.01)])
+def test_gpu_sets_of_hundreds_of_sequences(gpu_finder, m, n, nsets, seed, snp):
+    """sets of 33 .. 300 near-identical sequences: the carried word sort with a CTA per root (k_cywalk_cta), roots ordered
+    word by word (k_wsort_words, both CTA sizes), blocks straight from the LCP array up to 256 sequences (k_blockfind2's
+    cooperative path) and through the cover array beyond -- free choice, forced carried sort and forced plain word sort
+    leave the suffix array, LCP array and rotations of the doubling rounds; the smaller cases are checked against the oracle"""
+    from csa_b200.workloads import make_batch
+    b = make_batch(nsets=nsets, m=m, n=n, snp=snp, indel=snp / 10, seed=seed, population=True)
+    out = {}
+    try:
+        for mode in (5, 0, 10, 6):
+            gpu_finder.debug_rounds(mode)
+            res = gpu_finder.find_rotations_batch(b)
+            out[mode] = (res,) + tuple(gpu_finder.suffix_array())
+    finally:
+        gpu_finder.debug_rounds(0)
+    for mode in (0, 10, 6):
+        assert np.array_equal(out[5][1], out[mode][1]) and np.array_equal(out[5][2], out[mode][2]), mode
+        for x, y in zip(out[5][0], out[mode][0]):
+            assert np.array_equal(x.rotations, y.rotations) and np.array_equal(x.positions, y.positions), mode
+    if m * n < 400000:
+        for i, (r, seqs) in enumerate(zip(out[0][0], batch_sets(b))):
+            compare_with_oracle(r, oracle_run(seqs), seqs, f"m={m} set {i}")
+
+
 def test_gpu_one_process_several_gpus():
     """csa_gpu_multi_*: one process, one host thread per GPU, bucket exchange by peer copies; needs two GPUs
     (skipped on a one-GPU box; tests/test_emu_pipeline.py covers the logic on the CPU single-stepper)"""
