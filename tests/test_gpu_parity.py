@@ -459,3 +459,45 @@ def test_gpu_full_size_against_the_oracle(gpu_finder, name):
         gpu_finder.upload(batch)
         run_bucket_sharded(gpu_finder, 0, 1, cuda=True, flags=1)
         check("bucket entry points, one rank")
+
+
+def gen_hundreds(rng):
+    """a set of 33 .. 300 variants of one ancestor: ACGT, a two-letter alphabet (groups of thousands) or with IUPAC letters
+    (the word sort's mask plane), equal or ragged lengths, randomly rotated, identical rotations dropped"""
+    from common import drop_rotation_duplicates, mutate
+    kind = rng.choice(["acgt", "acgt", "binary", "iupac", "ragged"])
+    alphabet = "AC" if kind == "binary" else "ACGT"
+    m = rng.choice([rng.randint(33, 70), rng.randint(70, 140), rng.randint(140, 300)])
+    n = rng.choice([rng.randint(20, 120), rng.randint(120, 600), rng.randint(600, 2500)])
+    base = [rng.choice(alphabet) for _ in range(n)]
+    snp, indel = rng.choice([0.002, 0.01, 0.03, 0.1]), rng.choice([0.0, 0.002, 0.01])
+    out = []
+    for _ in range(m):
+        s = mutate(rng, base[:rng.randint(max(2, n // 2), n)] if kind == "ragged" else base, snp, indel, alphabet)
+        if kind == "iupac":
+            for _ in range(rng.randint(0, 3)):
+                if s:
+                    s[rng.randrange(len(s))] = rng.choice("NRYKM")
+        if len(s) < 2:
+            s = s + ["A", "C"]
+        r = rng.randrange(len(s))
+        out.append("".join(s[r:] + s[:r]).encode())
+    out = drop_rotation_duplicates(out)
+    return out if len(out) >= 2 else gen_hundreds(rng)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_gpu_randomized_sweep_sets_of_hundreds(gpu_finder, seed):
+    """seeded sets of 33 .. 300 sequences, batches of 24 sets of mixed sizes, through the free choice, the forced carried word
+    sort (packed and unpacked group table) and the forced plain word sort: every result equals the oracle's"""
+    rng = random.Random(7000 + seed)
+    cases = [gen_hundreds(rng) for _ in range(24)]
+    oras = [oracle_run(s) for s in cases]
+    try:
+        for mode in (0, 10, 12, 6):
+            gpu_finder.debug_rounds(mode)
+            res = gpu_finder.find_rotations_batch(cases, flags=1 if mode == 0 else 0)
+            for i, (r, o, s) in enumerate(zip(res, oras, cases)):
+                compare_with_oracle(r, o, s, f"seed {seed} mode {mode} case {i} ({len(s)} sequences)")
+    finally:
+        gpu_finder.debug_rounds(0)
