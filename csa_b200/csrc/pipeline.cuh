@@ -2648,6 +2648,7 @@ struct WSortArgs {
     u32 *roots2, *nroots2;
     u32 big_min;               // (k_wsort_big) entries of big of up to big_min suffixes are k_wsort_words' (0: none)
     u32 list_cap;              // (k_wsort_list) groups of more suffixes than this go to big (0: WS_CAP, what a warp holds)
+    u32 words_small;           // (k_wsort_list, ACGT only) groups of up to 32 suffixes word by word too (ws_words_warp)
 };
 HD const u32 *ws_head_in(const WSortArgs &a) { return a.head_in ? a.head_in : a.head; }
 HD bool ws_taken(const WSortArgs &a, u32 start) { return !a.flag || a.flag[start] == a.want; }
@@ -2780,15 +2781,15 @@ HD bool cy_big(const u32 *h, u32 hs, u32 hi, u32 maxg) { return (u64)hs + maxg <
 HD void cygrp_body(long long i, const CarryArgs &a) {
     const u32 x = a.lo + (u32)i, hs = a.head[x] & 0x7FFFFFFFu;
     a.head2[x] = hs;
-    const bool big = cy_big(a.head, hs, a.hi, a.maxg);
-    u32 val = (big || cy_single(a.head, x, hs, a.hi)) ? CY_UNSET : hs;
+    const bool big = cy_big(a.head, hs, a.hi, a.maxg), single = cy_single(a.head, x, hs, a.hi);
+    u32 val = (big || single) ? CY_UNSET : hs;
     if (a.pack && val != CY_UNSET) {
         u32 e = x + 1;
         while (e < a.hi && (a.head[e] & 0x7FFFFFFFu) == hs) e++; // (at most 31 steps: the group holds no more than 32; pack only with maxg == CY_MAXG)
         val = (hs << 5) | (e - hs - 1u);
     }
     if (a.gval) a.gval[i] = val; else a.grp[a.sa[x]] = val;
-    a.flag[x] = (big && hs == x) ? 1 : 0;
+    a.flag[x] = (hs != x || single) ? 3 : big ? 1 : 0; // 3: no first place of a group of two or more (k_cylist reads the flags alone there)
 }
 #ifdef CSA_EMU
 MAP_KERNEL(cygrp, CarryArgs, 17)
@@ -2812,7 +2813,7 @@ __global__ void __launch_bounds__(256) k_cygrp(long long n, CarryArgs a) {
     u32 val = (big || single) ? CY_UNSET : hs;
     if (a.pack && val != CY_UNSET) val = (hs << 5) | (e - hs - 1u);
     if (a.gval) a.gval[i] = val; else a.grp[a.sa[x]] = val;
-    a.flag[x] = (big && hs == x) ? 1 : 0;
+    a.flag[x] = (hs != x || single) ? 3 : big ? 1 : 0; // 3: no first place of a group of two or more (k_cylist reads the flags alone there)
 }
 HD void cygrp_any_body(long long i, const CarryArgs &a) { cygrp_body(i, a); }
 MAP_KERNEL(cygrp_any, CarryArgs, 17) // (groups of up to CY_BIGG: the group's end is not among the 64 places of two ballots)
@@ -2873,7 +2874,8 @@ static inline void launch_cyroots(Exec &ex, long long n, CarryArgs a) {
 struct CyListArgs { const u32 *head2; const unsigned char *flag; u32 want; u32 lo, hi; u64 *list; u32 *count; };
 HD void cylist_body(long long i, const CyListArgs &a) {
     const u32 x = a.lo + (u32)i;
-    if (a.head2[x] != x || a.flag[x] != a.want || cy_single(a.head2, x, x, a.hi)) return;
+    if (a.flag[x] != a.want) return; // (first places of groups of two or more only: k_cygrp marks all others)
+    if (a.head2[x] != x || cy_single(a.head2, x, x, a.hi)) return;
     u64 e = (u64)x + 2;
     while (e < a.hi && e < (u64)x + CY_MAXG && a.head2[e] == x) e++;
     if (e < a.hi && a.head2[e] == x) { // longer than a warp: gallop, then bisect
@@ -2885,7 +2887,38 @@ HD void cylist_body(long long i, const CyListArgs &a) {
     }
     a.list[ATOMIC_ADD(a.count, 1u)] = ((u64)x << 32) | (u32)(e - x);
 }
-MAP_KERNEL(cylist, CyListArgs, 5)
+#ifdef CSA_EMU
+MAP_KERNEL(cylist, CyListArgs, 1)
+#else
+// the same, 16 places a thread: the flags are read as one 16-byte word, and almost none of them is wanted (a thread a place
+// is 400 000 CTAs that read one byte each and leave: the launch rate, not the 100 MB, set the 0.26 ms)
+__global__ void __launch_bounds__(256) k_cylist(long long nthreads, CyListArgs a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    const u64 x0 = (u64)(a.lo & ~15u) + 16ull * (u64)t;
+    const uint4 f = *reinterpret_cast<const uint4 *>(a.flag + x0); // (the flags of a batch: a 256-byte aligned buffer of its own, padded)
+    const u32 w[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        // bytes equal to want: x ^ want*0x01010101 has a zero byte there
+        const u32 v = w[q] ^ (a.want * 0x01010101u);
+        if (((v - 0x01010101u) & ~v & 0x80808080u) == 0u) continue; // no zero byte
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const u64 x = x0 + 4u * q + b;
+            if (((v >> (8 * b)) & 0xFFu) == 0u && x >= a.lo && x < a.hi) cylist_body((long long)(x - a.lo), a);
+        }
+    }
+}
+static inline void launch_cylist(Exec &ex, long long n, CyListArgs a) {
+    if (n <= 0) return;
+    const long long nthreads = ((long long)a.hi - (long long)(a.lo & ~15u) + 15) / 16;
+    PROF_BEGIN(ex, "k_cylist", 1.0 * n);
+    k_cylist<<<(unsigned)((nthreads + 255) / 256), 256, 0, ex.stream>>>(nthreads, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
 
 struct CyWalkArgs {
     BatchView v; u32 *sa; u32 *head; u32 *lcp; const u32 *head2; const u32 *grp; int pack; unsigned char *flag;
@@ -3583,6 +3616,78 @@ __global__ void __launch_bounds__(WSW_THREADS) k_wsort_words(WSortArgs a) {
     }
 }
 
+// k_wsort_words for a group of up to 32 suffixes and ONE warp: a lane per suffix, the barriers are warp barriers, the
+// borders one word.  s_key: 32 u64, s_flag: 32 u32, s_bits: one u32 (slices of the warp's WsSmem).
+template <bool ROOTS>
+__device__ __forceinline__ void ws_words_warp(const WSortArgs &a, u64 *s_key, u32 *s_flag, u32 *s_bits, const u32 lane,
+                                              const u32 start, const u32 g, const u32 Lmax) {
+    const bool have = lane < g;
+    u64 x = 0;
+    u32 suf = 0;
+    if (have) {
+        suf = a.sa[start + lane];
+        const u32 k = seq_of_few(a.v, suf);
+        x = LDG(a.v.dbl_off + k) + (suf - LDG(a.v.seq_off + k));
+    }
+    u32 pos = lane, sub = have ? 0u : lane, end = have ? g : lane + 1u;
+    u32 L = a.L0;
+    u64 knext = (have && L + 32u <= Lmax) ? lexkey2(fetch2(a.v.p2, x + L)) : 0ull;
+    bool ties = false;
+    for (;; L += 32u) {
+        const bool active = end - sub >= 2u;
+        if (L + 32u > Lmax) { ties = __any_sync(0xffffffffu, active) != 0; break; }
+        const u64 k = knext;
+        if (active && L + 64u <= Lmax) knext = lexkey2(fetch2(a.v.p2, x + L + 32u));
+        if (active) s_key[pos] = k;
+        s_flag[pos] = 0u;
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, active)) break;
+        const bool nonuni = active && s_key[sub] != k;
+        const bool anysplit = __any_sync(0xffffffffu, nonuni) != 0;
+        __syncwarp();
+        if (!anysplit) continue;
+        if (nonuni) s_flag[sub] = 1u;
+        if (lane == 0) *s_bits = 0u;
+        __syncwarp();
+        const bool split = active && s_flag[sub] != 0u;
+        u32 np = pos;
+        if (split) {
+            u32 c = 0;
+            for (u32 q = sub; q < end; q++) { const u64 kq = s_key[q]; c += (kq < k || (kq == k && q < pos)) ? 1u : 0u; }
+            np = sub + c;
+        }
+        __syncwarp();
+        pos = np;
+        if (split) s_key[pos] = k;
+        __syncwarp();
+        bool isstart = pos == sub;
+        if (split && pos != sub) {
+            const u64 kp = s_key[pos - 1u];
+            if (kp != k) { isstart = true; a.lcp[start + pos] = L + ((u32)__clzll((long long)(kp ^ k)) >> 1); }
+        }
+        if (isstart) atomicOr(s_bits, 1u << pos);
+        __syncwarp();
+        {
+            const u32 b = *s_bits;
+            sub = 31u - (u32)__clz((int)(b & (0xFFFFFFFFu >> (31u - pos))));
+            const u32 e = b & (pos < 31u ? 0xFFFFFFFFu << (pos + 1u) : 0u);
+            end = e ? (u32)__ffs((int)e) - 1u : 32u;
+        }
+        __syncwarp();
+    }
+    if (have) {
+        a.sa[start + pos] = suf;
+        a.head[start + pos] = start + sub;
+        if (pos == sub && end - sub >= 2u) {
+            a.left[atomicAdd(a.res + 0, 1u)] = ((u64)(start + sub) << 32) | (end - sub);
+            atomicAdd(a.res + 1, end - sub);
+            atomicMin(a.res + 2, L);
+            atomicMax(a.res + 3, end - sub);
+        }
+    }
+    if (ROOTS && a.roots && lane == 0 && !ties && g <= a.maxg) a.roots[atomicAdd(a.nroots, 1u)] = start; // (g <= 32 = CY_MAXG)
+}
+
 // the groups of a list (k_cylist), one warp a group, the warps fetching entries until the list is done
 template <bool MASKS>
 __global__ void __launch_bounds__(WSL_WARPS * 32) k_wsort_list(WSortArgs a, const u64 *list, const u32 *count, u32 *next) {
@@ -3598,6 +3703,12 @@ __global__ void __launch_bounds__(WSL_WARPS * 32) k_wsort_list(WSortArgs a, cons
         const u64 desc = list[i];
         const u32 start = (u32)(desc >> 32), size = (u32)desc;
         if (size > (a.list_cap ? a.list_cap : (u32)WS_CAP)) { if (lane == 0) a.big[atomicAdd(a.res + 5, 1u)] = desc; continue; }
+        if (!MASKS && a.words_small && size <= 32u) {
+            const u32 nm = LDG(a.v.seq_nmin + seq_of_few(a.v, a.sa[start])); // a group never leaves its set
+            ws_words_warp<true>(a, s.x, s.ct, s.best, lane, start, size, nm < a.depth_cap ? nm : a.depth_cap);
+            __syncwarp();
+            continue;
+        }
         bool act[WS_T];
         u32 nmin = 0xFFFFFFFFu;
 #pragma unroll
