@@ -239,6 +239,7 @@ static inline int exec_sync(Exec &ex) {
         (void)ex;                                                       \
         for (long long i = 0; i < n; i++) name##_body(i, a);            \
     }
+#define MAP_KERNEL_N(name, Args, BYTES_PER_ITEM) MAP_KERNEL(name, Args, BYTES_PER_ITEM)
 #else
 #define MAP_KERNEL(name, Args, BYTES_PER_ITEM)                                            \
     __global__ void __launch_bounds__(256) k_##name(long long n, Args a) {                \
@@ -249,6 +250,24 @@ static inline int exec_sync(Exec &ex) {
         if (n <= 0) return;                                                               \
         PROF_BEGIN(ex, "k_" #name, (double)n * (BYTES_PER_ITEM));                         \
         k_##name<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);               \
+        PROF_END(ex);                                                                     \
+        ex.launches++;                                                                    \
+    }
+// The same with MAP_ITEMS elements a thread (a CTA's threads side by side on each), for the LIGHT kernels over all suffixes of
+// a batch: a thread an element is 400 000 CTAs for 10^8 suffixes, and the rate at which CTAs start (~1.5 per ns) then bounds
+// the kernel at ~0.26 ms whatever it reads (k_initkey 0.48 -> 0.38 ms = 0.81 of the copy peak).  Not for kernels whose
+// elements are few and heavy (a block, a set): they lose their parallelism.
+#define MAP_ITEMS 4
+#define MAP_KERNEL_N(name, Args, BYTES_PER_ITEM)                                          \
+    __global__ void __launch_bounds__(256) k_##name(long long n, Args a) {                \
+        long long i = (long long)blockIdx.x * (256 * MAP_ITEMS) + threadIdx.x;            \
+        _Pragma("unroll 1")                                                               \
+        for (int j = 0; j < MAP_ITEMS && i < n; j++, i += 256) name##_body(i, a);         \
+    }                                                                                     \
+    static inline void launch_##name(Exec &ex, long long n, Args a) {                     \
+        if (n <= 0) return;                                                               \
+        PROF_BEGIN(ex, "k_" #name, (double)n * (BYTES_PER_ITEM));                         \
+        k_##name<<<(unsigned)((n + 256 * MAP_ITEMS - 1) / (256 * MAP_ITEMS)), 256, 0, ex.stream>>>(n, a); \
         PROF_END(ex);                                                                     \
         ex.launches++;                                                                    \
     }

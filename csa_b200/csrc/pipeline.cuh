@@ -94,7 +94,7 @@ HD void encode_body(long long i, const EncodeArgs &a) {
     a.v.seqof[g] = k;
 }
 #ifdef CSA_EMU
-MAP_KERNEL(encode, EncodeArgs, 6)
+MAP_KERNEL_N(encode, EncodeArgs, 6)
 #else
 // 16 bases per thread: one 16-byte load, one search for the sequence of the first base (the others follow
 // by comparing with the next border), 16 + 64 bytes stored as five 16-byte words
@@ -226,7 +226,7 @@ HD void initkey_body(long long i, const InitKeyArgs &a) {
     }
     if (a.vals) a.vals[g] = g; // (the first pass of the first sort makes up the suffix numbers itself)
 }
-MAP_KERNEL(initkey, InitKeyArgs, 21)
+MAP_KERNEL_N(initkey, InitKeyArgs, 21)
 
 // head[i] = i where a new group of equal keys starts, else 0 (max-scanned afterwards)
 // With lcp != nullptr (first sort only) a border also gets its LCP: the letters the two keys share.
@@ -261,20 +261,27 @@ MAP_KERNEL(flag, FlagArgs, 12)
 #else
 // one atomic per CTA: same-address atomics serialise in L2 (one per warp cost 0.5 ms per launch)
 __global__ void __launch_bounds__(256) k_flag(long long n, FlagArgs a) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool f = false;
-    if (i < n) {
-        f = (i == 0) || flag_differs(a, i);
+    long long i = (long long)blockIdx.x * (256 * MAP_ITEMS) + threadIdx.x;
+    int mine = 0;
+#pragma unroll 1
+    for (int j = 0; j < MAP_ITEMS && i < n; j++, i += 256) {
+        const bool f = (i == 0) || flag_differs(a, i);
         a.head[i] = f ? a.base + (u32)i : 0u;
         if (f && a.lcp) flag_lcp(a, i);
+        mine += f ? 1 : 0;
     }
-    int c = __syncthreads_count(f);
-    if (threadIdx.x == 0 && c) atomicAdd(a.ngroups, (u32)c);
+    __shared__ int s_c;
+    if (threadIdx.x == 0) s_c = 0;
+    __syncthreads();
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_c, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_c) atomicAdd(a.ngroups, (u32)s_c);
 }
 static inline void launch_flag(Exec &ex, long long n, FlagArgs a) {
     if (n <= 0) return;
     PROF_BEGIN(ex, "k_flag", 12.0 * n);
-    k_flag<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    k_flag<<<(unsigned)((n + 256 * MAP_ITEMS - 1) / (256 * MAP_ITEMS)), 256, 0, ex.stream>>>(n, a);
     PROF_END(ex);
     ex.launches++;
 }
@@ -292,7 +299,7 @@ MAP_KERNEL(setstart, SetStartArgs, 8)
 
 struct SetRankArgs { const u32 *sa; const u32 *head; u32 *rank; };
 HD void setrank_body(long long i, const SetRankArgs &a) { a.rank[a.sa[i]] = a.head[i]; }
-MAP_KERNEL(setrank, SetRankArgs, 12)
+MAP_KERNEL_N(setrank, SetRankArgs, 12)
 
 // key of the doubling round: (rank of the first h letters, rank of the next h letters)
 struct Key2Args { BatchView v; const u32 *sa; const u32 *rank; u64 *keys; u32 h; int nbits; };
@@ -314,7 +321,7 @@ MAP_KERNEL(key2, Key2Args, 24)
 #define LCP_CHUNK 32
 struct IsaArgs { const u32 *sa; u32 *isa; };
 HD void isa_body(long long i, const IsaArgs &a) { a.isa[a.sa[i]] = (u32)i; }
-MAP_KERNEL(isa, IsaArgs, 12)
+MAP_KERNEL_N(isa, IsaArgs, 12)
 
 struct LcpArgs { BatchView v; const u32 *sa; const u32 *isa; u32 *lcp; const u32 *any_other; };
 HD void lcp_body(long long t, const LcpArgs &a) {
@@ -718,7 +725,7 @@ HD void blockemit_body(long long i, const BlockEmitArgs &a) {
     a.blk_depth[b] = a.depth[i];
     a.blk_set[b] = s;
 }
-MAP_KERNEL(blockemit, BlockEmitArgs, 8)
+MAP_KERNEL_N(blockemit, BlockEmitArgs, 8)
 // blocks per set, from the running count (one thread per set): the one number the host waits for before the emit
 struct SetCountArgs { BatchView v; const u32 *isblock; const u32 *bidx; u32 *set_nblocks; };
 HD void setcount_body(long long s, const SetCountArgs &a) {
@@ -1698,11 +1705,24 @@ __global__ void __launch_bounds__(256) k_maxgroup(long long n, MaxGroupArgs a) {
     // a persistent grid: every thread folds many places (neighbouring lanes read neighbouring words)
     u32 sz = 0, sh = 0, wk = 0, wk2 = 0;
     unsigned long long pr = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        if ((u32)i + 1 == a.N || (a.head[i + 1] & 0x7FFFFFFFu) == (u32)i + 1) {
-            const u32 z = (u32)i - (a.head[i] & 0x7FFFFFFFu) + 1;
-            sz = z > sz ? z : sz;
-            if (z > 1) { pr += (unsigned long long)z * (z - 1) / 2; sh += z; if (z <= 32u) wk += z; if (z <= 256u) wk2 += z; }
+    // (four places a round, their heads loaded before any is looked at: the loads of a round are in flight together)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        u32 hn[4], hc[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const long long i = i0 + q * stride;
+            hn[q] = (i < n && (u32)i + 1 != a.N) ? a.head[i + 1] & 0x7FFFFFFFu : 0xFFFFFFFFu;
+            hc[q] = i < n ? a.head[i] & 0x7FFFFFFFu : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const long long i = i0 + q * stride;
+            if (i < n && ((u32)i + 1 == a.N || hn[q] == (u32)i + 1)) {
+                const u32 z = (u32)i - hc[q] + 1;
+                sz = z > sz ? z : sz;
+                if (z > 1) { pr += (unsigned long long)z * (z - 1) / 2; sh += z; if (z <= 32u) wk += z; if (z <= 256u) wk2 += z; }
+            }
         }
     }
     if (a.pairs) { // one atomic per CTA: same-address atomics serialise in L2
@@ -2796,8 +2816,11 @@ MAP_KERNEL(cygrp, CarryArgs, 17)
 #else
 // the same; a group's end from the borders of the warp's 32 places and the 32 behind them (two ballots), no walk along the heads
 __global__ void __launch_bounds__(256) k_cygrp(long long n, CarryArgs a) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 lane = threadIdx.x & 31u;
+#pragma unroll 1
+    for (int j = 0; j < MAP_ITEMS; j++) { // (MAP_ITEMS stretches of 256 places a CTA: see MAP_KERNEL_N)
+    const long long i = (long long)blockIdx.x * (256 * MAP_ITEMS) + 256 * j + threadIdx.x;
+    if (i - lane >= n) break; // (the whole warp at once: the ballots below are the warp's)
     const bool in = i < n;
     const u64 x64 = (u64)a.lo + (u64)(in ? i : 0), y64 = x64 + 32u;
     const u32 x = (u32)x64;
@@ -2805,7 +2828,7 @@ __global__ void __launch_bounds__(256) k_cygrp(long long n, CarryArgs a) {
     const u32 hy = (in && y64 < a.hi) ? a.head[y64] & 0x7FFFFFFFu : 0u;
     // border bits: place p starts a group (the end of the range counts as one)
     const u64 b = (u64)__ballot_sync(0xffffffffu, !in || hs == x) | ((u64)__ballot_sync(0xffffffffu, !in || y64 >= a.hi || hy == (u32)y64) << 32);
-    if (!in) return;
+    if (!in) continue;
     a.head2[x] = hs;
     const u64 above = b & (~0ull << (lane + 1u));
     const u32 e = above ? x - lane + (u32)(__ffsll((long long)above) - 1) : x - lane + 64u; // first border behind x (at most 63 places on)
@@ -2814,6 +2837,7 @@ __global__ void __launch_bounds__(256) k_cygrp(long long n, CarryArgs a) {
     if (a.pack && val != CY_UNSET) val = (hs << 5) | (e - hs - 1u);
     if (a.gval) a.gval[i] = val; else a.grp[a.sa[x]] = val;
     a.flag[x] = (hs != x || single) ? 3 : big ? 1 : 0; // 3: no first place of a group of two or more (k_cylist reads the flags alone there)
+    }
 }
 HD void cygrp_any_body(long long i, const CarryArgs &a) { cygrp_body(i, a); }
 MAP_KERNEL(cygrp_any, CarryArgs, 17) // (groups of up to CY_BIGG: the group's end is not among the 64 places of two ballots)
@@ -2821,14 +2845,14 @@ static inline void launch_cygrp(Exec &ex, long long n, CarryArgs a) {
     if (n <= 0) return;
     if (a.maxg != CY_MAXG) { launch_cygrp_any(ex, n, a); return; }
     PROF_BEGIN(ex, "k_cygrp", 17.0 * n);
-    k_cygrp<<<(unsigned)((n + 255) / 256), 256, 0, ex.stream>>>(n, a);
+    k_cygrp<<<(unsigned)((n + 256 * MAP_ITEMS - 1) / (256 * MAP_ITEMS)), 256, 0, ex.stream>>>(n, a);
     PROF_END(ex);
     ex.launches++;
 }
 #endif
 struct CyScatterArgs { const u32 *suffix; const u32 *val; u32 *grp; };
 HD void cyscatter_body(long long i, const CyScatterArgs &a) { a.grp[a.suffix[i]] = a.val[i]; }
-MAP_KERNEL(cyscatter, CyScatterArgs, 12)
+MAP_KERNEL_N(cyscatter, CyScatterArgs, 12)
 // the group (first place) of the suffix one letter back round its sequence; *cut: the suffix stands at a multiple of CY_CUT
 HD u32 cy_parent(const CarryArgs &a, u32 s, bool *cut) {
     const u32 k = seq_of_few(a.v, s), st = LDG(a.v.seq_off + k), off = s - st;

@@ -31,7 +31,28 @@ HD void leafscan_body(long long i0, const LeafScanArgs &a) {
     if ((u32)i == LDG(a.v.set_base0 + s)) return;     // the first place of a set has no left neighbour
     if (l >= LDG(a.v.set_nmin + s)) ATOMIC_OR(a.set_flags + s, CSA_FLAG_RARE);
 }
+#ifdef CSA_EMU
 MAP_KERNEL(leafscan, LeafScanArgs, 4)
+#else
+// four places a thread, their LCPs in one 16-byte load (a 4-byte stream a thread ran at 2 TB/s); almost no place passes
+__global__ void __launch_bounds__(256) k_leafscan(long long n, LeafScanArgs a) {
+    const long long i0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i0 >= n) return;
+    if (i0 + 4 <= n && ((a.off + (u32)i0) & 3u) == 0u) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(a.lcp + a.off + i0);
+        const u32 l[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (l[q] >= a.batch_nmin && l[q] != 0xFFFFFFFFu) leafscan_body(i0 + q, a);
+    } else for (long long i = i0; i < n && i < i0 + 4; i++) leafscan_body(i, a);
+}
+static inline void launch_leafscan(Exec &ex, long long n, LeafScanArgs a) {
+    if (n <= 0) return;
+    PROF_BEGIN(ex, "k_leafscan", 4.0 * n);
+    k_leafscan<<<(unsigned)((n + 1023) / 1024), 256, 0, ex.stream>>>(n, a);
+    PROF_END(ex);
+    ex.launches++;
+}
+#endif
 
 HD u32 rare_seq_len(const BatchView &v, u32 k) { return LDG(v.seq_off + k + 1) - LDG(v.seq_off + k); }
 
