@@ -805,15 +805,21 @@ __global__ void __launch_bounds__(CS_THREADS) k_seq0compact(long long n, Seq0Com
     u32 s = s_set;
     u32 g[CS_ITEMS], sset[CS_ITEMS];
     u32 cnt = 0, flags = 0;
+    // (the set's tables are read again only where a thread's places cross into the next set, not for every place)
+    u32 nextb = s + 1 < (u32)a.v.nsets ? LDG(a.v.set_base0 + s + 1) : 0xFFFFFFFFu;
+    u32 k0 = LDG(a.v.set_seq0 + s), off = LDG(a.v.seq_off + k0), offe = LDG(a.v.seq_off + k0 + 1);
 #pragma unroll
     for (int j = 0; j < CS_ITEMS; j++) {
         const long long i = base + j;
         g[j] = 0; sset[j] = 0;
         if (i < n) {
-            while (s + 1 < (u32)a.v.nsets && (u32)i + a.off >= LDG(a.v.set_base0 + s + 1)) s++;
-            const u32 k0 = LDG(a.v.set_seq0 + s), off = LDG(a.v.seq_off + k0);
+            if ((u32)i + a.off >= nextb) {
+                while (s + 1 < (u32)a.v.nsets && (u32)i + a.off >= LDG(a.v.set_base0 + s + 1)) s++;
+                nextb = s + 1 < (u32)a.v.nsets ? LDG(a.v.set_base0 + s + 1) : 0xFFFFFFFFu;
+                k0 = LDG(a.v.set_seq0 + s); off = LDG(a.v.seq_off + k0); offe = LDG(a.v.seq_off + k0 + 1);
+            }
             const u32 x = a.sa[i + a.off];
-            if (x >= off && x < LDG(a.v.seq_off + k0 + 1)) { flags |= 1u << j; cnt++; g[j] = x - off; sset[j] = s; }
+            if (x >= off && x < offe) { flags |= 1u << j; cnt++; g[j] = x - off; sset[j] = s; }
         }
     }
     u32 total;
