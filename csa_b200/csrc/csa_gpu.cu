@@ -592,7 +592,10 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
                 static const bool direct = getenv("CSA_GPU_CYGRP_DIRECT") != nullptr; // (experiments)
                 const bool dealt = !direct && (c->carry_mode == 1 || c->max_set_bases > WS_LARGE_SET) && hi - lo > 1; // (sets of a few MB: their stretch of grp sits in L2 anyway)
                 const int pack = (N < (1u << 27) && !c->cy_nopack && !cybig) ? 1 : 0;
-                CarryArgs ca{v, P<u32>(c->valsA), head, head2, grp, flag, lo, hi, pack, dealt ? P<u32>(c->valsB) : nullptr, cybig ? CY_BIGG : CY_MAXG};
+                u32 *startbits = P<u32>(c->keysB) + ((size_t)N + 3) / 4 + 4; // (behind the flags: N bits)
+                TRY(dev_zero(ex, startbits, sizeof(u32) * ((size_t)N / 32 + 1)));
+                { CySeqBitsArgs sb{v, startbits}; launch_cyseqbits(ex, (long long)c->M, sb); }
+                CarryArgs ca{v, P<u32>(c->valsA), head, head2, grp, flag, lo, hi, pack, dealt ? P<u32>(c->valsB) : nullptr, cybig ? CY_BIGG : CY_MAXG, startbits};
                 launch_cygrp(ex, (long long)hi - lo, ca);
                 if (dealt) {
                     u32 *k = P<u32>(c->valsA) + lo, *ka = P<u32>(c->sa), *vv = P<u32>(c->valsB), *va = P<u32>(c->t2);
