@@ -611,10 +611,8 @@ static int stage_suffix_array(csa_gpu_ctx *c, const BatchView &v, int phase = 0)
                 { CyListArgs l{head2, flag, 1u, lo, hi, list, nlistA}; launch_cylist(ex, (long long)hi - lo, l); }
                 a.head_in = head2; a.flag = flag; a.want = 1u; a.roots = roots; a.nroots = nroots;
                 a.maxg = ca.maxg; a.roots2 = roots2; a.nroots2 = nroots2;
-                static const u32 env_cap = getenv("CSA_GPU_LIST_CAP") ? (u32)atoi(getenv("CSA_GPU_LIST_CAP")) : 0u; // (experiments)
-                if (cybig && !any_other) a.list_cap = env_cap ? env_cap : CY_MAXG; // (ACGT only: longer roots word by word, k_wsort_words)
-                static const bool env_nowords = getenv("CSA_GPU_NO_WORDS_SMALL") != nullptr; // (experiments)
-                a.words_small = (!any_other && !env_nowords) ? 1u : 0u;
+                if (cybig && !any_other) a.list_cap = CY_MAXG; // (ACGT only: longer roots word by word, k_wsort_words; measured with 64 and 128: slower)
+                a.words_small = any_other ? 0u : 1u;           // (... and the shorter ones by a warp, ws_words_warp)
                 launch_wsort_list(ex, a, list, nlistA);
                 if (cybig) { // roots longer than a warp's window: one CTA each, BEFORE the walks (they start from these too)
                     TRY(d2h(ex, c->ws_left, res, sizeof(c->ws_left)));
