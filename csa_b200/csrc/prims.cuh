@@ -264,32 +264,35 @@ static int scan_u32(Exec &ex, PrimScratch &ps, const u32 *in, u32 *out, long lon
 static_assert(RS_TILE == RS_TILE_ELEMS, "tile size");
 #define RS_BITS 8
 #define RS_BINS 256
+#ifndef RS_HCOPIES
+#define RS_HCOPIES 2
+#endif
 
 template <class K>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const K *__restrict__ keys, u32 *__restrict__ counts,
                                                         long long n, int shift, RsSeg seg) {
-    __shared__ u32 h[RS_WARPS][RS_BINS];
-    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
+    // two copies of the counters (even and odd warps): a copy per warp cost more in zeroing and summing 2048 words a tile than
+    // it saved in colliding atomics
+    __shared__ u32 h[RS_HCOPIES][RS_BINS];
+    for (int i = threadIdx.x; i < RS_HCOPIES * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long start = seg.blk_start ? (long long)seg.blk_start[blockIdx.x] : (long long)blockIdx.x * RS_TILE;
     const long long end = seg.blk_start ? start + seg.blk_count[blockIdx.x] : (start + RS_TILE < n ? start + RS_TILE : n);
     long long base = start + (long long)warp * (RS_ITEMS * 32) + lane;
+    K k[RS_ITEMS];
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; j++) {
-        long long i = base + j * 32;
-        if (i < end) {
-            unsigned d = (unsigned)(keys[i] >> shift) & (RS_BINS - 1);
-            atomicAdd(&h[warp][d], 1u);
-        }
-    }
+    for (int j = 0; j < RS_ITEMS; j++) { const long long i = base + j * 32; k[j] = i < end ? keys[i] : (K)0; } // (all loads in flight before the first atomic)
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++)
+        if (base + j * 32 < end) atomicAdd(&h[warp % RS_HCOPIES][(unsigned)(k[j] >> shift) & (RS_BINS - 1)], 1u);
     __syncthreads();
     const size_t cbase = seg.blk_start ? seg.blk_cbase[blockIdx.x] : blockIdx.x;
     const size_t stride = seg.blk_start ? seg.blk_stride[blockIdx.x] : seg.nblocks;
     for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
         u32 s = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) s += h[w][d];
+        for (int w = 0; w < RS_HCOPIES; w++) s += h[w][d];
         counts[cbase + (size_t)d * stride] = s;
     }
 }
