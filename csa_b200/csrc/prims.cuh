@@ -306,8 +306,6 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_scatter(const K *__restric
     __shared__ K s_keys[RS_TILE];
     __shared__ u32 s_vals[RS_TILE];
     __shared__ u32 s_scan[33];
-    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
-    __syncthreads();
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const long long start = seg.blk_start ? (long long)seg.blk_start[blockIdx.x] : (long long)blockIdx.x * RS_TILE;
@@ -318,13 +316,20 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_scatter(const K *__restric
     u32 rank[RS_ITEMS];
     unsigned dig[RS_ITEMS];
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; j++) {
+    for (int j = 0; j < RS_ITEMS; j++) { // (the tile's loads are in flight while the counters are zeroed)
         long long i = base + j * 32;
         bool ok = i < end;
         k[j] = ok ? keys[i] : (K)0;
         v[j] = ok ? (vals ? vals[i] : (u32)i) : 0; // (vals == nullptr: the values are the places themselves, first pass of a sort)
-        dig[j] = ok ? ((unsigned)(k[j] >> shift) & (RS_BINS - 1)) : RS_BINS; // RS_BINS = "no key"
     }
+    const size_t cbase = seg.blk_start ? seg.blk_cbase[blockIdx.x] : blockIdx.x;
+    const size_t stride = seg.blk_start ? seg.blk_stride[blockIdx.x] : seg.nblocks;
+    const u32 goff = offsets[cbase + (size_t)threadIdx.x * stride]; // (where this tile's run of digit threadIdx.x starts in the output: asked for now, needed below)
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++)
+        dig[j] = base + j * 32 < end ? ((unsigned)(k[j] >> shift) & (RS_BINS - 1)) : RS_BINS; // RS_BINS = "no key"
 #pragma unroll
     for (int j = 0; j < RS_ITEMS; j++) {
         unsigned d = dig[j];
@@ -356,9 +361,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) k_rs_scatter(const K *__restric
     tstart[threadIdx.x] = dstart;
     // the element that ends up at place q of the sorted tile goes to out[gbase[d] + q - tstart[d]]:
     // fold both into one word so the write-out loop needs a single lookup
-    const size_t cbase = seg.blk_start ? seg.blk_cbase[blockIdx.x] : blockIdx.x;
-    const size_t stride = seg.blk_start ? seg.blk_stride[blockIdx.x] : seg.nblocks;
-    gdelta[threadIdx.x] = offsets[cbase + (size_t)threadIdx.x * stride] - dstart;
+    gdelta[threadIdx.x] = goff - dstart;
     __syncthreads();
     // stage the tile in digit order in shared memory ...
 #pragma unroll
