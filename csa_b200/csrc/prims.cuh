@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_scan_chain(const u32 *in, u32 *o
 template <class Op, bool INCLUSIVE>
 static int scan_u32(Exec &ex, PrimScratch &ps, const u32 *in, u32 *out, long long n, int level = 0) {
     if (n <= 0) return 0;
-    if (n >= (1ll << 20)) { // long arrays: one pass
+    if (n > 4 * SCAN_TILE) { // more than a few tiles: one pass (decoupled look-back), one launch instead of three
         long long nt = (n + CS_TILE - 1) / CS_TILE;
         int rc = dev_alloc(ps.chain, sizeof(unsigned long long) * (size_t)(nt + 1));
         if (rc) return rc;
