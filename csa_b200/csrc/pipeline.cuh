@@ -633,9 +633,11 @@ __global__ void __launch_bounds__(BF2_THREADS, 8) k_blockfind2(long long n, Bloc
         m = LDG(a.v.set_seq0 + s + 1) - LDG(a.v.set_seq0 + s);
         if (m >= 2 && lb + m <= s1) {
             const u32 rb = lb + m - 1;
-            const long long outer_l = (lb == s0) ? -1 : (long long)a.lcp[lb];
-            const long long outer_r = (rb + 1 == s1) ? -1 : (long long)a.lcp[rb + 1];
-            if (outer_l < (long long)a.lcp[lb + 1] && outer_r < (long long)a.lcp[rb]) {
+            // (the four LCPs at the window's two borders asked for together, not one after the other's test)
+            const u32 la = a.lcp[lb], lb1 = a.lcp[lb + 1], lr = a.lcp[rb], lr1 = (rb + 1 == s1) ? 0u : a.lcp[rb + 1];
+            const long long outer_l = (lb == s0) ? -1 : (long long)la;
+            const long long outer_r = (rb + 1 == s1) ? -1 : (long long)lr1;
+            if (outer_l < (long long)lb1 && outer_r < (long long)lr) {
                 const long long outer = outer_l > outer_r ? outer_l : outer_r;
                 outer1 = (u32)(outer + 1);
                 inner = 0xFFFFFFFFu;
