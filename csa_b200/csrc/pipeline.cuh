@@ -2788,9 +2788,12 @@ static inline void launch_bounds(Exec &ex, const BoundsArgs &a) { launch_bounds_
 //   k_cyroots  flag[first place] = 1 for the groups that must be ordered afresh: a predecessor in another group or
 //              in none, or its first suffix's number a multiple of CY_CUT (cuts the walks,
 //              so that ten thousand of them run side by side whatever the genomes share)
-//   k_wsort    (want = 1) orders the roots, lists those a walk can start from (<= 32 suffixes, no two still equal)
+//   k_cylist + k_wsort_list   (want = 1) orders the roots by letters -- word by word, a warp a group (ws_words_warp), when the
+//              batch is ACGT only, else pair by pair -- and lists those a walk can start from (no two suffixes still equal)
 //   k_cywalk   the walks; flag = 2 on every group written
-//   k_wsort    (want = 0) whatever no walk reached (descendants of roots with ties): as before, by letters
+//   k_cylist + k_wsort_list   (want = 0) whatever no walk reached (descendants of roots with ties): as before, by letters
+// Sets of hundreds of near-identical sequences (a.maxg == CY_BIGG): groups of up to 256 suffixes are walked too, a CTA a
+// root (k_cywalk_cta, a second list of roots); roots of more than 32 suffixes are ordered by k_wsort_words, a CTA a group.
 // Results are those of the word sort alone, place by place (tests: forced on every golden set; full-size agreement).
 #define CY_MAXG 32u   // suffixes a warp's walk carries
 #define CY_BIGG 256u  // ... a CTA's walk (k_cywalk_cta: sets of hundreds of near-identical sequences)
